@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Convert the reference's own test fixtures for the CI-test hot path into compact
+golden files that travel with this repo (the GPU box has no /root/reference).
+
+Sources (all data, no code), relative to /root/reference/test/data:
+  preprocessing_expected/{pres_abs,clr_nonzero_binned,clr_adapt,clr_nonzero}.tsv
+      -> the exact *inputs* of test/tests.jl and test/learning.jl for mi / mi_nz / fz / fz_nz
+  tests_expected.tsv            -> 204 golden TestResults (test/tests.jl:41-74)
+  learning_expected/*.edgelist  -> 8 expected graphs (test/learning.jl:176-237)
+
+Run once in the build container:  python tests/golden/make_golden.py
+Outputs: tests/golden/hmp_inputs.npz, tests/golden/tests_expected.json,
+         tests/golden/learning_expected.json
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get("FW_REFERENCE", "/root/reference")
+D = os.path.join(REF, "test", "data")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    pe = os.path.join(D, "preprocessing_expected")
+    inputs = {
+        "mi": np.loadtxt(os.path.join(pe, "pres_abs.tsv"), delimiter="\t").astype(np.int8),
+        "mi_nz": np.loadtxt(os.path.join(pe, "clr_nonzero_binned.tsv"), delimiter="\t").astype(np.int8),
+        # text holds Float32-rounded values; keep them as float32 (exact round trip)
+        "fz": np.loadtxt(os.path.join(pe, "clr_adapt.tsv"), delimiter="\t").astype(np.float32),
+        "fz_nz": np.loadtxt(os.path.join(pe, "clr_nonzero.tsv"), delimiter="\t").astype(np.float32),
+    }
+    for k, v in inputs.items():
+        assert v.shape == (346, 50), (k, v.shape)
+    np.savez_compressed(os.path.join(OUT, "hmp_inputs.npz"), **inputs)
+
+    exp = {}
+    with open(os.path.join(D, "tests_expected.tsv")) as f:
+        header = f.readline().rstrip("\n").split("\t")
+        assert header == ["key", "stat", "pval", "df", "suff_power"], header
+        for line in f:
+            key, stat, pval, df, sp = line.rstrip("\n").split("\t")
+            exp.setdefault(key, []).append([float(stat), float(pval), int(float(df)), sp.strip() == "true"])
+    assert sum(len(v) for v in exp.values()) == 204
+    with open(os.path.join(OUT, "tests_expected.json"), "w") as f:
+        json.dump(exp, f, indent=0)
+
+    graphs = {}
+    ld = os.path.join(D, "learning_expected")
+    for fn in sorted(os.listdir(ld)):
+        name = os.path.splitext(fn)[0]
+        edges = []
+        with open(os.path.join(ld, fn)) as f:
+            for line in f:
+                if line.startswith("#") or not line.strip():
+                    continue
+                a, b, w = line.rstrip("\n").split("\t")
+                a, b = int(a[1:]) - 1, int(b[1:]) - 1      # "X17" -> 0-based 16
+                edges.append([min(a, b), max(a, b), float(w)])
+        graphs[name] = sorted(edges)
+    with open(os.path.join(OUT, "learning_expected.json"), "w") as f:
+        json.dump(graphs, f, indent=0)
+    print("wrote", os.listdir(OUT))
+
+
+if __name__ == "__main__":
+    sys.exit(main())
