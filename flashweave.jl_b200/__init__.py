@@ -1,0 +1,449 @@
+"""flashweave.jl_b200 — host side of the B200 CI-test engine (ctypes over libfwgpu.so).
+
+Mirrors the reference's operator interface for the hot path (names, argument meaning and
+error behaviour), 0-based indices:
+
+    reference (Julia, 1-based)                          here
+    ---------------------------------------------------------------------------------
+    test(X, Y, Zs, data, test_obj, ...)   tests.jl:28-265    Engine.test / Engine.test_batch
+    test_subsets(X, Y, Z_total, ...)      tests.jl:281-346   Engine.test_subsets(_batch)
+    pw_univar_neighbors(data; ...)        tests.jl:436-532   Engine.pw_univar_neighbors
+    cor(data) -> Matrix{Float32}          learning.jl:42-44  Engine.cor
+    si_HITON_PC(T, data, ...)             hiton.jl:283-400   Engine.si_HITON_PC
+    LGL(data; parallel="single", ...)     learning.jl:203-279 Engine.LGL
+
+There is no CPU fallback: every compute entry point goes through libfwgpu.so and raises
+FwError when the library or a CUDA device is missing.  (The directory name contains a dot,
+so import it through `fwload.load()` at the repo root, which registers it as
+`flashweave_jl_b200`.)
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KINDS = {"mi": 0, "mi_nz": 1, "fz": 2, "fz_nz": 3}
+FW_OK = 0
+
+# every symbol include/fwgpu.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "fw_create", "fw_destroy", "fw_last_error", "fw_set_index_base", "fw_stream", "fw_synchronize", "fw_launch_count",
+    "fw_set_data_f32", "fw_set_data_i32", "fw_adopt_data_f32_device", "fw_set_n_obs", "fw_levels", "fw_cor_matrix",
+    "fw_set_cor_f32", "fw_adopt_cor_device", "fw_cor_device_ptr", "fw_test_batch", "fw_test_subsets", "fw_test_subsets_batch",
+    "fw_pairwise", "fw_pairwise_copy", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_capacity",
+    "fw_build_info",
+]
+
+
+class FwError(RuntimeError):
+    pass
+
+
+class TestResult(C.Structure):
+    """src/types.jl:140-145"""
+    _fields_ = [("stat", C.c_double), ("pval", C.c_double), ("df", C.c_int64),
+                ("suff_power", C.c_uint8), ("_pad", C.c_uint8 * 7)]
+
+    def astuple(self):
+        return (self.stat, self.pval, int(self.df), bool(self.suff_power))
+
+    def __repr__(self):
+        return "TestResult(stat=%r, pval=%r, df=%d, suff_power=%s)" % self.astuple()
+
+
+def lib_path():
+    return os.path.join(_HERE, "libfwgpu.so")
+
+
+def load_library():
+    """dlopen libfwgpu.so (built in-tree by flashweave.jl_b200/build.py). Fails loudly."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    so = lib_path()
+    if not os.path.exists(so):
+        raise FwError("libfwgpu.so is not built (%s missing); run `python __graft_entry__.py` or flashweave.jl_b200/build.py. "
+                      "There is no CPU fallback." % so)
+    L = C.CDLL(so)
+    i32, i64, dbl, vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
+    sig = {
+        "fw_create": (i32, [i32, C.POINTER(vp)]),
+        "fw_destroy": (i32, [vp]),
+        "fw_last_error": (C.c_char_p, [vp]),
+        "fw_set_index_base": (i32, [vp, i32]),
+        "fw_stream": (vp, [vp]),
+        "fw_synchronize": (i32, [vp]),
+        "fw_launch_count": (i64, [vp]),
+        "fw_set_data_f32": (i32, [vp, vp, i64, i64, i64]),
+        "fw_set_data_i32": (i32, [vp, vp, i64, i64, i64]),
+        "fw_adopt_data_f32_device": (i32, [vp, vp, i64, i64, i64]),
+        "fw_set_n_obs": (i32, [vp, i64]),
+        "fw_levels": (i32, [vp, vp, vp]),
+        "fw_cor_matrix": (i32, [vp, vp]),
+        "fw_set_cor_f32": (i32, [vp, vp, i64]),
+        "fw_adopt_cor_device": (i32, [vp, vp, i64]),
+        "fw_cor_device_ptr": (vp, [vp]),
+        "fw_test_batch": (i32, [vp, i32, i64, vp, vp, vp, vp, i64, i64, vp]),
+        "fw_test_subsets": (i32, [vp, i32, i64, i64, vp, i64, i32, dbl, i64, i64, i64, vp, vp, vp, vp, vp]),
+        "fw_test_subsets_batch": (i32, [vp, i32, i64, vp, vp, vp, vp, i32, dbl, i64, i64, i64, vp, vp, vp, vp, vp]),
+        "fw_pairwise": (i32, [vp, i32, dbl, i64, i64, i32, i32, vp]),
+        "fw_pairwise_copy": (i32, [vp, vp, vp, vp, vp]),
+        "fw_set_univar_nbrs": (i32, [vp, vp, vp, vp, vp]),
+        "fw_pairwise_stats": (i32, [vp, vp, vp, vp]),
+        "fw_hiton_pc": (i32, [vp, i32, i64, vp, i32, dbl, i64, i64, i64] + [vp] * 11),
+        "fw_hiton_pc_capacity": (i32, [vp, i64, vp, vp]),
+        "fw_build_info": (C.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = L
+    return L
+
+
+def _p(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _i64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int64))
+
+
+class NbrCSR:
+    """var -> OrderedDict(nbr -> (stat, adj p)) of pw_univar_neighbors (tests.jl:372-388) as CSR."""
+
+    def __init__(self, offsets, nbr, stat, pval):
+        self.offsets, self.nbr, self.stat, self.pval = offsets, nbr, stat, pval
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    def __getitem__(self, v):
+        a, b = self.offsets[v], self.offsets[v + 1]
+        return {int(n): (float(s), float(p)) for n, s, p in zip(self.nbr[a:b], self.stat[a:b], self.pval[a:b])}
+
+    def degree(self):
+        return np.diff(self.offsets)
+
+
+class HitonResult:
+    """Per-target HitonState.state_results / inter_results (types.jl:154-160) as CSR over the listed targets."""
+
+    def __init__(self, targets, off, pc_count, pc_nbr, pc_stat, pc_p, tpc_count, tpc_nbr, tpc_stat, tpc_p, num_tests, executed):
+        self.targets, self.off = targets, off
+        self.pc_count, self.pc_nbr, self.pc_stat, self.pc_p = pc_count, pc_nbr, pc_stat, pc_p
+        self.tpc_count, self.tpc_nbr, self.tpc_stat, self.tpc_p = tpc_count, tpc_nbr, tpc_stat, tpc_p
+        self.num_tests, self.tests_executed = num_tests, executed
+
+    def pc(self, i):
+        a = self.off[i]
+        b = a + self.pc_count[i]
+        return self.pc_nbr[a:b], self.pc_stat[a:b], self.pc_p[a:b]
+
+    def tpc(self, i):
+        a = self.off[i]
+        b = a + self.tpc_count[i]
+        return self.tpc_nbr[a:b], self.tpc_stat[a:b], self.tpc_p[a:b]
+
+
+class Engine:
+    """One `fw_ctx`: the reference's test_obj + data + cor_mat, resident on one B200."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        st = self.L.fw_create(device, C.byref(h))
+        if st != FW_OK:
+            raise FwError("fw_create(device=%d) failed [%d]: %s" % (device, st, self.L.fw_last_error(None).decode()))
+        self.h = h
+        self.device = device
+        self.kind = None
+        self.n = self.p = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fw_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != FW_OK:
+            raise FwError("libfwgpu error [%d]: %s" % (st, self.L.fw_last_error(self.h).decode()))
+
+    # -- plumbing -------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return self.L.fw_stream(self.h)
+
+    def synchronize(self):
+        self._ck(self.L.fw_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.L.fw_launch_count(self.h))
+
+    # -- data -----------------------------------------------------------------------------
+    def set_data(self, data, kind):
+        """data: [n, p] array (any layout) or an already column-major buffer given as a [p, n] C-contiguous
+        array with `data.T` semantics via set_data_colmajor."""
+        d = np.asarray(data)
+        return self.set_data_colmajor(np.ascontiguousarray(d.T), kind)
+
+    def set_data_colmajor(self, data_pn, kind):
+        """data_pn: C-contiguous [p, n] (= Julia's column-major n x p Matrix)."""
+        k = KINDS[kind]
+        p, n = data_pn.shape
+        if k >= 2:
+            if data_pn.dtype != np.float32 or not data_pn.flags.c_contiguous:
+                data_pn = np.ascontiguousarray(data_pn, dtype=np.float32)
+            self._ck(self.L.fw_set_data_f32(self.h, _p(data_pn), n, p, n))
+        else:
+            if data_pn.dtype != np.int32 or not data_pn.flags.c_contiguous:
+                data_pn = np.ascontiguousarray(data_pn, dtype=np.int32)
+            self._ck(self.L.fw_set_data_i32(self.h, _p(data_pn), n, p, n))
+        self._keep = [data_pn]
+        self.kind, self.n, self.p = kind, n, p
+        return self
+
+    def set_data_ptr(self, host_ptr, n, p, kind="fz"):
+        """host pointer (e.g. a pinned torch tensor's data_ptr) to a column-major n x p float32 table"""
+        assert KINDS[kind] >= 2
+        self._ck(self.L.fw_set_data_f32(self.h, C.c_void_p(host_ptr), n, p, n))
+        self.kind, self.n, self.p = kind, n, p
+        return self
+
+    def adopt_data_device(self, dev_ptr, n, p, kind="fz"):
+        self._ck(self.L.fw_adopt_data_f32_device(self.h, C.c_void_p(dev_ptr), n, p, n))
+        self.kind, self.n, self.p = kind, n, p
+        return self
+
+    def set_n_obs(self, n):
+        self._ck(self.L.fw_set_n_obs(self.h, n))
+        self.n = n
+
+    # -- cor_mat ----------------------------------------------------------------------------
+    def cor(self, want_host=True):
+        """cor_mat = Float32.(cor(data)) (learning.jl:42-44), computed and kept on the device."""
+        out = np.empty((self.p, self.p), np.float32) if want_host else None
+        self._ck(self.L.fw_cor_matrix(self.h, _p(out)))
+        return out
+
+    def set_cor(self, cor, n_obs=None, kind="fz"):
+        c = np.ascontiguousarray(cor, dtype=np.float32)
+        assert c.ndim == 2 and c.shape[0] == c.shape[1]
+        self._ck(self.L.fw_set_cor_f32(self.h, _p(c), c.shape[0]))
+        self.p = c.shape[0]
+        if self.kind is None:
+            self.kind = kind
+        if n_obs is not None:
+            self.set_n_obs(n_obs)
+        self.synchronize()
+        return self
+
+    def adopt_cor_device(self, dev_ptr, p):
+        self._ck(self.L.fw_adopt_cor_device(self.h, C.c_void_p(dev_ptr), p))
+        self.p = p
+
+    def cor_device_ptr(self):
+        return self.L.fw_cor_device_ptr(self.h)
+
+    # -- tests ------------------------------------------------------------------------------
+    def test_batch(self, X, Y, Zs=None, k=None, hps=5, n_obs_min=0, kind=None):
+        X, Y = _i64(X), _i64(Y)
+        nt = len(X)
+        if Zs is None:
+            Zs = np.zeros((nt, 3), np.int64)
+            k = np.zeros(nt, np.int32)
+        else:
+            Zl = list(Zs)
+            if k is None:
+                k = np.array([len(z) for z in Zl], np.int32)
+            Zs = np.zeros((nt, 3), np.int64)
+            for i, z in enumerate(Zl):
+                Zs[i, :len(z)] = z
+        k = np.ascontiguousarray(k, dtype=np.int32)
+        out = (TestResult * max(nt, 1))()
+        self._ck(self.L.fw_test_batch(self.h, KINDS[kind or self.kind], nt, _p(X), _p(Y), _p(k), _p(np.ascontiguousarray(Zs)), hps, n_obs_min, out))
+        return [out[i].astuple() for i in range(nt)]
+
+    def test(self, X, Y, Zs=(), hps=5, n_obs_min=0, kind=None):
+        return self.test_batch([X], [Y], [tuple(Zs)], hps=hps, n_obs_min=n_obs_min, kind=kind)[0]
+
+    def test_subsets(self, X, Y, Z_total, max_k=3, alpha=0.01, hps=5, n_obs_min=0, max_tests=0, kind=None):
+        Z = _i64(Z_total)
+        out = TestResult()
+        Zs = np.zeros(3, np.int64)
+        k = C.c_int32(0)
+        nt = C.c_int64(0)
+        fr = C.c_double(0)
+        self._ck(self.L.fw_test_subsets(self.h, KINDS[kind or self.kind], X, Y, _p(Z), len(Z), max_k, alpha, hps, n_obs_min, max_tests,
+                                        C.byref(out), _p(Zs), C.byref(k), C.byref(nt), C.byref(fr)))
+        return out.astuple(), tuple(int(z) for z in Zs[:k.value]), int(nt.value), fr.value
+
+    def test_subsets_batch(self, X, Y, Z_lists, max_k=3, alpha=0.01, hps=5, n_obs_min=0, max_tests=0, kind=None):
+        X, Y = _i64(X), _i64(Y)
+        nj = len(X)
+        off = np.zeros(nj + 1, np.int64)
+        off[1:] = np.cumsum([len(z) for z in Z_lists])
+        zi = _i64(np.concatenate([np.asarray(z, np.int64) for z in Z_lists]) if off[-1] else np.zeros(0, np.int64))
+        out = (TestResult * max(nj, 1))()
+        Zs = np.zeros((max(nj, 1), 3), np.int64)
+        k = np.zeros(max(nj, 1), np.int32)
+        nt = np.zeros(max(nj, 1), np.int64)
+        fr = np.zeros(max(nj, 1), np.float64)
+        self._ck(self.L.fw_test_subsets_batch(self.h, KINDS[kind or self.kind], nj, _p(X), _p(Y), _p(off), _p(zi), max_k, alpha, hps,
+                                              n_obs_min, max_tests, out, _p(Zs), _p(k), _p(nt), _p(fr)))
+        return [(out[i].astuple(), tuple(int(z) for z in Zs[i, :k[i]]), int(nt[i]), float(fr[i])) for i in range(nj)]
+
+    # -- pairwise stage ------------------------------------------------------------------------
+    def pw_univar_neighbors(self, alpha=0.01, hps=5, n_obs_min=0, FDR=True, correct_reliable_only=True, want_host=True, kind=None):
+        ne = C.c_int64(0)
+        self._ck(self.L.fw_pairwise(self.h, KINDS[kind or self.kind], alpha, hps, n_obs_min, int(FDR), int(correct_reliable_only), C.byref(ne)))
+        self.uni_entries = int(ne.value)
+        if not want_host:
+            return None
+        return self.univar_nbrs()
+
+    def univar_nbrs(self):
+        ne = self.uni_entries
+        off = np.zeros(self.p + 1, np.int64)
+        nbr = np.zeros(max(ne, 1), np.int64)
+        st = np.zeros(max(ne, 1))
+        ap = np.zeros(max(ne, 1))
+        self._ck(self.L.fw_pairwise_copy(self.h, _p(off), _p(nbr), _p(st), _p(ap)))
+        return NbrCSR(off, nbr[:ne], st[:ne], ap[:ne])
+
+    def set_univar_nbrs(self, offsets, nbr, stat, pval):
+        off = _i64(offsets)
+        self._ck(self.L.fw_set_univar_nbrs(self.h, _p(off), _p(_i64(nbr)), _p(np.ascontiguousarray(stat, dtype=np.float64)),
+                                           _p(np.ascontiguousarray(pval, dtype=np.float64))))
+        self.uni_entries = int(off[-1])
+
+    def pairwise_stats(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.fw_pairwise_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"n_tests": a.value, "n_reliable": b.value, "n_raw_sig": c.value}
+
+    # -- HITON-PC ---------------------------------------------------------------------------------
+    def si_HITON_PC(self, targets, max_k=3, alpha=0.01, hps=5, n_obs_min=0, max_tests=10_000_000, kind=None, want_tpc=True,
+                    buffers=None):
+        """si_HITON_PC for each target (hiton.jl:283-400; parallel="single" semantics: no whitelist)."""
+        t = _i64(np.atleast_1d(targets))
+        nt = len(t)
+        cap = C.c_int64(0)
+        self._ck(self.L.fw_hiton_pc_capacity(self.h, nt, _p(t), C.byref(cap)))
+        cp = max(int(cap.value), 1)
+        if buffers is not None and buffers["cap"] >= cp and buffers["nt"] >= nt:
+            b = buffers
+        else:
+            b = {"cap": cp, "nt": nt, "off": np.zeros(nt + 1, np.int64), "pcc": np.zeros(max(nt, 1), np.int64),
+                 "pcn": np.zeros(cp, np.int64), "pcs": np.zeros(cp), "pcp": np.zeros(cp),
+                 "tpcc": np.zeros(max(nt, 1), np.int64), "tpcn": np.zeros(cp, np.int64), "tpcs": np.zeros(cp), "tpcp": np.zeros(cp),
+                 "ntests": np.zeros(max(nt, 1), np.int64)}
+        ex = C.c_int64(0)
+        tp = want_tpc
+        self._ck(self.L.fw_hiton_pc(self.h, KINDS[kind or self.kind], nt, _p(t), max_k, alpha, hps, n_obs_min, max_tests,
+                                    _p(b["off"]), _p(b["pcc"]), _p(b["pcn"]), _p(b["pcs"]), _p(b["pcp"]),
+                                    _p(b["tpcc"]), _p(b["tpcn"]) if tp else None, _p(b["tpcs"]) if tp else None, _p(b["tpcp"]) if tp else None,
+                                    _p(b["ntests"]), C.byref(ex)))
+        return HitonResult(t, b["off"][:nt + 1], b["pcc"][:nt], b["pcn"], b["pcs"], b["pcp"], b["tpcc"][:nt], b["tpcn"], b["tpcs"], b["tpcp"],
+                           b["ntests"][:nt], int(ex.value))
+
+    # -- LGL ------------------------------------------------------------------------------------------
+    def LGL(self, max_k=3, alpha=0.01, hps=5, n_obs_min=-1, max_tests=10_000_000, FDR=True, targets=None, kind=None):
+        """learning.jl:203-279 with parallel="single": cor -> pairwise -> HITON-PC per target -> OR-rule graph."""
+        kind = kind or self.kind
+        if n_obs_min < 0:
+            n_obs_min = auto_n_obs_min(kind, max_k, hps)
+        if kind == "fz" and not self.L.fw_cor_device_ptr(self.h):
+            self.cor(want_host=False)
+        uni = self.pw_univar_neighbors(alpha=alpha, hps=hps, n_obs_min=n_obs_min, FDR=FDR, kind=kind)
+        tg = target_order(uni) if targets is None else _i64(targets)
+        res = self.si_HITON_PC(tg, max_k=max_k, alpha=alpha, hps=hps, n_obs_min=n_obs_min, max_tests=max_tests, kind=kind, want_tpc=False)
+        edges = assemble_graph(res, uni, kind)
+        return {"edges": edges, "cond_tests": int(res.num_tests.sum()), "tests_executed": res.tests_executed,
+                "pair_tests": self.p * (self.p - 1) // 2, "hiton": res, "univar": uni}
+
+
+# ---- host logic shared with the tests (pure Python, no compute) --------------------------------------
+def auto_n_obs_min(kind, max_k, hps=5, max_level=None):
+    """learning.jl:51-61 (applies to every test kind because of the `<` / `&` precedence quirk)."""
+    if kind in ("mi", "mi_nz"):
+        assert max_level is not None
+        return hps * 2 * 2 * int(min(max_level ** max_k, 8))
+    return 20
+
+
+def target_order(uni):
+    """learning.jl:97-98: variables by ascending univariate degree, stable."""
+    return np.argsort(uni.degree(), kind="stable").astype(np.int64)
+
+
+def shard_targets(order, rank, world):
+    """Static interleaved sharding of the degree-ordered targets (target i -> rank i mod world);
+    replaces the job queue of interleaved.jl:76-93 for parallel="single" semantics."""
+    return np.ascontiguousarray(order[rank::world])
+
+
+def _maxweight(w1, w2):
+    # misc.jl:201-218
+    if math.isnan(w1):
+        return w2
+    if math.isnan(w2):
+        return w1
+    s1 = (w1 > 0) - (w1 < 0)
+    s2 = (w2 > 0) - (w2 < 0)
+    if s1 * s2 < 0:
+        return w1
+    return max(abs(w1), abs(w2)) * s1
+
+
+def assemble_graph(res, uni, kind):
+    """make_weights (misc.jl:137-159) + make_symmetric_graph (misc.jl:230-272), OR rule.
+    Returns sorted [(a, b, weight)] with a < b."""
+    W = {}
+    disc = kind in ("mi", "mi_nz")
+    for i, T in enumerate(res.targets):
+        nb, st, _ = res.pc(i)
+        T = int(T)
+        if disc:
+            u = uni[T]
+            W[T] = {int(v): float(np.sign(u[int(v)][0]) * abs(s)) for v, s in zip(nb, st)}
+        else:
+            W[T] = {int(v): float(s) for v, s in zip(nb, st)}
+    edges = {}
+    for a in sorted(W):
+        for b, w in W[a].items():
+            e = (min(a, b), max(a, b))
+            if e in edges:
+                continue
+            rw = W.get(b, {}).get(a, float("nan"))
+            sw = _maxweight(w, rw)
+            if not math.isnan(sw):
+                edges[e] = sw
+    return sorted((a, b, w) for (a, b), w in edges.items())
+
+
+def write_edgelist(path, edges, header=None, meta_mask=None, p=None):
+    """io.jl:338-359 edgelist format (`# header`, `# meta mask`, then `a<TAB>b<TAB>weight`)."""
+    if header is None:
+        header = ["X%d" % (i + 1) for i in range(p)]
+    if meta_mask is None:
+        meta_mask = [False] * len(header)
+    with open(path, "w") as f:
+        f.write("# header\t" + ",".join(header) + "\n")
+        f.write("# meta mask\t" + ",".join("true" if m else "false" for m in meta_mask) + "\n")
+        for a, b, w in edges:
+            f.write("%s\t%s\t%r\n" % (header[a], header[b], w))

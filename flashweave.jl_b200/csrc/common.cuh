@@ -1,0 +1,43 @@
+// common.cuh — shared types for the fwgpu kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+#define FW_INF_IDX 0x7fffffffffffffffLL
+
+// device-side image of src/types.jl:140-145 TestResult (same 32-byte layout as fw_test_result)
+struct DevResult {
+    double stat;
+    double pval;
+    i64 df;
+    unsigned char suff_power;
+    unsigned char pad_[7];
+};
+
+__device__ __forceinline__ DevResult make_result(double s, double p, i64 df, bool sp) {
+    DevResult r;
+    r.stat = s; r.pval = p; r.df = df; r.suff_power = sp ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) r.pad_[i] = 0;
+    return r;
+}
+
+__device__ __forceinline__ i64 choose2(i64 n) { return n < 2 ? 0 : n * (n - 1) / 2; }
+__device__ __forceinline__ i64 choose3(i64 n) { return n < 3 ? 0 : n * (n - 1) * (n - 2) / 6; }
+
+// Lexicographic unranking of pairs (a < b) out of n elements: rank q in [0, C(n,2)).
+// Number of pairs whose first element is < a:  off(a) = a*n - a*(a+1)/2.
+__device__ __forceinline__ void unrank2(i64 q, int n, int& a, int& b) {
+    double fn = 2.0 * (double)n - 1.0;
+    double disc = fn * fn - 8.0 * (double)q;
+    int aa = (int)((fn - sqrt(disc > 0.0 ? disc : 0.0)) * 0.5);
+    if (aa < 0) aa = 0;
+    if (aa > n - 2) aa = n - 2;
+    while (aa > 0 && (i64)aa * n - (i64)aa * (aa + 1) / 2 > q) --aa;
+    while (aa < n - 2 && (i64)(aa + 1) * n - (i64)(aa + 1) * (aa + 2) / 2 <= q) ++aa;
+    a = aa;
+    b = (int)(q - ((i64)aa * n - (i64)aa * (aa + 1) / 2)) + aa + 1;
+}

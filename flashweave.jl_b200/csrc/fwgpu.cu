@@ -1,0 +1,639 @@
+// fwgpu.cu — libfwgpu.so: context, C ABI (include/fwgpu.h) and kernel launches.
+// Built for sm_100a only (see build.py).  No torch types cross this boundary.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/fwgpu.h"
+#include "common.cuh"
+#include "fz.cuh"
+#include "subsets.cuh"
+#include "hiton.cuh"
+#include "pairwise.cuh"
+#include "cor_gemm.cuh"
+
+static_assert(sizeof(fw_test_result) == 32, "TestResult layout (src/types.jl:140-145)");
+static_assert(sizeof(DevResult) == 32, "DevResult layout");
+
+static thread_local std::string g_create_error;
+
+template <class T>
+struct DevBuf {
+    T* ptr = nullptr;
+    size_t cap = 0;     // elements
+    bool owned = true;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap && ptr && owned) return cudaSuccess;
+        release();
+        if (n == 0) n = 1;
+        cudaError_t e = cudaMalloc((void**)&ptr, n * sizeof(T));
+        if (e == cudaSuccess) { cap = n; owned = true; } else { ptr = nullptr; cap = 0; }
+        return e;
+    }
+    void adopt(T* p, size_t n) { release(); ptr = p; cap = n; owned = false; }
+    void release() { if (ptr && owned) cudaFree(ptr); ptr = nullptr; cap = 0; owned = true; }
+    ~DevBuf() { release(); }
+};
+
+struct fw_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int index_base = 0;
+    i64 launches = 0;
+
+    // data
+    i64 n = 0, p = 0, ld = 0;
+    int data_kind = -1;                  // 0: f32 continuous, 1: i32 discrete, -1 none
+    DevBuf<float> d_data_f32;
+    DevBuf<int> d_data_i32;
+    i64 n_obs = -1;                      // rows used by Fisher-z tests
+
+    // cor_mat
+    DevBuf<float> d_cor; i64 cor_p = 0;
+
+    // univariate neighbour lists (device-resident CSR + host copy of the offsets)
+    DevBuf<i64> d_uni_off, d_uni_nbr; DevBuf<double> d_uni_stat, d_uni_p;
+    std::vector<i64> h_uni_off; i64 uni_entries = -1;
+    i64 pw_tests = 0, pw_reliable = 0, pw_raw_sig = 0;
+
+    // scratch
+    DevBuf<int> d_counter; DevBuf<u64> d_exec;
+    PairwiseScratch pw;
+    CorGemmScratch cg;
+};
+
+static int fail(fw_ctx* c, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define NEED(cond, code, ...) do { if (!(cond)) return fail(ctx, code, __VA_ARGS__); } while (0)
+
+static FzConsts make_fz_consts(i64 n_rows, i64 n_obs_min) {
+    FzConsts fc;
+    i64 sf = n_rows - 0 - 3;                 // len_z is hard-coded 0 (src/tests.jl:156,256)
+    fc.sf_pos = sf > 0 ? 1 : 0;
+    fc.half_sqrt_sf = sf > 0 ? std::sqrt((double)sf) / 2.0 : 0.0;
+    fc.rows_ok = n_rows >= n_obs_min ? 1 : 0;
+    return fc;
+}
+
+// ---- capacity classes shared by the subset-search and HITON launches -------------------------
+static const int kCaps[4] = {32, 64, 128, 224};
+static size_t hiton_smem_bytes(int cap, bool r_in_smem) {
+    size_t o = r_in_smem ? sizeof(float) * (size_t)cap * cap : 0;
+    o = (o + 15) & ~(size_t)15;
+    o += sizeof(i64) * (cap + 1) + 4 * sizeof(double) * cap + sizeof(i64) * cap + 2 * sizeof(int) * cap;
+    return o + 16;
+}
+static size_t subsets_smem_bytes(int cap, bool r_in_smem) {
+    size_t o = r_in_smem ? sizeof(float) * (size_t)cap * cap : 0;
+    o = (o + 15) & ~(size_t)15;
+    o += sizeof(i64) * (cap + 1) + sizeof(int) * cap;
+    return o + 16;
+}
+
+template <class K>
+static cudaError_t grid_for(K kernel, int threads, size_t smem, int sm_count, i64 n_items, int* grid) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    i64 g = (i64)sm_count * occ;      // persistent CTAs: a whole number of CTAs per SM
+    if (g > n_items) g = n_items;
+    if (g < 1) g = 1;
+    *grid = (int)g;
+    return cudaSuccess;
+}
+
+
+extern "C" {
+
+const char* fw_build_info(void) {
+    return "libfwgpu sm_100a nvcc " __VERSION__
+#ifdef __CUDACC_VER_MAJOR__
+        " cuda"
+#endif
+        ;
+}
+
+int32_t fw_create(int32_t device, fw_ctx** out) {
+    fw_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, FW_ERR_INVALID, "fw_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, FW_ERR_CUDA, "fw_create: no CUDA device available (%s); libfwgpu has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, FW_ERR_INVALID, "fw_create: device %d out of range [0,%d)", device, ndev);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, FW_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, FW_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10) return fail(nullptr, FW_ERR_UNSUPPORTED, "fw_create: device is sm_%d%d; libfwgpu is built for sm_100a only", prop.major, prop.minor);
+    ctx = new fw_ctx();
+    ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    if (ctx->d_counter.reserve(16) != cudaSuccess || ctx->d_exec.reserve(16) != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_NOMEM, "scratch allocation failed"); }
+    *out = ctx;
+    return FW_OK;
+}
+
+int32_t fw_destroy(fw_ctx* ctx) {
+    if (!ctx) return FW_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    delete ctx;
+    return FW_OK;
+}
+
+const char* fw_last_error(fw_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int32_t fw_set_index_base(fw_ctx* ctx, int32_t base) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(base == 0 || base == 1, FW_ERR_INVALID, "index base must be 0 or 1");
+    ctx->index_base = base; return FW_OK;
+}
+void* fw_stream(fw_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int32_t fw_synchronize(fw_ctx* ctx) { if (!ctx) return FW_ERR_INVALID; CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return FW_OK; }
+int64_t fw_launch_count(fw_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- data -----------------------------------------------------------------------------
+int32_t fw_set_data_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, int64_t ld) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(host && n > 0 && p > 0 && ld >= n, FW_ERR_INVALID, "fw_set_data_f32: bad arguments (n=%lld p=%lld ld=%lld)", (long long)n, (long long)p, (long long)ld);
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_data_f32.reserve((size_t)n * p));
+    CK(cudaMemcpy2DAsync(ctx->d_data_f32.ptr, n * sizeof(float), host, ld * sizeof(float), n * sizeof(float), p, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n;
+    return FW_OK;
+}
+int32_t fw_adopt_data_f32_device(fw_ctx* ctx, const float* dev, int64_t n, int64_t p, int64_t ld) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(dev && n > 0 && p > 0 && ld >= n, FW_ERR_INVALID, "fw_adopt_data_f32_device: bad arguments");
+    ctx->d_data_f32.adopt(const_cast<float*>(dev), (size_t)ld * p);
+    ctx->n = n; ctx->p = p; ctx->ld = ld; ctx->data_kind = 0; ctx->n_obs = n;
+    return FW_OK;
+}
+int32_t fw_set_data_i32(fw_ctx* ctx, const int32_t* host, int64_t n, int64_t p, int64_t ld) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(host && n > 0 && p > 0 && ld >= n, FW_ERR_INVALID, "fw_set_data_i32: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_data_i32.reserve((size_t)n * p));
+    CK(cudaMemcpy2DAsync(ctx->d_data_i32.ptr, n * sizeof(int), host, ld * sizeof(int), n * sizeof(int), p, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 1; ctx->n_obs = n;
+    return FW_OK;
+}
+int32_t fw_set_n_obs(fw_ctx* ctx, int64_t n) { if (!ctx) return FW_ERR_INVALID; NEED(n >= 0, FW_ERR_INVALID, "n_obs < 0"); ctx->n_obs = n; return FW_OK; }
+
+int32_t fw_levels(fw_ctx* ctx, int32_t* levels, int32_t* max_vals) {
+    if (!ctx) return FW_ERR_INVALID;
+    (void)levels; (void)max_vals;
+    return fail(ctx, FW_ERR_UNSUPPORTED, "fw_levels: the discrete (mi / mi_nz) path is not built yet");
+}
+
+// ---- cor_mat ----------------------------------------------------------------------------
+int32_t fw_set_cor_f32(fw_ctx* ctx, const float* host_cor, int64_t p) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(host_cor && p > 0, FW_ERR_INVALID, "fw_set_cor_f32: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_cor.reserve((size_t)p * p));
+    CK(cudaMemcpyAsync(ctx->d_cor.ptr, host_cor, sizeof(float) * (size_t)p * p, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->cor_p = p; if (ctx->p == 0) ctx->p = p;
+    return FW_OK;
+}
+int32_t fw_adopt_cor_device(fw_ctx* ctx, const float* dev_cor, int64_t p) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(dev_cor && p > 0, FW_ERR_INVALID, "fw_adopt_cor_device: bad arguments");
+    ctx->d_cor.adopt(const_cast<float*>(dev_cor), (size_t)p * p);
+    ctx->cor_p = p; if (ctx->p == 0) ctx->p = p;
+    return FW_OK;
+}
+void* fw_cor_device_ptr(fw_ctx* ctx) { return ctx ? (void*)ctx->d_cor.ptr : nullptr; }
+
+int32_t fw_cor_matrix(fw_ctx* ctx, float* host_out) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(ctx->data_kind == 0, FW_ERR_STATE, "fw_cor_matrix: no continuous table resident (call fw_set_data_f32 first)");
+    CK(cudaSetDevice(ctx->device));
+    i64 p = ctx->p;
+    if (!(ctx->d_cor.ptr && ctx->d_cor.owned && ctx->d_cor.cap >= (size_t)p * p)) CK(ctx->d_cor.reserve((size_t)p * p));
+    std::string msg;
+    int nl = 0;
+    cudaError_t e = cor_gemm_run(ctx->cg, ctx->d_data_f32.ptr, ctx->n, p, ctx->ld, ctx->d_cor.ptr, ctx->sm_count, ctx->stream, &nl, &msg);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_cor_matrix: %s: %s", msg.c_str(), cudaGetErrorString(e));
+    ctx->cor_p = p;
+    if (host_out) {
+        CK(cudaMemcpyAsync(host_out, ctx->d_cor.ptr, sizeof(float) * (size_t)p * p, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return FW_OK;
+}
+
+// ---- single tests -------------------------------------------------------------------------
+int32_t fw_test_batch(fw_ctx* ctx, int32_t kind, int64_t n_tests, const int64_t* X, const int64_t* Y,
+                      const int32_t* k, const int64_t* Zs, int64_t hps, int64_t n_obs_min, fw_test_result* out) {
+    if (!ctx) return FW_ERR_INVALID;
+    (void)hps;
+    NEED(kind == FW_FZ, FW_ERR_UNSUPPORTED, "fw_test_batch: only kind FW_FZ is built yet (got %d)", kind);
+    NEED(n_tests >= 0 && (n_tests == 0 || (X && Y && k && Zs && out)), FW_ERR_INVALID, "fw_test_batch: NULL argument");
+    NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_test_batch: no cor_mat resident (fw_cor_matrix / fw_set_cor_f32)");
+    NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_test_batch: number of observations unknown (fw_set_data_f32 / fw_set_n_obs)");
+    if (n_tests == 0) return FW_OK;
+    CK(cudaSetDevice(ctx->device));
+    const i64 p = ctx->cor_p, base = ctx->index_base;
+    std::vector<i64> hx(n_tests), hy(n_tests), hz((size_t)n_tests * 3);
+    for (i64 t = 0; t < n_tests; ++t) {
+        NEED(k[t] >= 0 && k[t] <= 3, FW_ERR_UNSUPPORTED, "fw_test_batch: |Zs| = %d not in 0..3", k[t]);
+        hx[t] = X[t] - base; hy[t] = Y[t] - base;
+        NEED(hx[t] >= 0 && hx[t] < p && hy[t] >= 0 && hy[t] < p, FW_ERR_INVALID, "fw_test_batch: variable index out of range at test %lld", (long long)t);
+        for (int j = 0; j < 3; ++j) {
+            i64 z = j < k[t] ? Zs[t * 3 + j] - base : 0;
+            NEED(z >= 0 && z < p, FW_ERR_INVALID, "fw_test_batch: conditioning index out of range at test %lld", (long long)t);
+            hz[(size_t)t * 3 + j] = z;
+        }
+    }
+    DevBuf<i64> dx, dy, dz; DevBuf<int> dk; DevBuf<DevResult> dout;
+    CK(dx.reserve(n_tests)); CK(dy.reserve(n_tests)); CK(dz.reserve((size_t)n_tests * 3)); CK(dk.reserve(n_tests)); CK(dout.reserve(n_tests));
+    CK(cudaMemcpyAsync(dx.ptr, hx.data(), sizeof(i64) * n_tests, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dy.ptr, hy.data(), sizeof(i64) * n_tests, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dz.ptr, hz.data(), sizeof(i64) * n_tests * 3, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dk.ptr, k, sizeof(int) * n_tests, cudaMemcpyHostToDevice, ctx->stream));
+    FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
+    int threads = 128; i64 blocks = (n_tests + threads - 1) / threads;
+    fz_test_batch_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->d_cor.ptr, p, n_tests, dx.ptr, dy.ptr, dk.ptr, dz.ptr, fc, ctx->n_obs, n_obs_min, dout.ptr);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout.ptr, sizeof(DevResult) * n_tests, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FW_OK;
+}
+
+int32_t fw_test_subsets_batch(fw_ctx* ctx, int32_t kind, int64_t n_jobs, const int64_t* X, const int64_t* Y,
+                              const int64_t* z_off, const int64_t* z_idx,
+                              int32_t max_k, double alpha, int64_t hps, int64_t n_obs_min, int64_t max_tests,
+                              fw_test_result* out_result, int64_t* out_Zs, int32_t* out_k, int64_t* num_tests, double* frac) {
+    if (!ctx) return FW_ERR_INVALID;
+    (void)hps;
+    NEED(kind == FW_FZ, FW_ERR_UNSUPPORTED, "fw_test_subsets: only kind FW_FZ is built yet (got %d)", kind);
+    NEED(max_k >= 1 && max_k <= 3, FW_ERR_UNSUPPORTED, "fw_test_subsets: max_k = %d not in 1..3", max_k);
+    NEED(n_jobs >= 0 && (n_jobs == 0 || (X && Y && z_off && out_result && out_Zs && out_k && num_tests && frac)), FW_ERR_INVALID, "fw_test_subsets: NULL argument");
+    NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_test_subsets: no cor_mat resident");
+    NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_test_subsets: number of observations unknown");
+    if (n_jobs == 0) return FW_OK;
+    CK(cudaSetDevice(ctx->device));
+    const i64 p = ctx->cor_p, base = ctx->index_base;
+    const i64 nz = z_off[n_jobs];
+    NEED(nz == 0 || z_idx, FW_ERR_INVALID, "fw_test_subsets: z_idx is NULL");
+    std::vector<i64> hx(n_jobs), hy(n_jobs), hz((size_t)std::max<i64>(nz, 1));
+    for (i64 j = 0; j < n_jobs; ++j) {
+        hx[j] = X[j] - base; hy[j] = Y[j] - base;
+        NEED(hx[j] >= 0 && hx[j] < p && hy[j] >= 0 && hy[j] < p, FW_ERR_INVALID, "fw_test_subsets: variable index out of range in job %lld", (long long)j);
+        NEED(z_off[j + 1] >= z_off[j], FW_ERR_INVALID, "fw_test_subsets: z_off not monotone");
+    }
+    for (i64 i = 0; i < nz; ++i) { hz[i] = z_idx[i] - base; NEED(hz[i] >= 0 && hz[i] < p, FW_ERR_INVALID, "fw_test_subsets: conditioning index out of range"); }
+
+    // jobs with empty Z_total: the reference's sentinel (src/tests.jl:285); others by capacity class
+    std::vector<int> cls[5];
+    int max_need = 0;
+    for (i64 j = 0; j < n_jobs; ++j) {
+        i64 m = z_off[j + 1] - z_off[j];
+        if (m == 0) {
+            fw_test_result r; memset(&r, 0, sizeof(r)); r.stat = NAN; r.pval = NAN; r.df = -1; r.suff_power = 1;
+            out_result[j] = r; out_Zs[j * 3] = -1; out_Zs[j * 3 + 1] = -1; out_Zs[j * 3 + 2] = -1; out_k[j] = 1; num_tests[j] = -1; frac[j] = NAN;
+            continue;
+        }
+        NEED(m + 2 < (i64)1 << 20, FW_ERR_UNSUPPORTED, "fw_test_subsets: |Z_total| too large");
+        int need = (int)m + 2, c = 4;
+        for (int q = 0; q < 4; ++q) if (need <= kCaps[q]) { c = q; break; }
+        cls[c].push_back((int)j);
+        if (c == 4) max_need = std::max(max_need, need);
+    }
+    DevBuf<i64> dx, dy, dzo, dzi, dZs, dnt; DevBuf<int> dsel, dk; DevBuf<DevResult> dres; DevBuf<double> dfr; DevBuf<float> gs;
+    CK(dx.reserve(n_jobs)); CK(dy.reserve(n_jobs)); CK(dzo.reserve(n_jobs + 1)); CK(dzi.reserve(nz)); CK(dZs.reserve((size_t)n_jobs * 3));
+    CK(dnt.reserve(n_jobs)); CK(dsel.reserve(n_jobs)); CK(dk.reserve(n_jobs)); CK(dres.reserve(n_jobs)); CK(dfr.reserve(n_jobs));
+    CK(cudaMemcpyAsync(dx.ptr, hx.data(), sizeof(i64) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dy.ptr, hy.data(), sizeof(i64) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dzo.ptr, z_off, sizeof(i64) * (n_jobs + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (nz) CK(cudaMemcpyAsync(dzi.ptr, hz.data(), sizeof(i64) * nz, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_exec.ptr, 0, sizeof(u64), ctx->stream));
+    SubsetsArgs a;
+    a.cor = ctx->d_cor.ptr; a.p = p; a.X = dx.ptr; a.Y = dy.ptr; a.z_off = dzo.ptr; a.z_idx = dzi.ptr;
+    a.max_k = max_k; a.alpha = alpha; a.max_tests = max_tests; a.fc = make_fz_consts(ctx->n_obs, n_obs_min);
+    a.out = dres.ptr; a.out_Zs = dZs.ptr; a.out_k = dk.ptr; a.num_tests = dnt.ptr; a.frac = dfr.ptr; a.executed_total = ctx->d_exec.ptr;
+    a.counter = ctx->d_counter.ptr;
+    size_t sel_off = 0;
+    for (int c = 0; c < 5; ++c) {
+        if (cls[c].empty()) continue;
+        int n_sel = (int)cls[c].size();
+        CK(cudaMemcpyAsync(dsel.ptr + sel_off, cls[c].data(), sizeof(int) * n_sel, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_counter.ptr, 0, sizeof(int), ctx->stream));
+        a.sel = dsel.ptr + sel_off; a.n_sel = n_sel; sel_off += n_sel;
+        int grid = 1;
+        if (c < 4) {
+            a.cap = kCaps[c]; a.gscratch = nullptr;
+            size_t smem = subsets_smem_bytes(a.cap, true);
+            if (c < 2) { CK(grid_for(subsets_fz_kernel<128, 2>, 128, smem, ctx->sm_count, n_sel, &grid)); subsets_fz_kernel<128, 2><<<grid, 128, smem, ctx->stream>>>(a); }
+            else { CK(grid_for(subsets_fz_kernel<256, 2>, 256, smem, ctx->sm_count, n_sel, &grid)); subsets_fz_kernel<256, 2><<<grid, 256, smem, ctx->stream>>>(a); }
+        } else {
+            a.cap = max_need;
+            size_t smem = subsets_smem_bytes(a.cap, false);
+            NEED(smem <= 200 * 1024, FW_ERR_UNSUPPORTED, "fw_test_subsets: |Z_total| = %d exceeds the supported maximum", max_need - 2);
+            CK(grid_for(subsets_fz_kernel<256, 2>, 256, smem, ctx->sm_count, n_sel, &grid));
+            size_t per = (size_t)a.cap * a.cap;
+            while (grid > 1 && per * grid * sizeof(float) > ((size_t)4 << 30)) grid = (grid + 1) / 2;
+            CK(gs.reserve(per * grid));
+            a.gscratch = gs.ptr;
+            subsets_fz_kernel<256, 2><<<grid, 256, smem, ctx->stream>>>(a);
+        }
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<DevResult> hres(n_jobs); std::vector<i64> hZs((size_t)n_jobs * 3), hnt(n_jobs); std::vector<int> hk(n_jobs); std::vector<double> hfr(n_jobs);
+    CK(cudaMemcpy(hres.data(), dres.ptr, sizeof(DevResult) * n_jobs, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hZs.data(), dZs.ptr, sizeof(i64) * n_jobs * 3, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hnt.data(), dnt.ptr, sizeof(i64) * n_jobs, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hk.data(), dk.ptr, sizeof(int) * n_jobs, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hfr.data(), dfr.ptr, sizeof(double) * n_jobs, cudaMemcpyDeviceToHost));
+    for (i64 j = 0; j < n_jobs; ++j) {
+        if (z_off[j + 1] == z_off[j]) continue;
+        memcpy(&out_result[j], &hres[j], sizeof(fw_test_result));
+        for (int i = 0; i < 3; ++i) out_Zs[j * 3 + i] = hZs[(size_t)j * 3 + i] >= 0 ? hZs[(size_t)j * 3 + i] + base : -1;
+        out_k[j] = hk[j]; num_tests[j] = hnt[j]; frac[j] = hfr[j];
+    }
+    return FW_OK;
+}
+
+int32_t fw_test_subsets(fw_ctx* ctx, int32_t kind, int64_t X, int64_t Y, const int64_t* Z_total, int64_t m,
+                        int32_t max_k, double alpha, int64_t hps, int64_t n_obs_min, int64_t max_tests,
+                        fw_test_result* out_result, int64_t* out_Zs, int32_t* out_k, int64_t* num_tests, double* frac) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(m >= 0, FW_ERR_INVALID, "fw_test_subsets: m < 0");
+    int64_t z_off[2] = {0, m};
+    return fw_test_subsets_batch(ctx, kind, 1, &X, &Y, z_off, Z_total, max_k, alpha, hps, n_obs_min, max_tests, out_result, out_Zs, out_k, num_tests, frac);
+}
+
+// ---- pairwise stage -------------------------------------------------------------------------
+int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_t n_obs_min,
+                    int32_t fdr, int32_t correct_reliable_only, int64_t* n_entries) {
+    if (!ctx) return FW_ERR_INVALID;
+    (void)hps;
+    NEED(kind == FW_FZ, FW_ERR_UNSUPPORTED, "fw_pairwise: only kind FW_FZ is built yet (got %d)", kind);
+    NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_pairwise: no cor_mat resident (fw_cor_matrix / fw_set_cor_f32)");
+    NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_pairwise: number of observations unknown");
+    CK(cudaSetDevice(ctx->device));
+    const i64 p = ctx->cor_p;
+    PairwiseOut po;
+    std::string msg; int nl = 0;
+    FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
+    cudaError_t e = pairwise_fz_run(ctx->pw, ctx->d_cor.ptr, p, fc, ctx->n_obs, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0,
+                                    ctx->sm_count, ctx->stream, &po, &nl, &msg);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_pairwise: %s: %s", msg.c_str(), cudaGetErrorString(e));
+    // adopt the CSR
+    CK(ctx->d_uni_off.reserve(p + 1)); CK(ctx->d_uni_nbr.reserve(po.n_entries)); CK(ctx->d_uni_stat.reserve(po.n_entries)); CK(ctx->d_uni_p.reserve(po.n_entries));
+    CK(cudaMemcpyAsync(ctx->d_uni_off.ptr, po.d_off, sizeof(i64) * (p + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (po.n_entries) {
+        CK(cudaMemcpyAsync(ctx->d_uni_nbr.ptr, po.d_nbr, sizeof(i64) * po.n_entries, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_uni_stat.ptr, po.d_stat, sizeof(double) * po.n_entries, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_uni_p.ptr, po.d_adjp, sizeof(double) * po.n_entries, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    ctx->h_uni_off.resize(p + 1);
+    CK(cudaMemcpyAsync(ctx->h_uni_off.data(), po.d_off, sizeof(i64) * (p + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->uni_entries = po.n_entries; ctx->pw_tests = po.n_tests; ctx->pw_reliable = po.n_reliable; ctx->pw_raw_sig = po.n_raw_sig;
+    if (n_entries) *n_entries = po.n_entries;
+    return FW_OK;
+}
+
+int32_t fw_pairwise_copy(fw_ctx* ctx, int64_t* offsets, int64_t* nbr, double* stat, double* adjp) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(ctx->uni_entries >= 0, FW_ERR_STATE, "fw_pairwise_copy: no neighbour lists resident");
+    CK(cudaSetDevice(ctx->device));
+    const i64 p = (i64)ctx->h_uni_off.size() - 1, ne = ctx->uni_entries, base = ctx->index_base;
+    if (offsets) memcpy(offsets, ctx->h_uni_off.data(), sizeof(i64) * (p + 1));
+    if (ne) {
+        if (nbr) { CK(cudaMemcpyAsync(nbr, ctx->d_uni_nbr.ptr, sizeof(i64) * ne, cudaMemcpyDeviceToHost, ctx->stream)); }
+        if (stat) CK(cudaMemcpyAsync(stat, ctx->d_uni_stat.ptr, sizeof(double) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+        if (adjp) CK(cudaMemcpyAsync(adjp, ctx->d_uni_p.ptr, sizeof(double) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (nbr && base) for (i64 i = 0; i < ne; ++i) nbr[i] += base;
+    return FW_OK;
+}
+
+int32_t fw_set_univar_nbrs(fw_ctx* ctx, const int64_t* offsets, const int64_t* nbr, const double* stat, const double* adjp) {
+    if (!ctx) return FW_ERR_INVALID;
+    i64 p = ctx->cor_p > 0 ? ctx->cor_p : ctx->p;
+    NEED(p > 0, FW_ERR_STATE, "fw_set_univar_nbrs: number of variables unknown (install data or cor_mat first)");
+    NEED(offsets, FW_ERR_INVALID, "fw_set_univar_nbrs: offsets is NULL");
+    CK(cudaSetDevice(ctx->device));
+    i64 ne = offsets[p];
+    NEED(offsets[0] == 0 && ne >= 0 && (ne == 0 || (nbr && stat && adjp)), FW_ERR_INVALID, "fw_set_univar_nbrs: bad CSR");
+    std::vector<i64> hn((size_t)std::max<i64>(ne, 1));
+    for (i64 i = 0; i < ne; ++i) { hn[i] = nbr[i] - ctx->index_base; NEED(hn[i] >= 0 && hn[i] < p, FW_ERR_INVALID, "fw_set_univar_nbrs: neighbour index out of range"); }
+    for (i64 v = 0; v < p; ++v) NEED(offsets[v + 1] >= offsets[v], FW_ERR_INVALID, "fw_set_univar_nbrs: offsets not monotone");
+    CK(ctx->d_uni_off.reserve(p + 1)); CK(ctx->d_uni_nbr.reserve(ne)); CK(ctx->d_uni_stat.reserve(ne)); CK(ctx->d_uni_p.reserve(ne));
+    CK(cudaMemcpyAsync(ctx->d_uni_off.ptr, offsets, sizeof(i64) * (p + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (ne) {
+        CK(cudaMemcpyAsync(ctx->d_uni_nbr.ptr, hn.data(), sizeof(i64) * ne, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_uni_stat.ptr, stat, sizeof(double) * ne, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_uni_p.ptr, adjp, sizeof(double) * ne, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->h_uni_off.assign(offsets, offsets + p + 1);
+    ctx->uni_entries = ne;
+    return FW_OK;
+}
+
+int32_t fw_pairwise_stats(fw_ctx* ctx, int64_t* n_tests, int64_t* n_reliable, int64_t* n_raw_sig) {
+    if (!ctx) return FW_ERR_INVALID;
+    if (n_tests) *n_tests = ctx->pw_tests;
+    if (n_reliable) *n_reliable = ctx->pw_reliable;
+    if (n_raw_sig) *n_raw_sig = ctx->pw_raw_sig;
+    return FW_OK;
+}
+
+// ---- HITON-PC -------------------------------------------------------------------------------
+int32_t fw_hiton_pc_capacity(fw_ctx* ctx, int64_t n_targets, const int64_t* targets, int64_t* capacity) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(ctx->uni_entries >= 0, FW_ERR_STATE, "fw_hiton_pc: no neighbour lists resident (fw_pairwise / fw_set_univar_nbrs)");
+    NEED(capacity && (n_targets == 0 || targets), FW_ERR_INVALID, "fw_hiton_pc_capacity: NULL argument");
+    const i64 p = (i64)ctx->h_uni_off.size() - 1;
+    i64 tot = 0;
+    for (i64 t = 0; t < n_targets; ++t) {
+        i64 T = targets[t] - ctx->index_base;
+        NEED(T >= 0 && T < p, FW_ERR_INVALID, "fw_hiton_pc: target index out of range");
+        tot += ctx->h_uni_off[T + 1] - ctx->h_uni_off[T];
+    }
+    *capacity = tot;
+    return FW_OK;
+}
+
+int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t* targets,
+                    int32_t max_k, double alpha, int64_t hps, int64_t n_obs_min, int64_t max_tests,
+                    int64_t* pc_off, int64_t* pc_count, int64_t* pc_nbr, double* pc_stat, double* pc_p,
+                    int64_t* tpc_count, int64_t* tpc_nbr, double* tpc_stat, double* tpc_p,
+                    int64_t* num_tests, int64_t* tests_executed_total) {
+    if (!ctx) return FW_ERR_INVALID;
+    (void)hps;
+    NEED(kind == FW_FZ, FW_ERR_UNSUPPORTED, "fw_hiton_pc: only kind FW_FZ is built yet (got %d)", kind);
+    NEED(max_k >= 0 && max_k <= 3, FW_ERR_UNSUPPORTED, "fw_hiton_pc: max_k = %d not in 0..3", max_k);
+    NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_hiton_pc: no cor_mat resident");
+    NEED(ctx->uni_entries >= 0, FW_ERR_STATE, "fw_hiton_pc: no neighbour lists resident (fw_pairwise / fw_set_univar_nbrs)");
+    NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_hiton_pc: number of observations unknown");
+    NEED(n_targets >= 0 && (n_targets == 0 || targets), FW_ERR_INVALID, "fw_hiton_pc: NULL targets");
+    if (n_targets == 0) { if (pc_off) pc_off[0] = 0; if (tests_executed_total) *tests_executed_total = 0; return FW_OK; }
+    CK(cudaSetDevice(ctx->device));
+    const i64 p = ctx->cor_p, base = ctx->index_base;
+    NEED((i64)ctx->h_uni_off.size() == p + 1, FW_ERR_STATE, "fw_hiton_pc: neighbour lists and cor_mat disagree on the number of variables");
+
+    std::vector<i64> ht(n_targets), hoff(n_targets + 1);
+    hoff[0] = 0;
+    for (i64 t = 0; t < n_targets; ++t) {
+        ht[t] = targets[t] - base;
+        NEED(ht[t] >= 0 && ht[t] < p, FW_ERR_INVALID, "fw_hiton_pc: target index out of range");
+        hoff[t + 1] = hoff[t] + (ctx->h_uni_off[ht[t] + 1] - ctx->h_uni_off[ht[t]]);
+    }
+    const i64 cap_total = std::max<i64>(hoff[n_targets], 1);
+
+    DevBuf<i64> dt, doff, dpcn, dtpcn, dpcc, dtpcc, dnt; DevBuf<double> dpcs, dpcp, dtpcs, dtpcp; DevBuf<int> dsel, dorder, dstatus; DevBuf<float> gs;
+    CK(dt.reserve(n_targets)); CK(doff.reserve(n_targets + 1)); CK(dpcn.reserve(cap_total)); CK(dtpcn.reserve(cap_total));
+    CK(dpcc.reserve(n_targets)); CK(dtpcc.reserve(n_targets)); CK(dnt.reserve(n_targets));
+    CK(dpcs.reserve(cap_total)); CK(dpcp.reserve(cap_total)); CK(dtpcs.reserve(cap_total)); CK(dtpcp.reserve(cap_total));
+    CK(dsel.reserve(n_targets)); CK(dorder.reserve(cap_total)); CK(dstatus.reserve(n_targets));
+    CK(cudaMemcpyAsync(dt.ptr, ht.data(), sizeof(i64) * n_targets, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(doff.ptr, hoff.data(), sizeof(i64) * (n_targets + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_exec.ptr, 0, sizeof(u64), ctx->stream));
+    CK(cudaMemsetAsync(dpcc.ptr, 0, sizeof(i64) * n_targets, ctx->stream));
+    CK(cudaMemsetAsync(dtpcc.ptr, 0, sizeof(i64) * n_targets, ctx->stream));
+    CK(cudaMemsetAsync(dnt.ptr, 0, sizeof(i64) * n_targets, ctx->stream));
+
+    std::vector<i64> h_pcc(n_targets, 0), h_tpcc(n_targets, 0), h_nt(n_targets, 0);
+    if (max_k == 0) {
+        // hiton.jl:394-397: PC = univariate neighbours, no conditioning (handled on the host side of the ABI:
+        // it is a copy of the resident lists, there is nothing to compute)
+        std::vector<i64> un((size_t)std::max<i64>(ctx->uni_entries, 1)); std::vector<double> us(un.size()), up(un.size());
+        if (ctx->uni_entries) {
+            CK(cudaMemcpy(un.data(), ctx->d_uni_nbr.ptr, sizeof(i64) * ctx->uni_entries, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(us.data(), ctx->d_uni_stat.ptr, sizeof(double) * ctx->uni_entries, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(up.data(), ctx->d_uni_p.ptr, sizeof(double) * ctx->uni_entries, cudaMemcpyDeviceToHost));
+        }
+        for (i64 t = 0; t < n_targets; ++t) {
+            i64 e0 = ctx->h_uni_off[ht[t]], cnt = ctx->h_uni_off[ht[t] + 1] - e0;
+            if (pc_count) pc_count[t] = cnt;
+            if (tpc_count) tpc_count[t] = 0;
+            if (num_tests) num_tests[t] = 0;
+            for (i64 i = 0; i < cnt; ++i) {
+                if (pc_nbr) pc_nbr[hoff[t] + i] = un[e0 + i] + base;
+                if (pc_stat) pc_stat[hoff[t] + i] = us[e0 + i];
+                if (pc_p) pc_p[hoff[t] + i] = up[e0 + i];
+            }
+        }
+        if (pc_off) memcpy(pc_off, hoff.data(), sizeof(i64) * (n_targets + 1));
+        if (tests_executed_total) *tests_executed_total = 0;
+        return FW_OK;
+    }
+
+    HitonArgs a;
+    a.cor = ctx->d_cor.ptr; a.p = p;
+    a.uni_off = ctx->d_uni_off.ptr; a.uni_nbr = ctx->d_uni_nbr.ptr; a.uni_stat = ctx->d_uni_stat.ptr; a.uni_p = ctx->d_uni_p.ptr;
+    a.targets = dt.ptr; a.out_off = doff.ptr; a.counter = ctx->d_counter.ptr;
+    a.max_k = max_k; a.alpha = alpha; a.max_tests = max_tests; a.fc = make_fz_consts(ctx->n_obs, n_obs_min);
+    a.cand_order = dorder.ptr;
+    a.pc_nbr = dpcn.ptr; a.pc_stat = dpcs.ptr; a.pc_p = dpcp.ptr; a.pc_count = dpcc.ptr;
+    a.tpc_nbr = dtpcn.ptr; a.tpc_stat = dtpcs.ptr; a.tpc_p = dtpcp.ptr; a.tpc_count = dtpcc.ptr;
+    a.num_tests = dnt.ptr; a.executed_total = ctx->d_exec.ptr; a.status = dstatus.ptr;
+
+    // capacity classes: a target needs at most (#candidates + 2) slots; start optimistic (<= 64) and
+    // escalate the few targets whose accepted set outgrows the class
+    std::vector<int> pending[5];
+    for (i64 t = 0; t < n_targets; ++t) {
+        i64 need = (hoff[t + 1] - hoff[t]) + 2;
+        pending[need <= 32 ? 0 : 1].push_back((int)t);
+    }
+    std::vector<int> hstatus(n_targets);
+    for (int c = 0; c < 5; ++c) {
+        if (pending[c].empty()) continue;
+        std::vector<int>& sel = pending[c];
+        // longest jobs first (candidate count is the work proxy)
+        std::stable_sort(sel.begin(), sel.end(), [&](int x, int y) { return (hoff[x + 1] - hoff[x]) > (hoff[y + 1] - hoff[y]); });
+        int n_sel = (int)sel.size();
+        CK(cudaMemcpyAsync(dsel.ptr, sel.data(), sizeof(int) * n_sel, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_counter.ptr, 0, sizeof(int), ctx->stream));
+        a.sel = dsel.ptr; a.n_sel = n_sel;
+        int grid = 1;
+        if (c < 4) {
+            a.cap = kCaps[c]; a.gscratch = nullptr;
+            size_t smem = hiton_smem_bytes(a.cap, true);
+            if (c < 2) { CK(grid_for(hiton_fz_kernel<128, 2>, 128, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<128, 2><<<grid, 128, smem, ctx->stream>>>(a); }
+            else { CK(grid_for(hiton_fz_kernel<256, 2>, 256, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<256, 2><<<grid, 256, smem, ctx->stream>>>(a); }
+        } else {
+            i64 need = 0; for (int t : sel) need = std::max<i64>(need, hoff[t + 1] - hoff[t] + 2);
+            NEED(need <= 3000, FW_ERR_UNSUPPORTED, "fw_hiton_pc: a target has %lld candidates; more than 2998 accepted neighbours are not supported", (long long)need - 2);
+            a.cap = (int)need;
+            size_t smem = hiton_smem_bytes(a.cap, false);
+            CK(grid_for(hiton_fz_kernel<256, 2>, 256, smem, ctx->sm_count, n_sel, &grid));
+            size_t per = (size_t)a.cap * a.cap;
+            while (grid > 1 && per * grid * sizeof(float) > ((size_t)8 << 30)) grid = (grid + 1) / 2;
+            CK(gs.reserve(per * grid));
+            a.gscratch = gs.ptr;
+            hiton_fz_kernel<256, 2><<<grid, 256, smem, ctx->stream>>>(a);
+        }
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(hstatus.data(), dstatus.ptr, sizeof(int) * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int t : sel) if (hstatus[t] == 1) {
+            NEED(c < 4, FW_ERR_UNSUPPORTED, "fw_hiton_pc: capacity overflow in the unbounded class");
+            pending[c + 1].push_back(t);
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    // copy out
+    if (pc_off) memcpy(pc_off, hoff.data(), sizeof(i64) * (n_targets + 1));
+    if (pc_count) CK(cudaMemcpyAsync(pc_count, dpcc.ptr, sizeof(i64) * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tpc_count) CK(cudaMemcpyAsync(tpc_count, dtpcc.ptr, sizeof(i64) * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+    if (num_tests) CK(cudaMemcpyAsync(num_tests, dnt.ptr, sizeof(i64) * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hoff[n_targets] > 0) {
+        i64 ne = hoff[n_targets];
+        if (pc_nbr) CK(cudaMemcpyAsync(pc_nbr, dpcn.ptr, sizeof(i64) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+        if (pc_stat) CK(cudaMemcpyAsync(pc_stat, dpcs.ptr, sizeof(double) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+        if (pc_p) CK(cudaMemcpyAsync(pc_p, dpcp.ptr, sizeof(double) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+        if (tpc_nbr) CK(cudaMemcpyAsync(tpc_nbr, dtpcn.ptr, sizeof(i64) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+        if (tpc_stat) CK(cudaMemcpyAsync(tpc_stat, dtpcs.ptr, sizeof(double) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+        if (tpc_p) CK(cudaMemcpyAsync(tpc_p, dtpcp.ptr, sizeof(double) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    u64 hexec = 0;
+    CK(cudaMemcpyAsync(&hexec, ctx->d_exec.ptr, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (tests_executed_total) *tests_executed_total = (i64)hexec;
+    if (base) {
+        // only the valid prefix of each target's slot range holds variable ids
+        std::vector<i64> pcc(n_targets), tpcc(n_targets);
+        CK(cudaMemcpy(pcc.data(), dpcc.ptr, sizeof(i64) * n_targets, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(tpcc.data(), dtpcc.ptr, sizeof(i64) * n_targets, cudaMemcpyDeviceToHost));
+        for (i64 t = 0; t < n_targets; ++t) {
+            if (pc_nbr) for (i64 i = 0; i < pcc[t]; ++i) pc_nbr[hoff[t] + i] += base;
+            if (tpc_nbr) for (i64 i = 0; i < tpcc[t]; ++i) tpc_nbr[hoff[t] + i] += base;
+        }
+    }
+    return FW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+/* fwgpu.h — C ABI of libfwgpu.so: the B200 (sm_100a) conditional-independence test engine
+ * that replaces the inner test batches of FlashWeave.jl's HITON-PC skeleton search.
+ *
+ * The reference has no FFI of its own; its seam is a set of Julia generic functions
+ * (SURVEY.md §8b).  Each entry point below names the reference function it replaces
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the Julia `ccall`
+ * glue a maintainer would add.
+ *
+ * Conventions
+ *  - every function returns an int32 status (FW_OK = 0); nothing throws; the message of
+ *    the last failure on a context is fw_last_error(ctx) (fw_last_error(NULL) for
+ *    fw_create failures);
+ *  - one context per host worker, calls on a context are serialised by the caller
+ *    (mirrors one single-threaded Julia process per worker, src/interleaved.jl:90);
+ *  - matrices are column-major, n samples x p variables (Julia Matrix layout);
+ *  - variable indices are 0-based unless fw_set_index_base(ctx, 1) was called (the Julia
+ *    glue does that once);
+ *  - host pointers are borrowed for the duration of the call only;
+ *  - "insufficient power" is not an error: it is TestResult(0,1,0,false) as in the
+ *    reference (src/tests.jl:36-40, 58-62, 210-214, 258-262).
+ */
+#ifndef FWGPU_H
+#define FWGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fw_ctx fw_ctx;
+
+/* src/types.jl:140-145  struct TestResult {stat::Float64; pval::Float64; df::Int; suff_power::Bool}
+ * (isbits, 32 bytes with padding: identical layout, so a Julia Vector{TestResult} can be
+ * passed directly as the output buffer). */
+typedef struct fw_test_result {
+    double stat;
+    double pval;
+    int64_t df;
+    uint8_t suff_power;
+    uint8_t pad_[7];
+} fw_test_result;
+
+/* test_name strings of the reference (src/types.jl:64-72) */
+enum fw_test_kind { FW_MI = 0, FW_MI_NZ = 1, FW_FZ = 2, FW_FZ_NZ = 3 };
+
+enum fw_status {
+    FW_OK = 0,
+    FW_ERR_INVALID = 1,      /* bad argument */
+    FW_ERR_CUDA = 2,         /* CUDA runtime / driver failure (message has the CUDA error string) */
+    FW_ERR_STATE = 3,        /* call order: e.g. tests before data / cor_mat were provided */
+    FW_ERR_UNSUPPORTED = 4,  /* e.g. max_k > 3 */
+    FW_ERR_NOMEM = 5
+};
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+int32_t fw_create(int32_t device, fw_ctx** out);
+int32_t fw_destroy(fw_ctx* ctx);
+const char* fw_last_error(fw_ctx* ctx);
+int32_t fw_set_index_base(fw_ctx* ctx, int32_t base);          /* 0 (default) or 1 */
+/* cudaStream_t all kernels of this context are launched on (for CUDA-event timing). */
+void* fw_stream(fw_ctx* ctx);
+int32_t fw_synchronize(fw_ctx* ctx);
+/* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
+int64_t fw_launch_count(fw_ctx* ctx);
+
+/* ---- data (the `data` argument of every reference test function) ----------------------- */
+/* continuous table (fz / fz_nz): Matrix{Float32}, prec=32 (src/learning.jl:470, misc.jl:54-62) */
+int32_t fw_set_data_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, int64_t ld);
+/* discrete table (mi / mi_nz): Matrix{Int32} level codes >= 0 */
+int32_t fw_set_data_i32(fw_ctx* ctx, const int32_t* host, int64_t n, int64_t p, int64_t ld);
+/* same, device-resident inputs owned by the caller (e.g. a tensor that was NCCL-broadcast);
+ * the pointer must stay valid until the next fw_set_data / fw_adopt_data / fw_destroy */
+int32_t fw_adopt_data_f32_device(fw_ctx* ctx, const float* dev, int64_t n, int64_t p, int64_t ld);
+/* number of observations used by Fisher-z tests when only a cor_mat is installed
+ * (size(data,1) in src/tests.jl:150,256) */
+int32_t fw_set_n_obs(fw_ctx* ctx, int64_t n);
+
+/* ---- precompute (src/learning.jl:33-47 prepare_lgl) ------------------------------------ */
+/* get_levels / get_max_vals, src/misc.jl:64-97 */
+int32_t fw_levels(fw_ctx* ctx, int32_t* levels, int32_t* max_vals);
+/* cor_mat = convert(Matrix{Float32}, cor(data)), src/learning.jl:42-44.  Computed on the
+ * tensor cores from the resident table and kept resident; host_out may be NULL. */
+int32_t fw_cor_matrix(fw_ctx* ctx, float* host_out);
+/* install a caller-provided cor_mat (the `cor_mat` field of FzTest/FzTestCond, src/types.jl:126-136) */
+int32_t fw_set_cor_f32(fw_ctx* ctx, const float* host_cor, int64_t p);
+int32_t fw_adopt_cor_device(fw_ctx* ctx, const float* dev_cor, int64_t p);
+/* device pointer of the resident cor_mat (p*p floats), e.g. to broadcast it with NCCL */
+void* fw_cor_device_ptr(fw_ctx* ctx);
+
+/* ---- single tests ---------------------------------------------------------------------- */
+/* test(X, Y, Zs, data, test_obj, ...) for a batch of independent tests
+ * (src/tests.jl:28 / :108 with k = 0, :184 / :250 with k in 1..3).  Zs is n_tests x 3,
+ * row-major, entries beyond k[i] ignored.  Row trimming for the _nz kinds is applied by
+ * the engine exactly as the callers in src/tests.jl:412-416 and src/hiton.jl:41-50,85 do. */
+int32_t fw_test_batch(fw_ctx* ctx, int32_t kind, int64_t n_tests, const int64_t* X, const int64_t* Y,
+                      const int32_t* k, const int64_t* Zs, int64_t hps, int64_t n_obs_min,
+                      fw_test_result* out);
+
+/* ---- subset search: drop-in for test_subsets, src/tests.jl:281-346 ---------------------- */
+/* Returns what the reference returns: the first non-significant result in the reference's
+ * enumeration order (subset size max_k..1, lexicographic in Z_total's order), or the
+ * maximum-p-value result (ties: later subset) when all are significant; out_Zs[0..out_k)
+ * the subset; num_tests as counted at src/tests.jl:322; frac = num_tests / total.
+ * Empty Z_total gives the sentinel (NaN, NaN, -1, true), Zs = (-1,), num_tests = -1, frac = NaN. */
+int32_t fw_test_subsets(fw_ctx* ctx, int32_t kind, int64_t X, int64_t Y, const int64_t* Z_total, int64_t m,
+                        int32_t max_k, double alpha, int64_t hps, int64_t n_obs_min, int64_t max_tests,
+                        fw_test_result* out_result, int64_t* out_Zs, int32_t* out_k,
+                        int64_t* num_tests, double* frac);
+/* many (X, Y, Z_total) jobs in one launch; Z lists as CSR (z_off[n_jobs+1], z_idx[]) */
+int32_t fw_test_subsets_batch(fw_ctx* ctx, int32_t kind, int64_t n_jobs, const int64_t* X, const int64_t* Y,
+                              const int64_t* z_off, const int64_t* z_idx,
+                              int32_t max_k, double alpha, int64_t hps, int64_t n_obs_min, int64_t max_tests,
+                              fw_test_result* out_result, int64_t* out_Zs, int32_t* out_k,
+                              int64_t* num_tests, double* frac);
+
+/* ---- pairwise stage: pw_univar_neighbors, src/tests.jl:436-532 -------------------------- */
+/* All p(p-1)/2 univariate tests, Benjamini-Hochberg (src/statfuns.jl:326-350) when fdr != 0,
+ * neighbour lists (var -> nbr -> (stat, adjusted p)), neighbours in ascending index
+ * (src/tests.jl:372-388).  The result stays resident on the device (it feeds fw_hiton_pc)
+ * and can be copied out as CSR. */
+int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_t n_obs_min,
+                    int32_t fdr, int32_t correct_reliable_only, int64_t* n_entries);
+int32_t fw_pairwise_copy(fw_ctx* ctx, int64_t* offsets /* p+1 */, int64_t* nbr, double* stat, double* adjp);
+/* install caller-provided neighbour lists (the `all_univar_nbrs` argument of LGL, src/learning.jl:213,235-242) */
+int32_t fw_set_univar_nbrs(fw_ctx* ctx, const int64_t* offsets /* p+1 */, const int64_t* nbr,
+                           const double* stat, const double* adjp);
+/* counters of the last fw_pairwise: tests evaluated, reliable (non-NaN) tests = BH's m, raw p < alpha */
+int32_t fw_pairwise_stats(fw_ctx* ctx, int64_t* n_tests, int64_t* n_reliable, int64_t* n_raw_sig);
+
+/* ---- per-target loop: si_HITON_PC, src/hiton.jl:283-400 (time_limit = 0, no white/blacklist) ---- */
+/* Runs interleaving + elimination for every target in targets[] on the device, one CTA per
+ * target, against the resident neighbour lists (fw_pairwise / fw_set_univar_nbrs).
+ * Outputs per target t (slot range pc_off[t]..pc_off[t+1], capacity = its candidate count):
+ *   PC  = HitonState.state_results (after update_PC_dict!, src/hiton.jl:249-256), insertion order
+ *   TPC = HitonState.inter_results
+ *   num_tests[t] = sum of test_subsets' num_tests (src/tests.jl:322) over the target's candidates.
+ * Any output pointer may be NULL. */
+int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t* targets,
+                    int32_t max_k, double alpha, int64_t hps, int64_t n_obs_min, int64_t max_tests,
+                    int64_t* pc_off /* n_targets+1 */, int64_t* pc_count, int64_t* pc_nbr, double* pc_stat, double* pc_p,
+                    int64_t* tpc_count, int64_t* tpc_nbr, double* tpc_stat, double* tpc_p,
+                    int64_t* num_tests, int64_t* tests_executed_total);
+/* capacity query for the arrays above: sum over targets of their candidate counts */
+int32_t fw_hiton_pc_capacity(fw_ctx* ctx, int64_t n_targets, const int64_t* targets, int64_t* capacity);
+
+/* build information: "sm_100a", compiler version */
+const char* fw_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FWGPU_H */

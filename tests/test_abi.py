@@ -1,0 +1,70 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol that
+include/fwgpu.h declares, and fails loudly (no CPU fallback) without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import fwload
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def fw():
+    import __graft_entry__ as ge
+    ge.build()
+    return fwload.load()
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "fwgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fw_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(fw):
+    L = fw.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for s in declared:
+        assert hasattr(L, s), "libfwgpu.so does not export %s" % s
+    assert sorted(fw.ABI_SYMBOLS) == declared
+
+
+def test_testresult_layout(fw):
+    # src/types.jl:140-145: isbits {Float64, Float64, Int64, Bool} = 32 bytes with padding
+    assert C.sizeof(fw.TestResult) == 32
+    assert fw.TestResult.pval.offset == 8 and fw.TestResult.df.offset == 16 and fw.TestResult.suff_power.offset == 24
+
+
+def test_no_cpu_fallback(fw):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(fw.FwError) as ei:
+        fw.Engine(0)
+    assert "no CUDA device" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under flashweave.jl_b200/ may import, link or dlopen it."""
+    pkg = os.path.join(ROOT, "flashweave.jl_b200")
+    bad = re.compile(r"from\s+oracle|import\s+oracle|liboracle|\bfwo\b|#include\s+\"[^\"]*oracle")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not bad.search(txt), f
+
+
+def test_host_graph_assembly(fw):
+    import numpy as np
+    # two targets, one edge seen from both sides with different weights -> larger |w| wins (misc.jl:201-218)
+    res = fw.HitonResult(np.array([0, 1]), np.array([0, 1, 2]), np.array([1, 1]), np.array([1, 0]), np.array([0.2, 0.5]), np.array([1e-3, 1e-4]),
+                         np.array([0, 0]), None, None, None, np.array([3, 4]), 7)
+    uni = fw.NbrCSR(np.array([0, 1, 2]), np.array([1, 0]), np.array([0.3, 0.3]), np.array([1e-5, 1e-5]))
+    assert fw.assemble_graph(res, uni, "fz") == [(0, 1, 0.5)]
+    assert list(fw.target_order(fw.NbrCSR(np.array([0, 2, 2, 3]), None, None, None))) == [1, 2, 0]
+    assert list(fw.shard_targets(np.arange(10), 1, 4)) == [1, 5, 9]
