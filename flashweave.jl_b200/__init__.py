@@ -31,7 +31,8 @@ FW_OK = 0
 
 # every symbol include/fwgpu.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "fw_create", "fw_destroy", "fw_last_error", "fw_set_index_base", "fw_stream", "fw_synchronize", "fw_launch_count",
+    "fw_create", "fw_destroy", "fw_last_error", "fw_set_index_base", "fw_stream", "fw_synchronize", "fw_launch_count", "fw_last_timing",
+    "fw_hiton_exec_by_k",
     "fw_set_data_f32", "fw_set_data_i32", "fw_adopt_data_f32_device", "fw_set_n_obs", "fw_levels", "fw_cor_matrix",
     "fw_set_cor_f32", "fw_adopt_cor_device", "fw_cor_device_ptr", "fw_test_batch", "fw_test_subsets", "fw_test_subsets_batch",
     "fw_pairwise", "fw_pairwise_copy", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_capacity",
@@ -78,6 +79,8 @@ def load_library():
         "fw_stream": (vp, [vp]),
         "fw_synchronize": (i32, [vp]),
         "fw_launch_count": (i64, [vp]),
+        "fw_last_timing": (i32, [vp, vp, i32]),
+        "fw_hiton_exec_by_k": (i32, [vp, vp]),
         "fw_set_data_f32": (i32, [vp, vp, i64, i64, i64]),
         "fw_set_data_i32": (i32, [vp, vp, i64, i64, i64]),
         "fw_adopt_data_f32_device": (i32, [vp, vp, i64, i64, i64]),
@@ -193,6 +196,17 @@ class Engine:
 
     def launch_count(self):
         return int(self.L.fw_launch_count(self.h))
+
+    def last_timing(self):
+        """device ms of the last cor / pairwise / hiton phases (CUDA events on the engine's stream)"""
+        out = np.zeros(4)
+        self._ck(self.L.fw_last_timing(self.h, _p(out), 4))
+        return {"cor_ms": out[0], "pairwise_ms": out[1], "hiton_ms": out[2]}
+
+    def hiton_exec_by_k(self):
+        out = np.zeros(3, np.int64)
+        self._ck(self.L.fw_hiton_exec_by_k(self.h, _p(out)))
+        return out
 
     # -- data -----------------------------------------------------------------------------
     def set_data(self, data, kind):

@@ -63,6 +63,11 @@ struct fw_ctx {
     DevBuf<i64> d_uni_off, d_uni_nbr; DevBuf<double> d_uni_stat, d_uni_p;
     std::vector<i64> h_uni_off; i64 uni_entries = -1;
     i64 pw_tests = 0, pw_reliable = 0, pw_raw_sig = 0;
+    i64 exec_by_k[3] = {0, 0, 0};     // tests executed by the last fw_hiton_pc with |Zs| = 1, 2, 3
+
+    // per-phase device timing (CUDA events on `stream`), see fw_last_timing
+    cudaEvent_t ev[8] = {nullptr};
+    bool ev_valid[4] = {false, false, false, false};
 
     // scratch
     DevBuf<int> d_counter; DevBuf<u64> d_exec;
@@ -122,11 +127,9 @@ static cudaError_t grid_for(K kernel, int threads, size_t smem, int sm_count, i6
 extern "C" {
 
 const char* fw_build_info(void) {
-    return "libfwgpu sm_100a nvcc " __VERSION__
-#ifdef __CUDACC_VER_MAJOR__
-        " cuda"
-#endif
-        ;
+#define FW_STR2(x) #x
+#define FW_STR(x) FW_STR2(x)
+    return "libfwgpu sm_100a, nvcc " FW_STR(__CUDACC_VER_MAJOR__) "." FW_STR(__CUDACC_VER_MINOR__) "." FW_STR(__CUDACC_VER_BUILD__) ", host gcc " __VERSION__;
 }
 
 int32_t fw_create(int32_t device, fw_ctx** out) {
@@ -149,6 +152,7 @@ int32_t fw_create(int32_t device, fw_ctx** out) {
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     if (ctx->d_counter.reserve(16) != cudaSuccess || ctx->d_exec.reserve(16) != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_NOMEM, "scratch allocation failed"); }
+    for (int i = 0; i < 8; ++i) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_CUDA, "cudaEventCreate failed"); }
     *out = ctx;
     return FW_OK;
 }
@@ -157,6 +161,7 @@ int32_t fw_destroy(fw_ctx* ctx) {
     if (!ctx) return FW_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     delete ctx;
     return FW_OK;
 }
@@ -171,6 +176,22 @@ int32_t fw_set_index_base(fw_ctx* ctx, int32_t base) {
 void* fw_stream(fw_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int32_t fw_synchronize(fw_ctx* ctx) { if (!ctx) return FW_ERR_INVALID; CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return FW_OK; }
 int64_t fw_launch_count(fw_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// device time (ms, CUDA events on the context's stream) of the last run of each phase:
+// out[0] = cor_mat kernels, out[1] = pairwise stage kernels, out[2] = HITON-PC kernel(s), out[3] = subset-search kernel(s); -1 = not run
+int32_t fw_last_timing(fw_ctx* ctx, double* out_ms, int32_t n) {
+    if (!ctx || !out_ms) return FW_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    for (int i = 0; i < n && i < 4; ++i) {
+        out_ms[i] = -1.0;
+        if (!ctx->ev_valid[i]) continue;
+        float ms = 0.f;
+        CK(cudaEventSynchronize(ctx->ev[2 * i + 1]));
+        CK(cudaEventElapsedTime(&ms, ctx->ev[2 * i], ctx->ev[2 * i + 1]));
+        out_ms[i] = (double)ms;
+    }
+    return FW_OK;
+}
 
 // ---- data -----------------------------------------------------------------------------
 int32_t fw_set_data_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, int64_t ld) {
@@ -233,9 +254,11 @@ int32_t fw_cor_matrix(fw_ctx* ctx, float* host_out) {
     if (!(ctx->d_cor.ptr && ctx->d_cor.owned && ctx->d_cor.cap >= (size_t)p * p)) CK(ctx->d_cor.reserve((size_t)p * p));
     std::string msg;
     int nl = 0;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     cudaError_t e = cor_gemm_run(ctx->cg, ctx->d_data_f32.ptr, ctx->n, p, ctx->ld, ctx->d_cor.ptr, ctx->sm_count, ctx->stream, &nl, &msg);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_cor_matrix: %s: %s", msg.c_str(), cudaGetErrorString(e));
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_valid[0] = true;
     ctx->cor_p = p;
     if (host_out) {
         CK(cudaMemcpyAsync(host_out, ctx->d_cor.ptr, sizeof(float) * (size_t)p * p, cudaMemcpyDeviceToHost, ctx->stream));
@@ -330,7 +353,7 @@ int32_t fw_test_subsets_batch(fw_ctx* ctx, int32_t kind, int64_t n_jobs, const i
     CK(cudaMemcpyAsync(dy.ptr, hy.data(), sizeof(i64) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dzo.ptr, z_off, sizeof(i64) * (n_jobs + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (nz) CK(cudaMemcpyAsync(dzi.ptr, hz.data(), sizeof(i64) * nz, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_exec.ptr, 0, sizeof(u64), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_exec.ptr, 0, 4 * sizeof(u64), ctx->stream));
     SubsetsArgs a;
     a.cor = ctx->d_cor.ptr; a.p = p; a.X = dx.ptr; a.Y = dy.ptr; a.z_off = dzo.ptr; a.z_idx = dzi.ptr;
     a.max_k = max_k; a.alpha = alpha; a.max_tests = max_tests; a.fc = make_fz_consts(ctx->n_obs, n_obs_min);
@@ -401,10 +424,12 @@ int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_
     PairwiseOut po;
     std::string msg; int nl = 0;
     FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     cudaError_t e = pairwise_fz_run(ctx->pw, ctx->d_cor.ptr, p, fc, ctx->n_obs, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0,
                                     ctx->sm_count, ctx->stream, &po, &nl, &msg);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_pairwise: %s: %s", msg.c_str(), cudaGetErrorString(e));
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->ev_valid[1] = true;
     // adopt the CSR
     CK(ctx->d_uni_off.reserve(p + 1)); CK(ctx->d_uni_nbr.reserve(po.n_entries)); CK(ctx->d_uni_stat.reserve(po.n_entries)); CK(ctx->d_uni_p.reserve(po.n_entries));
     CK(cudaMemcpyAsync(ctx->d_uni_off.ptr, po.d_off, sizeof(i64) * (p + 1), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -470,6 +495,12 @@ int32_t fw_pairwise_stats(fw_ctx* ctx, int64_t* n_tests, int64_t* n_reliable, in
 }
 
 // ---- HITON-PC -------------------------------------------------------------------------------
+int32_t fw_hiton_exec_by_k(fw_ctx* ctx, int64_t* out3) {
+    if (!ctx || !out3) return FW_ERR_INVALID;
+    for (int i = 0; i < 3; ++i) out3[i] = ctx->exec_by_k[i];
+    return FW_OK;
+}
+
 int32_t fw_hiton_pc_capacity(fw_ctx* ctx, int64_t n_targets, const int64_t* targets, int64_t* capacity) {
     if (!ctx) return FW_ERR_INVALID;
     NEED(ctx->uni_entries >= 0, FW_ERR_STATE, "fw_hiton_pc: no neighbour lists resident (fw_pairwise / fw_set_univar_nbrs)");
@@ -519,7 +550,7 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
     CK(dsel.reserve(n_targets)); CK(dorder.reserve(cap_total)); CK(dstatus.reserve(n_targets));
     CK(cudaMemcpyAsync(dt.ptr, ht.data(), sizeof(i64) * n_targets, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(doff.ptr, hoff.data(), sizeof(i64) * (n_targets + 1), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_exec.ptr, 0, sizeof(u64), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_exec.ptr, 0, 4 * sizeof(u64), ctx->stream));
     CK(cudaMemsetAsync(dpcc.ptr, 0, sizeof(i64) * n_targets, ctx->stream));
     CK(cudaMemsetAsync(dtpcc.ptr, 0, sizeof(i64) * n_targets, ctx->stream));
     CK(cudaMemsetAsync(dnt.ptr, 0, sizeof(i64) * n_targets, ctx->stream));
@@ -568,6 +599,7 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         pending[need <= 32 ? 0 : 1].push_back((int)t);
     }
     std::vector<int> hstatus(n_targets);
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     for (int c = 0; c < 5; ++c) {
         if (pending[c].empty()) continue;
         std::vector<int>& sel = pending[c];
@@ -597,6 +629,7 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         }
         ctx->launches++;
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[5], ctx->stream)); ctx->ev_valid[2] = true;
         CK(cudaMemcpyAsync(hstatus.data(), dstatus.ptr, sizeof(int) * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         for (int t : sel) if (hstatus[t] == 1) {
@@ -619,10 +652,11 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         if (tpc_stat) CK(cudaMemcpyAsync(tpc_stat, dtpcs.ptr, sizeof(double) * ne, cudaMemcpyDeviceToHost, ctx->stream));
         if (tpc_p) CK(cudaMemcpyAsync(tpc_p, dtpcp.ptr, sizeof(double) * ne, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    u64 hexec = 0;
-    CK(cudaMemcpyAsync(&hexec, ctx->d_exec.ptr, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    u64 hexec[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(hexec, ctx->d_exec.ptr, 4 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (tests_executed_total) *tests_executed_total = (i64)hexec;
+    if (tests_executed_total) *tests_executed_total = (i64)hexec[0];
+    for (int i = 0; i < 3; ++i) ctx->exec_by_k[i] = (i64)hexec[i + 1];
     if (base) {
         // only the valid prefix of each target's slot range holds variable ids
         std::vector<i64> pcc(n_targets), tpcc(n_targets);

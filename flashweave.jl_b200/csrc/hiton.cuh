@@ -32,7 +32,7 @@ struct HitonArgs {
     int* cand_order;
     i64* pc_nbr; double* pc_stat; double* pc_p; i64* pc_count;
     i64* tpc_nbr; double* tpc_stat; double* tpc_p; i64* tpc_count;
-    i64* num_tests; u64* executed_total;
+    i64* num_tests; u64* executed_total;      // executed_total[0] = all, [1..3] = by |Zs|
     int* status;                             // per target: 0 ok, 1 capacity overflow (re-run with larger cap)
 };
 
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
     __shared__ EvalOut ev;
     __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_accept;
     __shared__ i64 s_ntests;
-    __shared__ u64 s_exec;
+    __shared__ u64 s_exec, s_exk[3];
 
     float* R = a.gscratch ? a.gscratch + (size_t)blockIdx.x * cap * cap : Rs;
     const int ld = cap;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
         int* order = a.cand_order + o0;
 
         // ---- prepare_interleaving_phase (hiton.jl:199-220): p < alpha, stable sort by p ----
-        if (tid == 0) { s_nc = 0; s_M = 0; s_ntests = 0; s_exec = 0; }
+        if (tid == 0) { s_nc = 0; s_M = 0; s_ntests = 0; s_exec = 0; s_exk[0] = s_exk[1] = s_exk[2] = 0; }
         __syncthreads();
         for (int i = tid; i < n_uni; i += THREADS) {
             double pi = a.uni_p[e0 + i];
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
                 FzSlotTest tf; tf.r.R = R; tf.r.ld = ld; tf.x = 0; tf.y = ys; tf.fc = a.fc;
                 eval_subsets<THREADS, TPT>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
                 if (tid == 0) {
-                    s_ntests += ev.num_tests; s_exec += (u64)ev.executed;
+                    s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
                     if (ev.sig) { tpc_stat[M] = ev.stat; tpc_p[M] = ev.pval; s_accept = 1; }
                 }
             }
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
                 FzSlotTest tf; tf.r.R = R; tf.r.ld = ld; tf.x = 0; tf.y = c; tf.fc = a.fc;
                 eval_subsets<THREADS, TPT>(tf, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
                 if (tid == 0) {
-                    s_ntests += ev.num_tests; s_exec += (u64)ev.executed;
+                    s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
                     if (ev.sig) { pcs_stat[s_npc] = ev.stat; pcs_p[s_npc] = ev.pval; s_accept = 1; }
                 }
             }
@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
         if (tid == 0) {
             a.pc_count[tsel] = npc; a.tpc_count[tsel] = M; a.num_tests[tsel] = s_ntests; a.status[tsel] = 0;
             atomicAdd(a.executed_total, s_exec);
+            atomicAdd(a.executed_total + 1, s_exk[0]); atomicAdd(a.executed_total + 2, s_exk[1]); atomicAdd(a.executed_total + 3, s_exk[2]);
         }
     }
 }

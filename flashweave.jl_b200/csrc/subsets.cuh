@@ -20,6 +20,7 @@ struct EvalOut {
     i64 num_tests;      // tests.jl:322 counter at return
     i64 total;          // num_tests_total (tests.jl:310-333)
     i64 executed;       // tests actually evaluated on the device
+    i64 ex_k[3];        // ... of which with |Zs| = 1, 2, 3
 };
 
 struct EvalShared {
@@ -31,6 +32,12 @@ struct EvalShared {
 };
 
 struct SubsetCounts { i64 c3, c2, c1, total; };
+__device__ __forceinline__ void executed_by_k(const SubsetCounts& sc, i64 executed, i64* ex_k) {
+    i64 e3 = executed < sc.c3 ? executed : sc.c3;
+    i64 r = executed - e3;
+    i64 e2 = r < sc.c2 ? r : sc.c2;
+    ex_k[2] = e3; ex_k[1] = e2; ex_k[0] = r - e2;
+}
 __device__ __forceinline__ SubsetCounts subset_counts(int m, int max_k) {
     SubsetCounts s;
     s.c3 = (max_k >= 3) ? choose3(m) : 0;
@@ -100,7 +107,7 @@ __device__ void eval_subsets(const TestFn& test, const int* acc, int m, int max_
             out->stat = f_stat; out->pval = f_p; out->df = f_df; out->suff = f_suff;
             out->sig = ((f_p < alpha) && f_suff) ? 1 : 0;
             out->k = k; out->pos[0] = a; out->pos[1] = b; out->pos[2] = c;
-            out->num_tests = my_fail + 1; out->total = sc.total; out->executed = executed;
+            out->num_tests = my_fail + 1; out->total = sc.total; out->executed = executed; executed_by_k(sc, executed, out->ex_k);
         }
         __syncthreads();
         return;
@@ -128,7 +135,7 @@ __device__ void eval_subsets(const TestFn& test, const int* acc, int m, int max_
         out->stat = b_stat; out->pval = b_p; out->df = b_df; out->suff = 1;
         out->sig = (b_p < alpha) ? 1 : 0;
         out->k = k; out->pos[0] = a; out->pos[1] = b; out->pos[2] = c;
-        out->num_tests = limit; out->total = sc.total; out->executed = executed;
+        out->num_tests = limit; out->total = sc.total; out->executed = executed; executed_by_k(sc, executed, out->ex_k);
     }
     __syncthreads();
 }

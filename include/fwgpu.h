@@ -63,6 +63,9 @@ void* fw_stream(fw_ctx* ctx);
 int32_t fw_synchronize(fw_ctx* ctx);
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 int64_t fw_launch_count(fw_ctx* ctx);
+/* device time in ms (CUDA events on the context's stream) of the last run of each phase:
+ * out[0] cor_mat kernels, out[1] pairwise-stage kernels, out[2] HITON-PC kernel(s), out[3] reserved; -1 = not run */
+int32_t fw_last_timing(fw_ctx* ctx, double* out_ms, int32_t n);
 
 /* ---- data (the `data` argument of every reference test function) ----------------------- */
 /* continuous table (fz / fz_nz): Matrix{Float32}, prec=32 (src/learning.jl:470, misc.jl:54-62) */
@@ -141,6 +144,8 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
                     int64_t* pc_off /* n_targets+1 */, int64_t* pc_count, int64_t* pc_nbr, double* pc_stat, double* pc_p,
                     int64_t* tpc_count, int64_t* tpc_nbr, double* tpc_stat, double* tpc_p,
                     int64_t* num_tests, int64_t* tests_executed_total);
+/* tests executed by the last fw_hiton_pc with |Zs| = 1, 2, 3 (for the algorithmic-bytes figure of the roofline) */
+int32_t fw_hiton_exec_by_k(fw_ctx* ctx, int64_t* out3);
 /* capacity query for the arrays above: sum over targets of their candidate counts */
 int32_t fw_hiton_pc_capacity(fw_ctx* ctx, int64_t n_targets, const int64_t* targets, int64_t* capacity);
 

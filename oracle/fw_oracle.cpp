@@ -249,6 +249,7 @@ static void cor_columns(const Data& D, const Rows& R, const i64* vars, i64 nv, d
         for (i64 i = 0; i < m; ++i) { x[i] = col[R[i]] - mu; ss += x[i] * x[i]; }
         sd[a] = std::sqrt(ss);
     }
+#pragma omp parallel for schedule(dynamic, 4) if (nv > 64)
     for (i64 a = 0; a < nv; ++a) {
         out[a + a * nv] = 1.0;
         const double* xa = &xc[(size_t)(a * m)];
@@ -688,11 +689,22 @@ struct Edge { i64 a, b; double w; };
 // whitelist (interleaved.jl:60-86,113-179; used only to pin the oracle to the
 // committed edgelists).
 // ---------------------------------------------------------------------------------
+static double now_s() {
+#ifdef _OPENMP
+    return omp_get_wtime();
+#else
+    return 0.0;
+#endif
+}
+
 static void lgl(Ctx& c, Params P, int mode, std::vector<Edge>& edges, i64* cond_tests, i64* pair_tests, int n_threads,
-                const i64* target_subset, i64 n_target_subset, std::vector<HitonOut>* per_target_out) {
+                const i64* target_subset, i64 n_target_subset, std::vector<HitonOut>* per_target_out, double* phase_secs) {
     i64 p = c.D.p;
     NbrLists uni;
+    double t0 = now_s();
     pairwise(c, P, uni, nullptr, nullptr, pair_tests);
+    double t1 = now_s();
+    if (phase_secs) phase_secs[1] = t1 - t0;
     // learning.jl:97-98 target order: ascending univariate degree, stable
     std::vector<i64> order((size_t)p); std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](i64 a, i64 b) { return uni[(size_t)a].size() < uni[(size_t)b].size(); });
@@ -738,6 +750,7 @@ static void lgl(Ctx& c, Params P, int mode, std::vector<Edge>& edges, i64* cond_
         }
     }
     if (cond_tests) *cond_tests = total_tests;
+    if (phase_secs) phase_secs[2] = now_s() - t1;
     // weights + make_symmetric_graph (misc.jl:230-272), OR rule
     std::vector<std::map<i64, double>> W((size_t)p);
     for (i64 t = 0; t < p; ++t) for (const Nbr& nb : res[(size_t)t].PC) W[(size_t)t][nb.v] = make_weight(c.kind, nb, uni[(size_t)t]);
@@ -956,17 +969,18 @@ i64 fwo_hiton_pc(fwo_ctx* h, i64 T, const i64* uni_nbr, const double* uni_stat, 
 i64 fwo_lgl(fwo_ctx* h, int max_k, double alpha, i64 hps, i64 n_obs_min, i64 max_tests, int fdr, int mode, int n_threads,
             const i64* target_subset, i64 n_target_subset,
             i64* edge_a, i64* edge_b, double* edge_w, i64 max_edges, i64* cond_tests, i64* pair_tests,
-            i64* pc_offsets, i64* pc_nbr, double* pc_stat, double* pc_p, i64 max_pc) {
+            i64* pc_offsets, i64* pc_nbr, double* pc_stat, double* pc_p, i64 max_pc, double* phase_secs /* cor, pairwise, hiton */) {
     Ctx& c = h->c;
     Params P; P.kind = c.kind; P.max_k = max_k; P.alpha = alpha; P.hps = hps; P.max_tests = max_tests;
     P.fdr = fdr != 0; P.correct_reliable_only = true; P.fast_elim = true;
     P.n_obs_min = n_obs_min < 0 ? fwo_auto_n_obs_min(h, max_k, hps) : n_obs_min;
-    if (c.kind == FZ && !c.C.m) fwo_compute_cor(h);
 #ifdef _OPENMP
     if (n_threads > 0) omp_set_num_threads(n_threads);
 #endif
+    if (phase_secs) phase_secs[0] = phase_secs[1] = phase_secs[2] = 0.0;
+    if (c.kind == FZ && !c.C.m) { double t0 = now_s(); fwo_compute_cor(h); if (phase_secs) phase_secs[0] = now_s() - t0; }
     std::vector<Edge> edges; std::vector<HitonOut> per;
-    lgl(c, P, mode, edges, cond_tests, pair_tests, n_threads, target_subset, n_target_subset, &per);
+    lgl(c, P, mode, edges, cond_tests, pair_tests, n_threads, target_subset, n_target_subset, &per, phase_secs);
     if ((i64)edges.size() > max_edges) return -1;
     std::sort(edges.begin(), edges.end(), [](const Edge& x, const Edge& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
     for (size_t i = 0; i < edges.size(); ++i) { edge_a[i] = edges[i].a; edge_b[i] = edges[i].b; edge_w[i] = edges[i].w; }

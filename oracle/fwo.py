@@ -70,7 +70,7 @@ def lib():
         L.fwo_hiton_pc.argtypes = [p, i64, p, p, p, i64, C.c_int, dbl, i64, i64, i64, p, i64, p, p, p, p]
         L.fwo_lgl.restype = i64
         L.fwo_lgl.argtypes = [p, C.c_int, dbl, i64, i64, i64, C.c_int, C.c_int, C.c_int, p, i64,
-                              p, p, p, i64, p, p, p, p, p, p, i64]
+                              p, p, p, i64, p, p, p, p, p, p, i64, p]
         L.fwo_num_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -206,6 +206,7 @@ class Oracle:
         tg = None if targets is None else _i64(targets)
         pco = pcn = pcs = pcp = None
         max_pc = 0
+        secs = np.zeros(3)
         if want_pc:
             max_pc = cap * 2
             pco = np.zeros(p + 1, np.int64)
@@ -214,10 +215,11 @@ class Oracle:
             pcp = np.zeros(max_pc)
         ne = self.L.fwo_lgl(self.h, max_k, alpha, hps, n_obs_min, max_tests, int(fdr), {"single": 0, "single_il": 1}[mode], n_threads,
                             _ptr(tg), 0 if tg is None else len(tg), _ptr(ea), _ptr(eb), _ptr(ew), cap, C.byref(ct), C.byref(pt),
-                            _ptr(pco), _ptr(pcn), _ptr(pcs), _ptr(pcp), max_pc)
+                            _ptr(pco), _ptr(pcn), _ptr(pcs), _ptr(pcp), max_pc, _ptr(secs))
         assert ne >= 0, "edge capacity exceeded"
         res = {"edges": [(int(a), int(b), float(w)) for a, b, w in zip(ea[:ne], eb[:ne], ew[:ne])],
-               "cond_tests": int(ct.value), "pair_tests": int(pt.value)}
+               "cond_tests": int(ct.value), "pair_tests": int(pt.value),
+               "secs": {"cor": float(secs[0]), "pairwise": float(secs[1]), "hiton": float(secs[2])}}
         if want_pc:
             res["pc"] = (pco, pcn[:pco[-1]], pcs[:pco[-1]], pcp[:pco[-1]])
         return res
