@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -16,7 +17,7 @@
 #include "subsets.cuh"
 #include "hiton.cuh"
 #include "pairwise.cuh"
-#include "cor_gemm.cuh"
+#include "cor_tc.cuh"
 
 static_assert(sizeof(fw_test_result) == 32, "TestResult layout (src/types.jl:140-145)");
 static_assert(sizeof(DevResult) == 32, "DevResult layout");
@@ -72,7 +73,11 @@ struct fw_ctx {
     // scratch
     DevBuf<int> d_counter; DevBuf<u64> d_exec;
     PairwiseScratch pw;
-    CorGemmScratch cg;
+    cortc::Scratch tc;
+    // fw_hiton_pc work buffers (grow-only, reused across calls)
+    struct HitonBufs {
+        DevBuf<i64> dt, doff, dpcn, dtpcn, dpcc, dtpcc, dnt; DevBuf<double> dpcs, dpcp, dtpcs, dtpcp; DevBuf<int> dsel, dorder, dstatus; DevBuf<float> gs;
+    } hb;
 };
 
 static int fail(fw_ctx* c, int code, const char* fmt, ...) {
@@ -255,7 +260,7 @@ int32_t fw_cor_matrix(fw_ctx* ctx, float* host_out) {
     std::string msg;
     int nl = 0;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    cudaError_t e = cor_gemm_run(ctx->cg, ctx->d_data_f32.ptr, ctx->n, p, ctx->ld, ctx->d_cor.ptr, ctx->sm_count, ctx->stream, &nl, &msg);
+    cudaError_t e = cortc::run(ctx->tc, ctx->d_data_f32.ptr, ctx->n, p, ctx->ld, ctx->d_cor.ptr, ctx->stream, &nl, &msg);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_cor_matrix: %s: %s", msg.c_str(), cudaGetErrorString(e));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_valid[0] = true;
@@ -543,7 +548,10 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
     }
     const i64 cap_total = std::max<i64>(hoff[n_targets], 1);
 
-    DevBuf<i64> dt, doff, dpcn, dtpcn, dpcc, dtpcc, dnt; DevBuf<double> dpcs, dpcp, dtpcs, dtpcp; DevBuf<int> dsel, dorder, dstatus; DevBuf<float> gs;
+    fw_ctx::HitonBufs& B = ctx->hb;
+    DevBuf<i64>&dt = B.dt, &doff = B.doff, &dpcn = B.dpcn, &dtpcn = B.dtpcn, &dpcc = B.dpcc, &dtpcc = B.dtpcc, &dnt = B.dnt;
+    DevBuf<double>&dpcs = B.dpcs, &dpcp = B.dpcp, &dtpcs = B.dtpcs, &dtpcp = B.dtpcp;
+    DevBuf<int>&dsel = B.dsel, &dorder = B.dorder, &dstatus = B.dstatus; DevBuf<float>& gs = B.gs;
     CK(dt.reserve(n_targets)); CK(doff.reserve(n_targets + 1)); CK(dpcn.reserve(cap_total)); CK(dtpcn.reserve(cap_total));
     CK(dpcc.reserve(n_targets)); CK(dtpcc.reserve(n_targets)); CK(dnt.reserve(n_targets));
     CK(dpcs.reserve(cap_total)); CK(dpcp.reserve(cap_total)); CK(dtpcs.reserve(cap_total)); CK(dtpcp.reserve(cap_total));
