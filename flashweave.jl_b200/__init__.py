@@ -243,6 +243,13 @@ class Engine:
         self.kind, self.n, self.p = kind, n, p
         return self
 
+    def levels(self):
+        """get_levels / get_max_vals (misc.jl:64-97) of the resident discrete table"""
+        lv = np.zeros(self.p, np.int32)
+        mv = np.zeros(self.p, np.int32)
+        self._ck(self.L.fw_levels(self.h, _p(lv), _p(mv)))
+        return lv, mv
+
     def set_n_obs(self, n):
         self._ck(self.L.fw_set_n_obs(self.h, n))
         self.n = n

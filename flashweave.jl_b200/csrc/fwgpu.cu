@@ -18,6 +18,7 @@
 #include "hiton.cuh"
 #include "pairwise.cuh"
 #include "cor_tc.cuh"
+#include "mi.cuh"
 
 static_assert(sizeof(fw_test_result) == 32, "TestResult layout (src/types.jl:140-145)");
 static_assert(sizeof(DevResult) == 32, "DevResult layout");
@@ -56,6 +57,10 @@ struct fw_ctx {
     DevBuf<float> d_data_f32;
     DevBuf<int> d_data_i32;
     i64 n_obs = -1;                      // rows used by Fisher-z tests
+    // discrete table: bit planes + per-variable level statistics (mi.cuh)
+    DevBuf<unsigned int> d_planes; DevBuf<int> d_levels, d_maxvals, d_nnz, d_bad;
+    std::vector<int> h_levels, h_maxvals;
+    int disc_L = 0, disc_W = 0;
 
     // cor_mat
     DevBuf<float> d_cor; i64 cor_p = 0;
@@ -96,6 +101,15 @@ static FzConsts make_fz_consts(i64 n_rows, i64 n_obs_min) {
     fc.half_sqrt_sf = sf > 0 ? std::sqrt((double)sf) / 2.0 : 0.0;
     fc.rows_ok = n_rows >= n_obs_min ? 1 : 0;
     return fc;
+}
+
+static MiTable make_mi_table(const fw_ctx* c, int kind) {
+    MiTable t;
+    t.planes = c->d_planes.ptr; t.levels = c->d_levels.ptr; t.max_vals = c->d_maxvals.ptr; t.nnz = c->d_nnz.ptr;
+    t.p = c->p; t.n = (int)c->n; t.W = c->disc_W; t.L = c->disc_L; t.nz = (kind == FW_MI_NZ) ? 1 : 0;
+    const int rem = (int)(c->n & 31);
+    t.tail_mask = rem ? ((1u << rem) - 1u) : 0xffffffffu;
+    return t;
 }
 
 // ---- capacity classes shared by the subset-search and HITON launches -------------------------
@@ -221,6 +235,34 @@ int32_t fw_set_data_i32(fw_ctx* ctx, const int32_t* host, int64_t n, int64_t p, 
     CK(cudaSetDevice(ctx->device));
     CK(ctx->d_data_i32.reserve((size_t)n * p));
     CK(cudaMemcpy2DAsync(ctx->d_data_i32.ptr, n * sizeof(int), host, ld * sizeof(int), n * sizeof(int), p, cudaMemcpyHostToDevice, ctx->stream));
+    NEED(n < ((i64)1 << 31) - 64, FW_ERR_UNSUPPORTED, "fw_set_data_i32: more than 2^31 rows");
+    // get_levels / get_max_vals (src/misc.jl:64-97), then the bit-plane table
+    CK(ctx->d_levels.reserve(p)); CK(ctx->d_maxvals.reserve(p)); CK(ctx->d_nnz.reserve(p)); CK(ctx->d_bad.reserve(4));
+    CK(cudaMemsetAsync(ctx->d_bad.ptr, 0, sizeof(int), ctx->stream));
+    {
+        const int T = 256; const i64 blocks = (p * 32 + T - 1) / T;
+        mi_levels_kernel<<<(unsigned)blocks, T, 0, ctx->stream>>>(ctx->d_data_i32.ptr, n, n, p, ctx->d_levels.ptr, ctx->d_maxvals.ptr, ctx->d_nnz.ptr, ctx->d_bad.ptr);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    ctx->h_levels.resize(p); ctx->h_maxvals.resize(p);
+    int bad = 0;
+    CK(cudaMemcpyAsync(ctx->h_levels.data(), ctx->d_levels.ptr, sizeof(int) * p, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_maxvals.data(), ctx->d_maxvals.ptr, sizeof(int) * p, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&bad, ctx->d_bad.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->data_kind = -1;
+    NEED(!(bad & 1), FW_ERR_INVALID, "fw_set_data_i32: negative level codes");
+    int mx = 0; for (i64 v = 0; v < p; ++v) mx = std::max(mx, ctx->h_maxvals[v]);
+    NEED(mx + 1 <= FW_MAX_L, FW_ERR_UNSUPPORTED, "fw_set_data_i32: %d levels; the bit-plane engine supports at most %d (maximum(max_vals)+1)", mx + 1, FW_MAX_L);
+    ctx->disc_L = std::max(mx + 1, 2); ctx->disc_W = (int)((n + 31) / 32);
+    CK(ctx->d_planes.reserve((size_t)p * (ctx->disc_L - 1) * ctx->disc_W));
+    {
+        const int T = 256; const i64 warps = p * ctx->disc_W; const i64 blocks = (warps * 32 + T - 1) / T;
+        mi_pack_planes_kernel<<<(unsigned)blocks, T, 0, ctx->stream>>>(ctx->d_data_i32.ptr, n, n, p, ctx->disc_L, ctx->disc_W, ctx->d_planes.ptr);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
     ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 1; ctx->n_obs = n;
     return FW_OK;
 }
@@ -228,8 +270,10 @@ int32_t fw_set_n_obs(fw_ctx* ctx, int64_t n) { if (!ctx) return FW_ERR_INVALID; 
 
 int32_t fw_levels(fw_ctx* ctx, int32_t* levels, int32_t* max_vals) {
     if (!ctx) return FW_ERR_INVALID;
-    (void)levels; (void)max_vals;
-    return fail(ctx, FW_ERR_UNSUPPORTED, "fw_levels: the discrete (mi / mi_nz) path is not built yet");
+    NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_levels: no discrete table resident (call fw_set_data_i32 first)");
+    if (levels) memcpy(levels, ctx->h_levels.data(), sizeof(int) * ctx->p);
+    if (max_vals) memcpy(max_vals, ctx->h_maxvals.data(), sizeof(int) * ctx->p);
+    return FW_OK;
 }
 
 // ---- cor_mat ----------------------------------------------------------------------------
@@ -276,14 +320,17 @@ int32_t fw_cor_matrix(fw_ctx* ctx, float* host_out) {
 int32_t fw_test_batch(fw_ctx* ctx, int32_t kind, int64_t n_tests, const int64_t* X, const int64_t* Y,
                       const int32_t* k, const int64_t* Zs, int64_t hps, int64_t n_obs_min, fw_test_result* out) {
     if (!ctx) return FW_ERR_INVALID;
-    (void)hps;
-    NEED(kind == FW_FZ, FW_ERR_UNSUPPORTED, "fw_test_batch: only kind FW_FZ is built yet (got %d)", kind);
+    NEED(kind == FW_FZ || kind == FW_MI || kind == FW_MI_NZ, FW_ERR_UNSUPPORTED, "fw_test_batch: kind %d is not built yet", kind);
     NEED(n_tests >= 0 && (n_tests == 0 || (X && Y && k && Zs && out)), FW_ERR_INVALID, "fw_test_batch: NULL argument");
-    NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_test_batch: no cor_mat resident (fw_cor_matrix / fw_set_cor_f32)");
-    NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_test_batch: number of observations unknown (fw_set_data_f32 / fw_set_n_obs)");
+    const bool disc = kind != FW_FZ;
+    if (disc) NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_test_batch: no discrete table resident (fw_set_data_i32)");
+    else {
+        NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_test_batch: no cor_mat resident (fw_cor_matrix / fw_set_cor_f32)");
+        NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_test_batch: number of observations unknown (fw_set_data_f32 / fw_set_n_obs)");
+    }
     if (n_tests == 0) return FW_OK;
     CK(cudaSetDevice(ctx->device));
-    const i64 p = ctx->cor_p, base = ctx->index_base;
+    const i64 p = disc ? ctx->p : ctx->cor_p, base = ctx->index_base;
     std::vector<i64> hx(n_tests), hy(n_tests), hz((size_t)n_tests * 3);
     for (i64 t = 0; t < n_tests; ++t) {
         NEED(k[t] >= 0 && k[t] <= 3, FW_ERR_UNSUPPORTED, "fw_test_batch: |Zs| = %d not in 0..3", k[t]);
@@ -301,9 +348,17 @@ int32_t fw_test_batch(fw_ctx* ctx, int32_t kind, int64_t n_tests, const int64_t*
     CK(cudaMemcpyAsync(dy.ptr, hy.data(), sizeof(i64) * n_tests, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dz.ptr, hz.data(), sizeof(i64) * n_tests * 3, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dk.ptr, k, sizeof(int) * n_tests, cudaMemcpyHostToDevice, ctx->stream));
-    FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
-    int threads = 128; i64 blocks = (n_tests + threads - 1) / threads;
-    fz_test_batch_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->d_cor.ptr, p, n_tests, dx.ptr, dy.ptr, dk.ptr, dz.ptr, fc, ctx->n_obs, n_obs_min, dout.ptr);
+    if (disc) {
+        MiTable t = make_mi_table(ctx, kind);
+        const int WARPS = 8;
+        size_t smem = (size_t)WARPS * t.L * t.L * t.L * t.L * t.L * sizeof(int);
+        i64 blocks = std::min<i64>((n_tests + WARPS - 1) / WARPS, (i64)ctx->sm_count * 8);
+        mi_test_batch_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, smem, ctx->stream>>>(t, n_tests, dx.ptr, dy.ptr, dk.ptr, dz.ptr, hps, n_obs_min, dout.ptr);
+    } else {
+        FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
+        int threads = 128; i64 blocks = (n_tests + threads - 1) / threads;
+        fz_test_batch_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->d_cor.ptr, p, n_tests, dx.ptr, dy.ptr, dk.ptr, dz.ptr, fc, ctx->n_obs, n_obs_min, dout.ptr);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, dout.ptr, sizeof(DevResult) * n_tests, cudaMemcpyDeviceToHost, ctx->stream));

@@ -41,3 +41,19 @@ def binarize(x_pn):
     """C3: uint8(latent > column median) -> presence/absence codes (levels 2, max_val 1)."""
     med = np.median(x_pn, axis=1, keepdims=True)
     return (x_pn > med).astype(np.int32)
+
+
+def three_level(x_pn, zero_frac=0.4, seed=0):
+    """mi_nz-style codes: a fraction of structural zeros (absent), non-zeros binned to {1, 2} at the
+    per-variable median of the non-zero entries (the reference's clr_nonzero_binned form)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    p, n = x_pn.shape
+    out = np.zeros((p, n), np.int32)
+    present = rng.random((p, n)) >= zero_frac
+    for v in range(p):
+        nzv = x_pn[v][present[v]]
+        if nzv.size == 0:
+            continue
+        med = np.median(nzv)
+        out[v][present[v]] = 1 + (nzv > med)
+    return out

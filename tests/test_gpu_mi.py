@@ -1,0 +1,94 @@
+"""GPU parity tests of the discrete (mi / mi_nz) path through the C ABI against the CPU oracle.
+Bars: contingency-derived integers (df, suff_power, neighbour lists, test counts) exact; statistic and
+p-value to 1e-12 / 1e-10 relative (the summation order of the fp64 MI terms differs from the reference's loop)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import fwload
+from oracle import fwo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fw():
+    return fwload.load()
+
+
+@pytest.fixture(scope="module")
+def synth():
+    return fwload.load_sub("synth")
+
+
+@pytest.fixture(scope="module")
+def hmp(golden_dir):
+    return np.load(os.path.join(golden_dir, "hmp_inputs.npz"))
+
+
+def _close(a, b, rel):
+    if np.isnan(a) or np.isnan(b):
+        return np.isnan(a) and np.isnan(b)
+    return abs(a - b) <= rel * max(abs(a), abs(b)) + 1e-300
+
+
+def _same(g, w):
+    return _close(g[0], w[0], 1e-12) and _close(g[1], w[1], 1e-10) and g[2] == w[2] and g[3] == w[3]
+
+
+def _tables(synth, seed):
+    lat = np.concatenate([synth.clique(48, 700, B=8, seed=seed), synth.chain(32, 700, B=8, seed=seed + 1)])
+    b = synth.binarize(lat)
+    t = synth.three_level(lat, zero_frac=0.35, seed=seed)
+    t[3] = (t[3] > 0).astype(np.int32)        # a binary variable inside a 3-level table (offset rule, statfuns.jl:307-311)
+    t[5] = 0                                   # all-zero variable: levels 1
+    t[7] = np.where(t[7] == 1, 0, t[7])        # values {0, 2}: levels 2 but max_val 2
+    b[9] = 1                                   # constant variable
+    return b, t
+
+
+@pytest.mark.parametrize("kind", ["mi", "mi_nz"])
+def test_golden_discrete_tests(fw, hmp, golden_dir, kind):
+    exp = json.load(open(os.path.join(golden_dir, "tests_expected.json")))
+    x = np.ascontiguousarray(hmp[kind].T.astype(np.int32))
+    eng = fw.Engine(0)
+    eng.set_data_colmajor(x, kind)
+    ora = fwo.Oracle(x.T, kind)
+    lv, mv = eng.levels()
+    olv, omv = ora.levels()
+    assert (lv == olv).all() and (mv == omv).all()
+    got = eng.test_batch([0] * 49, list(range(1, 50)))
+    for g, w in zip(got, exp[f"exp_uni_{kind}"]):
+        assert abs(g[0] - w[0]) <= 1e-13 and abs(g[1] - w[1]) <= 1e-12 and g[2] == w[2] and g[3] == w[3], (g, w)
+    got = eng.test_batch([30, 30], [20, 20], [(6,), (6, 13, 17)])
+    for g, key in zip(got, [f"exp_condZ1_{kind}", f"exp_condZ3_{kind}"]):
+        w = exp[key][0]
+        assert abs(g[0] - w[0]) <= 1e-13 and abs(g[1] - w[1]) <= 1e-12 and g[2] == w[2] and g[3] == w[3], (g, w)
+
+
+@pytest.mark.parametrize("kind", ["mi", "mi_nz"])
+def test_random_discrete_tests(fw, synth, kind):
+    b, t = _tables(synth, 40)
+    x = b if kind == "mi" else t
+    eng = fw.Engine(0)
+    eng.set_data_colmajor(x, kind)
+    ora = fwo.Oracle(x.T, kind)
+    rng = np.random.default_rng(3)
+    p = x.shape[0]
+    X, Y, Zs = [], [], []
+    for _ in range(1500):
+        k = int(rng.integers(0, 4))
+        v = rng.choice(p, size=2 + k, replace=False)
+        X.append(int(v[0])); Y.append(int(v[1])); Zs.append(tuple(int(z) for z in v[2:]))
+    for trip in [(3, 1, ()), (1, 3, (2,)), (5, 1, ()), (1, 5, (2, 3)), (7, 1, (2,)), (1, 7, ()), (9, 1, ()), (1, 2, (9, 3)), (3, 7, (5, 9, 1))]:
+        X.append(trip[0]); Y.append(trip[1]); Zs.append(trip[2])
+    for hps, nom in [(5, 0), (5, 160), (1, 20)]:
+        got = eng.test_batch(X, Y, Zs, hps=hps, n_obs_min=nom)
+        n_pow = 0
+        for x_, y_, z_, g in zip(X, Y, Zs, got):
+            w = ora.test_cond(x_, y_, list(z_), hps=hps, n_obs_min=nom, max_k=3) if z_ else ora.test_uni(x_, [y_], hps=hps, n_obs_min=nom)[0]
+            assert _same(g, w), (kind, x_, y_, z_, hps, nom, g, w)
+            n_pow += int(g[3])
+        assert 0 < n_pow < len(X)
