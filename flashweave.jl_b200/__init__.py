@@ -387,7 +387,8 @@ class Engine:
         """learning.jl:203-279 with parallel="single": cor -> pairwise -> HITON-PC per target -> OR-rule graph."""
         kind = kind or self.kind
         if n_obs_min < 0:
-            n_obs_min = auto_n_obs_min(kind, max_k, hps)
+            ml = int(self.levels()[0].max()) if kind in ("mi", "mi_nz") else None
+            n_obs_min = auto_n_obs_min(kind, max_k, hps, max_level=ml)
         if kind == "fz" and not self.L.fw_cor_device_ptr(self.h):
             self.cor(want_host=False)
         uni = self.pw_univar_neighbors(alpha=alpha, hps=hps, n_obs_min=n_obs_min, FDR=FDR, kind=kind)

@@ -19,6 +19,7 @@
 #include "pairwise.cuh"
 #include "cor_tc.cuh"
 #include "mi.cuh"
+#include "hiton_mi.cuh"
 
 static_assert(sizeof(fw_test_result) == 32, "TestResult layout (src/types.jl:140-145)");
 static_assert(sizeof(DevResult) == 32, "DevResult layout");
@@ -371,15 +372,18 @@ int32_t fw_test_subsets_batch(fw_ctx* ctx, int32_t kind, int64_t n_jobs, const i
                               int32_t max_k, double alpha, int64_t hps, int64_t n_obs_min, int64_t max_tests,
                               fw_test_result* out_result, int64_t* out_Zs, int32_t* out_k, int64_t* num_tests, double* frac) {
     if (!ctx) return FW_ERR_INVALID;
-    (void)hps;
-    NEED(kind == FW_FZ, FW_ERR_UNSUPPORTED, "fw_test_subsets: only kind FW_FZ is built yet (got %d)", kind);
+    NEED(kind == FW_FZ || kind == FW_MI || kind == FW_MI_NZ, FW_ERR_UNSUPPORTED, "fw_test_subsets: kind %d is not built yet", kind);
     NEED(max_k >= 1 && max_k <= 3, FW_ERR_UNSUPPORTED, "fw_test_subsets: max_k = %d not in 1..3", max_k);
     NEED(n_jobs >= 0 && (n_jobs == 0 || (X && Y && z_off && out_result && out_Zs && out_k && num_tests && frac)), FW_ERR_INVALID, "fw_test_subsets: NULL argument");
-    NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_test_subsets: no cor_mat resident");
-    NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_test_subsets: number of observations unknown");
+    const bool disc = kind != FW_FZ;
+    if (disc) NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_test_subsets: no discrete table resident (fw_set_data_i32)");
+    else {
+        NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_test_subsets: no cor_mat resident");
+        NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_test_subsets: number of observations unknown");
+    }
     if (n_jobs == 0) return FW_OK;
     CK(cudaSetDevice(ctx->device));
-    const i64 p = ctx->cor_p, base = ctx->index_base;
+    const i64 p = disc ? ctx->p : ctx->cor_p, base = ctx->index_base;
     const i64 nz = z_off[n_jobs];
     NEED(nz == 0 || z_idx, FW_ERR_INVALID, "fw_test_subsets: z_idx is NULL");
     std::vector<i64> hx(n_jobs), hy(n_jobs), hz((size_t)std::max<i64>(nz, 1));
@@ -414,6 +418,25 @@ int32_t fw_test_subsets_batch(fw_ctx* ctx, int32_t kind, int64_t n_jobs, const i
     CK(cudaMemcpyAsync(dzo.ptr, z_off, sizeof(i64) * (n_jobs + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (nz) CK(cudaMemcpyAsync(dzi.ptr, hz.data(), sizeof(i64) * nz, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_exec.ptr, 0, 4 * sizeof(u64), ctx->stream));
+    if (disc) {
+        SubsetsMiArgs ma;
+        ma.t = make_mi_table(ctx, kind); ma.hps = hps;
+        ma.X = dx.ptr; ma.Y = dy.ptr; ma.z_off = dzo.ptr; ma.z_idx = dzi.ptr; ma.n_jobs = (int)n_jobs; ma.counter = ctx->d_counter.ptr;
+        ma.max_k = max_k; ma.alpha = alpha; ma.max_tests = max_tests;
+        int need = 2; for (int c = 0; c < 5; ++c) for (int j : cls[c]) need = std::max<int>(need, (int)(z_off[j + 1] - z_off[j]) + 2);
+        ma.cap = need;
+        ma.out = dres.ptr; ma.out_Zs = dZs.ptr; ma.out_k = dk.ptr; ma.num_tests = dnt.ptr; ma.frac = dfr.ptr; ma.executed_total = ctx->d_exec.ptr;
+        const int TH = 256; const int L = ma.t.L;
+        size_t smem = ((sizeof(i64) * (need + 1) + sizeof(i64) * need + sizeof(int) * need + 15) & ~(size_t)15) + (size_t)(TH / 32) * L * L * L * L * L * sizeof(int) + 16;
+        NEED(smem <= 200 * 1024, FW_ERR_UNSUPPORTED, "fw_test_subsets: |Z_total| = %d exceeds the supported maximum", need - 2);
+        CK(cudaMemsetAsync(ctx->d_counter.ptr, 0, sizeof(int), ctx->stream));
+        int grid = 1;
+        CK(grid_for(subsets_mi_kernel<256, 1>, TH, smem, ctx->sm_count, n_jobs, &grid));
+        subsets_mi_kernel<256, 1><<<grid, TH, smem, ctx->stream>>>(ma);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        for (int c = 0; c < 5; ++c) cls[c].clear();
+    }
     SubsetsArgs a;
     a.cor = ctx->d_cor.ptr; a.p = p; a.X = dx.ptr; a.Y = dy.ptr; a.z_off = dzo.ptr; a.z_idx = dzi.ptr;
     a.max_k = max_k; a.alpha = alpha; a.max_tests = max_tests; a.fc = make_fz_consts(ctx->n_obs, n_obs_min);
@@ -475,18 +498,27 @@ int32_t fw_test_subsets(fw_ctx* ctx, int32_t kind, int64_t X, int64_t Y, const i
 int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_t n_obs_min,
                     int32_t fdr, int32_t correct_reliable_only, int64_t* n_entries) {
     if (!ctx) return FW_ERR_INVALID;
-    (void)hps;
-    NEED(kind == FW_FZ, FW_ERR_UNSUPPORTED, "fw_pairwise: only kind FW_FZ is built yet (got %d)", kind);
-    NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_pairwise: no cor_mat resident (fw_cor_matrix / fw_set_cor_f32)");
-    NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_pairwise: number of observations unknown");
+    NEED(kind == FW_FZ || kind == FW_MI || kind == FW_MI_NZ, FW_ERR_UNSUPPORTED, "fw_pairwise: kind %d is not built yet", kind);
+    const bool disc = kind != FW_FZ;
+    if (disc) NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_pairwise: no discrete table resident (fw_set_data_i32)");
+    else {
+        NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_pairwise: no cor_mat resident (fw_cor_matrix / fw_set_cor_f32)");
+        NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_pairwise: number of observations unknown");
+    }
     CK(cudaSetDevice(ctx->device));
-    const i64 p = ctx->cor_p;
+    const i64 p = disc ? ctx->p : ctx->cor_p;
     PairwiseOut po;
     std::string msg; int nl = 0;
-    FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    cudaError_t e = pairwise_fz_run(ctx->pw, ctx->d_cor.ptr, p, fc, ctx->n_obs, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0,
-                                    ctx->sm_count, ctx->stream, &po, &nl, &msg);
+    cudaError_t e;
+    if (disc) {
+        MiTable t = make_mi_table(ctx, kind);
+        e = pairwise_mi_run(ctx->pw, t, hps, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0, ctx->stream, &po, &nl, &msg);
+    } else {
+        FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
+        e = pairwise_fz_run(ctx->pw, ctx->d_cor.ptr, p, fc, ctx->n_obs, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0,
+                            ctx->sm_count, ctx->stream, &po, &nl, &msg);
+    }
     ctx->launches += nl;
     if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_pairwise: %s: %s", msg.c_str(), cudaGetErrorString(e));
     CK(cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->ev_valid[1] = true;
@@ -524,7 +556,7 @@ int32_t fw_pairwise_copy(fw_ctx* ctx, int64_t* offsets, int64_t* nbr, double* st
 
 int32_t fw_set_univar_nbrs(fw_ctx* ctx, const int64_t* offsets, const int64_t* nbr, const double* stat, const double* adjp) {
     if (!ctx) return FW_ERR_INVALID;
-    i64 p = ctx->cor_p > 0 ? ctx->cor_p : ctx->p;
+    i64 p = ctx->p > 0 ? ctx->p : ctx->cor_p;
     NEED(p > 0, FW_ERR_STATE, "fw_set_univar_nbrs: number of variables unknown (install data or cor_mat first)");
     NEED(offsets, FW_ERR_INVALID, "fw_set_univar_nbrs: offsets is NULL");
     CK(cudaSetDevice(ctx->device));
@@ -582,16 +614,19 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
                     int64_t* tpc_count, int64_t* tpc_nbr, double* tpc_stat, double* tpc_p,
                     int64_t* num_tests, int64_t* tests_executed_total) {
     if (!ctx) return FW_ERR_INVALID;
-    (void)hps;
-    NEED(kind == FW_FZ, FW_ERR_UNSUPPORTED, "fw_hiton_pc: only kind FW_FZ is built yet (got %d)", kind);
+    NEED(kind == FW_FZ || kind == FW_MI || kind == FW_MI_NZ, FW_ERR_UNSUPPORTED, "fw_hiton_pc: kind %d is not built yet", kind);
     NEED(max_k >= 0 && max_k <= 3, FW_ERR_UNSUPPORTED, "fw_hiton_pc: max_k = %d not in 0..3", max_k);
-    NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_hiton_pc: no cor_mat resident");
+    const bool disc = kind != FW_FZ;
+    if (disc) NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_hiton_pc: no discrete table resident (fw_set_data_i32)");
+    else {
+        NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_hiton_pc: no cor_mat resident");
+        NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_hiton_pc: number of observations unknown");
+    }
     NEED(ctx->uni_entries >= 0, FW_ERR_STATE, "fw_hiton_pc: no neighbour lists resident (fw_pairwise / fw_set_univar_nbrs)");
-    NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_hiton_pc: number of observations unknown");
     NEED(n_targets >= 0 && (n_targets == 0 || targets), FW_ERR_INVALID, "fw_hiton_pc: NULL targets");
     if (n_targets == 0) { if (pc_off) pc_off[0] = 0; if (tests_executed_total) *tests_executed_total = 0; return FW_OK; }
     CK(cudaSetDevice(ctx->device));
-    const i64 p = ctx->cor_p, base = ctx->index_base;
+    const i64 p = disc ? ctx->p : ctx->cor_p, base = ctx->index_base;
     NEED((i64)ctx->h_uni_off.size() == p + 1, FW_ERR_STATE, "fw_hiton_pc: neighbour lists and cor_mat disagree on the number of variables");
 
     std::vector<i64> ht(n_targets), hoff(n_targets + 1);
@@ -644,6 +679,48 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         return FW_OK;
     }
 
+    if (disc) {
+        HitonMiArgs ma;
+        ma.t = make_mi_table(ctx, kind); ma.hps = hps;
+        ma.uni_off = ctx->d_uni_off.ptr; ma.uni_nbr = ctx->d_uni_nbr.ptr; ma.uni_stat = ctx->d_uni_stat.ptr; ma.uni_p = ctx->d_uni_p.ptr;
+        ma.targets = dt.ptr; ma.out_off = doff.ptr; ma.counter = ctx->d_counter.ptr;
+        ma.max_k = max_k; ma.alpha = alpha; ma.max_tests = max_tests;
+        ma.cand_order = dorder.ptr;
+        ma.pc_nbr = dpcn.ptr; ma.pc_stat = dpcs.ptr; ma.pc_p = dpcp.ptr; ma.pc_count = dpcc.ptr;
+        ma.tpc_nbr = dtpcn.ptr; ma.tpc_stat = dtpcs.ptr; ma.tpc_p = dtpcp.ptr; ma.tpc_count = dtpcc.ptr;
+        ma.num_tests = dnt.ptr; ma.executed_total = ctx->d_exec.ptr; ma.status = dstatus.ptr;
+        std::vector<int> sel(n_targets);
+        std::iota(sel.begin(), sel.end(), 0);
+        std::stable_sort(sel.begin(), sel.end(), [&](int x, int y) { return (hoff[x + 1] - hoff[x]) > (hoff[y + 1] - hoff[y]); });
+        i64 need = 2; for (i64 t = 0; t < n_targets; ++t) need = std::max<i64>(need, hoff[t + 1] - hoff[t] + 2);
+        const int TH = 256; const int L = ma.t.L;
+        const size_t tabs = (size_t)(TH / 32) * L * L * L * L * L * sizeof(int);
+        // optimistic capacity (accepted sets are far smaller than candidate lists); re-run overflowing targets with the full bound
+        int caps[2] = {(int)std::min<i64>(need, 64), (int)need};
+        CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+        std::vector<int> hstatus(n_targets);
+        for (int round = 0; round < 2 && !sel.empty(); ++round) {
+            ma.cap = caps[round];
+            size_t smem = sizeof(i64) * (ma.cap + 1) + 4 * sizeof(double) * ma.cap + sizeof(i64) * ma.cap + 2 * sizeof(int) * ma.cap + tabs + 16;
+            NEED(smem <= 220 * 1024, FW_ERR_UNSUPPORTED, "fw_hiton_pc: a target has %lld candidates; too many for the discrete kernel", (long long)need - 2);
+            int n_sel = (int)sel.size();
+            CK(cudaMemcpyAsync(dsel.ptr, sel.data(), sizeof(int) * n_sel, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_counter.ptr, 0, sizeof(int), ctx->stream));
+            ma.sel = dsel.ptr; ma.n_sel = n_sel;
+            int grid = 1;
+            CK(grid_for(hiton_mi_kernel<256, 1>, TH, smem, ctx->sm_count, n_sel, &grid));
+            hiton_mi_kernel<256, 1><<<grid, TH, smem, ctx->stream>>>(ma);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ctx->ev[5], ctx->stream)); ctx->ev_valid[2] = true;
+            CK(cudaMemcpyAsync(hstatus.data(), dstatus.ptr, sizeof(int) * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            std::vector<int> again;
+            for (int t : sel) if (hstatus[t] == 1) again.push_back(t);
+            NEED(again.empty() || round == 0, FW_ERR_UNSUPPORTED, "fw_hiton_pc: capacity overflow in the full-bound class");
+            sel.swap(again);
+        }
+    }
     HitonArgs a;
     a.cor = ctx->d_cor.ptr; a.p = p;
     a.uni_off = ctx->d_uni_off.ptr; a.uni_nbr = ctx->d_uni_nbr.ptr; a.uni_stat = ctx->d_uni_stat.ptr; a.uni_p = ctx->d_uni_p.ptr;
@@ -657,12 +734,12 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
     // capacity classes: a target needs at most (#candidates + 2) slots; start optimistic (<= 64) and
     // escalate the few targets whose accepted set outgrows the class
     std::vector<int> pending[5];
-    for (i64 t = 0; t < n_targets; ++t) {
+    for (i64 t = 0; t < n_targets && !disc; ++t) {
         i64 need = (hoff[t + 1] - hoff[t]) + 2;
         pending[need <= 32 ? 0 : 1].push_back((int)t);
     }
     std::vector<int> hstatus(n_targets);
-    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (!disc) CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     for (int c = 0; c < 5; ++c) {
         if (pending[c].empty()) continue;
         std::vector<int>& sel = pending[c];

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
                 for (int s = tid + THREADS; s < M; s += THREADS) acc[s] = s + 1;
                 __syncthreads();
                 FzSlotTest tf; tf.r.R = R; tf.r.ld = ld; tf.x = 0; tf.y = ys; tf.fc = a.fc;
-                eval_subsets<THREADS, TPT>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                eval_subsets<THREADS, TPT, 1>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
                 if (tid == 0) {
                     s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
                     if (ev.sig) { tpc_stat[M] = ev.stat; tpc_p[M] = ev.pval; s_accept = 1; }
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
                 if (tid == 0) { pcs_stat[s_npc] = tpc_stat[c - 1]; pcs_p[s_npc] = tpc_p[c - 1]; s_accept = 1; }   // support_dict = TPC_dict
             } else {
                 FzSlotTest tf; tf.r.R = R; tf.r.ld = ld; tf.x = 0; tf.y = c; tf.fc = a.fc;
-                eval_subsets<THREADS, TPT>(tf, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                eval_subsets<THREADS, TPT, 1>(tf, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
                 if (tid == 0) {
                     s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
                     if (ev.sig) { pcs_stat[s_npc] = ev.stat; pcs_p[s_npc] = ev.pval; s_accept = 1; }
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(THREADS) subsets_fz_kernel(SubsetsArgs a) {
         for (int s = tid; s < m; s += THREADS) acc[s] = s + 2;
         __syncthreads();
         FzSlotTest tf; tf.r.R = R; tf.r.ld = ld; tf.x = 0; tf.y = 1; tf.fc = a.fc;
-        eval_subsets<THREADS, TPT>(tf, acc, m, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+        eval_subsets<THREADS, TPT, 1>(tf, acc, m, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
         if (tid == 0) {
             a.out[job] = make_result(ev.stat, ev.pval, ev.df, ev.suff != 0);
             for (int i = 0; i < 3; ++i) a.out_Zs[job * 3 + i] = (i < ev.k) ? a.z_idx[z0 + ev.pos[i]] : -1;

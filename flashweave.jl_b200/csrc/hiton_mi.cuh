@@ -1,0 +1,285 @@
+// hiton_mi.cuh — device-resident si_HITON_PC (src/hiton.jl:283-400) and batched test_subsets
+// (src/tests.jl:281-346) for the discrete kinds (mi / mi_nz).  Same control skeleton as hiton.cuh; the
+// conditioning subsets of a candidate are evaluated one test per warp on the bit-plane table (mi.cuh).
+#pragma once
+#include "common.cuh"
+#include "mi.cuh"
+#include "subsets.cuh"
+#include "hiton.cuh"
+
+struct MiSlotTest {
+    MiTable t; const i64* var; int x, y; i64 hps; int* tab;
+    __device__ __forceinline__ MiResult operator()(int k, int za, int zb, int zc) const {
+        i64 Z[3] = {var[za], var[zb], var[zc]};
+        return mi_test_warp(t, var[x], var[y], Z, k, hps, 0, tab);
+    }
+};
+
+struct HitonMiArgs {
+    MiTable t; i64 hps;
+    const i64* uni_off; const i64* uni_nbr; const double* uni_stat; const double* uni_p;
+    const i64* targets; const int* sel; int n_sel; const i64* out_off; int* counter;
+    int max_k; double alpha; i64 max_tests; int cap;
+    int* cand_order;
+    i64* pc_nbr; double* pc_stat; double* pc_p; i64* pc_count;
+    i64* tpc_nbr; double* tpc_stat; double* tpc_p; i64* tpc_count;
+    i64* num_tests; u64* executed_total; int* status;
+};
+
+template <int THREADS, int TPT>
+__global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int cap = a.cap, L = a.t.L;
+    const int tab_ints = L * L * L * L * L;
+    size_t o = 0;
+    i64* tri_off = reinterpret_cast<i64*>(smem + o); o += sizeof(i64) * (cap + 1);
+    double* tpc_stat = reinterpret_cast<double*>(smem + o); o += sizeof(double) * cap;
+    double* tpc_p = reinterpret_cast<double*>(smem + o); o += sizeof(double) * cap;
+    double* pcs_stat = reinterpret_cast<double*>(smem + o); o += sizeof(double) * cap;
+    double* pcs_p = reinterpret_cast<double*>(smem + o); o += sizeof(double) * cap;
+    i64* var = reinterpret_cast<i64*>(smem + o); o += sizeof(i64) * cap;           // slot -> variable: 0 = T, 1..M members, M+1 candidate
+    int* acc = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;
+    int* pc_slot = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;
+    int* tabs = reinterpret_cast<int*>(smem + o);
+    int* tab = tabs + warp * tab_ints;
+    __shared__ EvalShared sh;
+    __shared__ EvalOut ev;
+    __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_accept;
+    __shared__ i64 s_ntests;
+    __shared__ u64 s_exec, s_exk[3];
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_ti = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int ti = s_ti;
+        if (ti >= a.n_sel) break;
+        const int tsel = a.sel[ti];
+        const i64 T = a.targets[tsel];
+        const i64 e0 = a.uni_off[T];
+        const int n_uni = (int)(a.uni_off[T + 1] - e0);
+        const i64 o0 = a.out_off[tsel];
+        int* order = a.cand_order + o0;
+        if (tid == 0) { s_nc = 0; s_M = 0; s_ntests = 0; s_exec = 0; s_exk[0] = s_exk[1] = s_exk[2] = 0; var[0] = T; }
+        __syncthreads();
+        // hiton.jl:182-183,300-302: a discrete target with fewer than 2 levels has no neighbours
+        if (a.t.levels[T] < 2) {
+            if (tid == 0) { a.pc_count[tsel] = 0; a.tpc_count[tsel] = 0; a.num_tests[tsel] = 0; a.status[tsel] = 0; }
+            continue;
+        }
+        for (int i = tid; i < n_uni; i += THREADS) {
+            double pi = a.uni_p[e0 + i];
+            if (pi < a.alpha) {
+                int rank = 0;
+                for (int j = 0; j < n_uni; ++j) {
+                    double pj = a.uni_p[e0 + j];
+                    if (pj < a.alpha && (pj < pi || (pj == pi && j < i))) ++rank;
+                }
+                order[rank] = i;
+                atomicAdd(&s_nc, 1);
+            }
+        }
+        __syncthreads();
+        const int n_c = s_nc;
+        bool overflow = false;
+        // ---- interleaving phase ----
+        for (int ci = 0; ci < n_c; ++ci) {
+            const int M = s_M;
+            if (M + 2 > cap) { overflow = true; break; }
+            const int ui = order[ci];
+            const i64 cand = a.uni_nbr[e0 + ui];
+            const int ys = M + 1;
+            if (tid == 0) { var[ys] = cand; s_accept = 0; }
+            __syncthreads();
+            if (M == 0) {
+                if (tid == 0) { tpc_stat[0] = a.uni_stat[e0 + ui]; tpc_p[0] = a.uni_p[e0 + ui]; s_accept = 1; }
+            } else {
+                for (int s = tid; s < M; s += THREADS) acc[s] = s + 1;
+                __syncthreads();
+                MiSlotTest tf; tf.t = a.t; tf.var = var; tf.x = 0; tf.y = ys; tf.hps = a.hps; tf.tab = tab;
+                eval_subsets<THREADS, TPT, 32>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                if (tid == 0) {
+                    s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
+                    if (ev.sig) { tpc_stat[M] = ev.stat; tpc_p[M] = ev.pval; s_accept = 1; }
+                }
+            }
+            __syncthreads();
+            if (s_accept) { if (tid == 0) s_M = M + 1; }      // var[M+1] already holds the candidate = member M
+            __syncthreads();
+        }
+        if (overflow) { if (tid == 0) a.status[tsel] = 1; continue; }
+        // ---- elimination phase ----
+        const int M = s_M;
+        for (int s = tid; s < M; s += THREADS) acc[s] = s + 1;
+        if (tid == 0) { s_macc = M; s_npc = 0; }
+        __syncthreads();
+        for (int c = 1; c <= M; ++c) {
+            if (tid == 0) {
+                int w = 0, macc = s_macc;
+                for (int j = 0; j < macc; ++j) { int v = acc[j]; if (v != c) acc[w++] = v; }
+                s_macc = w; s_accept = 0;
+            }
+            __syncthreads();
+            const int macc = s_macc;
+            if (macc == 0) {
+                if (tid == 0) { pcs_stat[s_npc] = tpc_stat[c - 1]; pcs_p[s_npc] = tpc_p[c - 1]; s_accept = 1; }
+            } else {
+                MiSlotTest tf; tf.t = a.t; tf.var = var; tf.x = 0; tf.y = c; tf.hps = a.hps; tf.tab = tab;
+                eval_subsets<THREADS, TPT, 32>(tf, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                if (tid == 0) {
+                    s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
+                    if (ev.sig) { pcs_stat[s_npc] = ev.stat; pcs_p[s_npc] = ev.pval; s_accept = 1; }
+                }
+            }
+            __syncthreads();
+            if (tid == 0 && s_accept) { acc[s_macc] = c; s_macc = s_macc + 1; pc_slot[s_npc] = c; s_npc = s_npc + 1; }
+            __syncthreads();
+        }
+        const int npc = s_npc;
+        for (int i = tid; i < npc; i += THREADS) {
+            int c = pc_slot[i];
+            double s = pcs_stat[i], pp = pcs_p[i];
+            double ts = tpc_stat[c - 1], tp = tpc_p[c - 1];
+            if (tp > pp || isnan(pp)) { s = ts; pp = tp; }
+            if (a.pc_nbr) { a.pc_nbr[o0 + i] = var[c]; a.pc_stat[o0 + i] = s; a.pc_p[o0 + i] = pp; }
+        }
+        for (int i = tid; i < M; i += THREADS) {
+            if (a.tpc_nbr) { a.tpc_nbr[o0 + i] = var[i + 1]; a.tpc_stat[o0 + i] = tpc_stat[i]; a.tpc_p[o0 + i] = tpc_p[i]; }
+        }
+        if (tid == 0) {
+            a.pc_count[tsel] = npc; a.tpc_count[tsel] = M; a.num_tests[tsel] = s_ntests; a.status[tsel] = 0;
+            atomicAdd(a.executed_total, s_exec);
+            atomicAdd(a.executed_total + 1, s_exk[0]); atomicAdd(a.executed_total + 2, s_exk[1]); atomicAdd(a.executed_total + 3, s_exk[2]);
+        }
+    }
+}
+
+struct SubsetsMiArgs {
+    MiTable t; i64 hps;
+    const i64* X; const i64* Y; const i64* z_off; const i64* z_idx;
+    int n_jobs; int* counter;
+    int max_k; double alpha; i64 max_tests; int cap;
+    DevResult* out; i64* out_Zs; int* out_k; i64* num_tests; double* frac; u64* executed_total;
+};
+
+template <int THREADS, int TPT>
+__global__ void __launch_bounds__(THREADS) subsets_mi_kernel(SubsetsMiArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int cap = a.cap, L = a.t.L;
+    const int tab_ints = L * L * L * L * L;
+    size_t o = 0;
+    i64* tri_off = reinterpret_cast<i64*>(smem + o); o += sizeof(i64) * (cap + 1);
+    i64* var = reinterpret_cast<i64*>(smem + o); o += sizeof(i64) * cap;
+    int* acc = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;
+    o = (o + 15) & ~(size_t)15;
+    int* tab = reinterpret_cast<int*>(smem + o) + warp * tab_ints;
+    __shared__ EvalShared sh;
+    __shared__ EvalOut ev;
+    __shared__ int s_ji;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_ji = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int job = s_ji;
+        if (job >= a.n_jobs) break;
+        const i64 z0 = a.z_off[job];
+        const int m = (int)(a.z_off[job + 1] - z0);
+        if (m == 0) continue;                                   // sentinel written by the host (tests.jl:285)
+        for (int s = tid; s < m + 2; s += THREADS) var[s] = s == 0 ? a.X[job] : (s == 1 ? a.Y[job] : a.z_idx[z0 + s - 2]);
+        for (int s = tid; s < m; s += THREADS) acc[s] = s + 2;
+        __syncthreads();
+        MiSlotTest tf; tf.t = a.t; tf.var = var; tf.x = 0; tf.y = 1; tf.hps = a.hps; tf.tab = tab;
+        eval_subsets<THREADS, TPT, 32>(tf, acc, m, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+        if (tid == 0) {
+            a.out[job] = make_result(ev.stat, ev.pval, ev.df, ev.suff != 0);
+            for (int i = 0; i < 3; ++i) a.out_Zs[job * 3 + i] = (i < ev.k) ? a.z_idx[z0 + ev.pos[i]] : -1;
+            a.out_k[job] = ev.k;
+            a.num_tests[job] = ev.num_tests;
+            a.frac[job] = (double)ev.num_tests / (double)ev.total;
+            atomicAdd(a.executed_total, (u64)ev.executed);
+        }
+    }
+}
+
+// ---- pairwise stage for the discrete kinds: one warp per pair, unordered emission of raw-significant pairs ----
+// (pw_univar_kernel!, tests.jl:410-433: X-trimmed view when needs_nz_view(X); add_pwresults_to_matrix!, :391-407)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) pw_mi_rows_kernel(MiTable t, i64 hps, i64 n_obs_min, double alpha, int reliable_only,
+                                                                u64* counters /* [0] emitted, [1] reliable */, i64 cap,
+                                                                int* c_x, int* c_y, double* c_p, double* c_stat) {
+    extern __shared__ int smem_tab[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* tab = smem_tab + warp * (t.L * t.L);
+    const i64 X = blockIdx.x;
+    i64 n_rel = 0;
+    for (i64 Y = X + 1 + warp; Y < t.p; Y += WARPS) {
+        MiResult r = mi_test_warp(t, X, Y, nullptr, 0, hps, n_obs_min, tab);
+        // unreliable tests become NaN and are excluded from BH's m (tests.jl:397-402, 521-526)
+        const bool rel = r.suff || !reliable_only;
+        n_rel += rel;
+        if (rel && r.pval < alpha && lane == 0) {
+            u64 pos = atomicAdd(&counters[0], 1ull);
+            if ((i64)pos < cap) { c_x[pos] = (int)X; c_y[pos] = (int)Y; c_p[pos] = r.pval; c_stat[pos] = r.stat; }
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && n_rel) atomicAdd(&counters[1], (u64)n_rel);
+}
+
+// pw_univar_neighbors for mi / mi_nz (tests.jl:436-532): all pairs -> raw-significant list -> condensed order -> BH + CSR
+static cudaError_t pairwise_mi_run(PairwiseScratch& S, const MiTable& t, i64 hps, i64 n_obs_min, double alpha, bool fdr, bool reliable_only,
+                                   cudaStream_t st, PairwiseOut* out, int* n_launch, std::string* msg) {
+    const int T = 256, WARPS = 8;
+    const i64 p = t.p, n_pairs = p * (p - 1) / 2;
+    out->n_tests = n_pairs;
+    u64* counters; PWCK(S.get(0, sizeof(u64) * 4, (void**)&counters), "alloc");
+    i64 cap = std::max<i64>((i64)1 << 16, std::min<i64>(n_pairs, n_pairs / 8 + 1024));
+    int *c_x, *c_y; double *c_p, *c_stat;
+    u64 h_cnt[2] = {0, 0};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        PWCK(S.get(7, sizeof(int) * cap, (void**)&c_x), "alloc");
+        PWCK(S.get(8, sizeof(int) * cap, (void**)&c_y), "alloc");
+        PWCK(S.get(9, sizeof(double) * cap, (void**)&c_p), "alloc");
+        PWCK(S.get(10, sizeof(double) * cap, (void**)&c_stat), "alloc");
+        PWCK(cudaMemsetAsync(counters, 0, sizeof(u64) * 4, st), "memset");
+        pw_mi_rows_kernel<WARPS><<<(unsigned)p, WARPS * 32, WARPS * t.L * t.L * sizeof(int), st>>>(t, hps, n_obs_min, alpha, reliable_only ? 1 : 0, counters, cap,
+                                                                                             c_x, c_y, c_p, c_stat);
+        (*n_launch)++;
+        PWCK(cudaGetLastError(), "pw_mi_rows_kernel");
+        PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 2, cudaMemcpyDeviceToHost, st), "d2h");
+        PWCK(cudaStreamSynchronize(st), "sync");
+        if ((i64)h_cnt[0] <= cap) break;
+        cap = (i64)h_cnt[0];
+    }
+    const i64 nf = (i64)h_cnt[0];
+    out->n_raw_sig = nf;
+    out->n_reliable = reliable_only ? (i64)h_cnt[1] : n_pairs;
+    const i64 m = reliable_only ? (i64)h_cnt[1] : n_pairs;             // tests.jl:521-526
+    i64* d_off; PWCK(S.get(6, sizeof(i64) * (p + 1), (void**)&d_off), "alloc");
+    out->d_off = d_off;
+    if (nf == 0) {
+        PWCK(cudaMemsetAsync(d_off, 0, sizeof(i64) * (p + 1), st), "memset");
+        out->n_entries = 0; out->d_nbr = nullptr; out->d_stat = nullptr; out->d_adjp = nullptr;
+        return cudaSuccess;
+    }
+    // restore condensed-index order (x, then y ascending): sort by x*p + y, gather
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    unsigned char* arena; PWCK(S.get(11, 2 * al(sizeof(u64) * nf) + 2 * al(sizeof(unsigned int) * nf), (void**)&arena), "alloc");
+    u64* keys = (u64*)arena; u64* keys2 = (u64*)(arena + al(sizeof(u64) * nf));
+    unsigned int* vals = (unsigned int*)(arena + 2 * al(sizeof(u64) * nf)); unsigned int* vals2 = (unsigned int*)(arena + 2 * al(sizeof(u64) * nf) + al(sizeof(unsigned int) * nf));
+    pw_pair_keys<<<pw_blocks(nf, T), T, 0, st>>>(c_x, c_y, p, keys, vals, nf); (*n_launch)++;
+    int end_bit = 1; while (((u64)1 << end_bit) < (u64)p * (u64)p && end_bit < 64) ++end_bit;
+    void* tmp = nullptr; size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys2, vals, vals2, (int)nf, 0, end_bit, st);
+    PWCK(S.get(5, need, &tmp), "alloc");
+    PWCK(cub::DeviceRadixSort::SortPairs(tmp, need, keys, keys2, vals, vals2, (int)nf, 0, end_bit, st), "sort"); (*n_launch) += 8;
+    unsigned char* ord; PWCK(S.get(15, 2 * al(sizeof(int) * nf) + 2 * al(sizeof(double) * nf), (void**)&ord), "alloc");
+    int* o_x = (int*)ord; int* o_y = (int*)(ord + al(sizeof(int) * nf));
+    double* o_p = (double*)(ord + 2 * al(sizeof(int) * nf)); double* o_s = (double*)(ord + 2 * al(sizeof(int) * nf) + al(sizeof(double) * nf));
+    pw_gather_pairs<<<pw_blocks(nf, T), T, 0, st>>>(vals2, c_x, c_y, c_p, c_stat, o_x, o_y, o_p, o_s, nf); (*n_launch)++;
+    PWCK(cudaGetLastError(), "pw_gather_pairs");
+    PWCK(cudaStreamSynchronize(st), "sync");      // the arena in slot 11 is re-used by pairwise_finish
+    return pairwise_finish(S, o_x, o_y, o_p, o_s, nf, m, p, alpha, fdr, st, out, n_launch, msg);
+}

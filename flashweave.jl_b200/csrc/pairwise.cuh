@@ -161,6 +161,81 @@ __global__ void pw_flags_to_i64(const unsigned char* keep, i64* out, i64 n) {
 
 static inline unsigned pw_blocks(i64 n, int t) { return (unsigned)((n + t - 1) / t); }
 
+// Common second half of the pairwise stage: Benjamini-Hochberg on the compacted raw-significant pairs (which must be in
+// condensed-index order: x ascending, then y ascending), then the symmetric neighbour CSR.
+static cudaError_t pairwise_finish(PairwiseScratch& S, int* c_x, int* c_y, double* c_p, double* c_stat, i64 nf, i64 m, i64 p, double alpha, bool fdr,
+                                   cudaStream_t st, PairwiseOut* out, int* n_launch, std::string* msg) {
+    const int T = 256;
+    void* tmp = nullptr; size_t tmp_bytes = 0, need = 0;
+    double *adj, *rev; unsigned char* keep; u64 *keys, *keys2; unsigned int *vals, *vals2; i64 *keep64, *keep_pos;
+    i64* d_off = out->d_off;
+    // one arena for the BH / CSR temporaries
+    size_t a_adj = sizeof(double) * nf, a_rev = sizeof(double) * nf, a_keep = (size_t)nf, a_keys = sizeof(u64) * 2 * nf, a_vals = sizeof(unsigned int) * 2 * nf, a_k64 = sizeof(i64) * nf;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t arena_bytes = al(a_adj) + al(a_rev) + al(a_keep) + 2 * al(a_keys) + 2 * al(a_vals) + 2 * al(a_k64);
+    unsigned char* arena; PWCK(S.get(11, arena_bytes, (void**)&arena), "alloc");
+    size_t o = 0;
+    adj = (double*)(arena + o); o += al(a_adj);
+    rev = (double*)(arena + o); o += al(a_rev);
+    keep = (unsigned char*)(arena + o); o += al(a_keep);
+    keys = (u64*)(arena + o); o += al(a_keys);
+    keys2 = (u64*)(arena + o); o += al(a_keys);
+    vals = (unsigned int*)(arena + o); o += al(a_vals);
+    vals2 = (unsigned int*)(arena + o); o += al(a_vals);
+    keep64 = (i64*)(arena + o); o += al(a_k64);
+    keep_pos = (i64*)(arena + o); o += al(a_k64);
+
+    if (fdr) {
+        pw_make_keys<<<pw_blocks(nf, T), T, 0, st>>>(c_p, keys, vals, nf); (*n_launch)++;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys2, vals, vals2, (int)nf, 0, 64, st);
+        if (need > tmp_bytes) { tmp_bytes = need; PWCK(S.get(5, tmp_bytes, &tmp), "alloc"); }
+        PWCK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)nf, 0, 64, st), "sort"); (*n_launch) += 8;
+        pw_bh_terms<<<pw_blocks(nf, T), T, 0, st>>>(keys2, rev, nf, (double)m); (*n_launch)++;
+        cub::DeviceScan::InclusiveScan(nullptr, need, rev, rev, MinOp(), (int)nf, st);
+        if (need > tmp_bytes) { tmp_bytes = need; PWCK(S.get(5, tmp_bytes, &tmp), "alloc"); }
+        PWCK(cub::DeviceScan::InclusiveScan(tmp, tmp_bytes, rev, rev, MinOp(), (int)nf, st), "minscan"); (*n_launch)++;
+        pw_bh_scatter<<<pw_blocks(nf, T), T, 0, st>>>(rev, vals2, nf, alpha, adj, keep); (*n_launch)++;
+    } else {
+        pw_nofdr_keep<<<pw_blocks(nf, T), T, 0, st>>>(c_p, nf, alpha, adj, keep); (*n_launch)++;
+    }
+    pw_flags_to_i64<<<pw_blocks(nf, T), T, 0, st>>>(keep, keep64, nf); (*n_launch)++;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, keep64, keep_pos, (int)nf, st);
+    if (need > tmp_bytes) { tmp_bytes = need; PWCK(S.get(5, tmp_bytes, &tmp), "alloc"); }
+    PWCK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, keep64, keep_pos, (int)nf, st), "scan"); (*n_launch)++;
+    i64 last_pos = 0; unsigned char last_keep = 0;
+    PWCK(cudaMemcpyAsync(&last_pos, keep_pos + nf - 1, sizeof(i64), cudaMemcpyDeviceToHost, st), "d2h");
+    PWCK(cudaMemcpyAsync(&last_keep, keep + nf - 1, 1, cudaMemcpyDeviceToHost, st), "d2h");
+    PWCK(cudaStreamSynchronize(st), "sync");
+    const i64 n_keep = last_pos + last_keep, ne = 2 * n_keep;
+    out->n_entries = ne;
+    if (ne == 0) { PWCK(cudaMemsetAsync(d_off, 0, sizeof(i64) * (p + 1), st), "memset"); return cudaSuccess; }
+    pw_emit_directed<<<pw_blocks(nf, T), T, 0, st>>>(c_x, c_y, keep, keep_pos, nf, p, keys, vals); (*n_launch)++;
+    int end_bit = 1; while (((u64)1 << end_bit) < (u64)p * (u64)p && end_bit < 64) ++end_bit;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys2, vals, vals2, (int)ne, 0, end_bit, st);
+    if (need > tmp_bytes) { tmp_bytes = need; PWCK(S.get(5, tmp_bytes, &tmp), "alloc"); }
+    PWCK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)ne, 0, end_bit, st), "sort"); (*n_launch) += 8;
+    i64* d_nbr; double *d_stat, *d_adjp;
+    PWCK(S.get(12, sizeof(i64) * ne, (void**)&d_nbr), "alloc");
+    PWCK(S.get(13, sizeof(double) * ne, (void**)&d_stat), "alloc");
+    PWCK(S.get(14, sizeof(double) * ne, (void**)&d_adjp), "alloc");
+    pw_fill_csr<<<pw_blocks(ne, T), T, 0, st>>>(keys2, vals2, ne, p, c_stat, adj, d_nbr, d_stat, d_adjp); (*n_launch)++;
+    pw_row_offsets<<<pw_blocks(p + 1, T), T, 0, st>>>(keys2, ne, p, d_off); (*n_launch)++;
+    PWCK(cudaGetLastError(), "csr kernels");
+    out->d_nbr = d_nbr; out->d_stat = d_stat; out->d_adjp = d_adjp;
+    return cudaSuccess;
+}
+
+// gather the unordered emission of the discrete pairwise kernel into condensed-index order
+__global__ void pw_pair_keys(const int* c_x, const int* c_y, i64 p, u64* keys, unsigned int* vals, i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = (u64)((i64)c_x[i] * p + c_y[i]); vals[i] = (unsigned int)i; }
+}
+__global__ void pw_gather_pairs(const unsigned int* perm, const int* sx, const int* sy, const double* sp, const double* ss,
+                                int* dx, int* dy, double* dp, double* ds, i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { unsigned int j = perm[i]; dx[i] = sx[j]; dy[i] = sy[j]; dp[i] = sp[j]; ds[i] = ss[j]; }
+}
+
 static cudaError_t pairwise_fz_run(PairwiseScratch& S, const float* d_cor, i64 p, FzConsts fc, i64 n_rows, i64 n_obs_min, double alpha,
                                    bool fdr, bool reliable_only, int sm_count, cudaStream_t st, PairwiseOut* out, int* n_launch, std::string* msg) {
     (void)sm_count;
@@ -221,7 +296,7 @@ static cudaError_t pairwise_fz_run(PairwiseScratch& S, const float* d_cor, i64 p
         out->n_entries = 0; out->d_nbr = nullptr; out->d_stat = nullptr; out->d_adjp = nullptr;
         return cudaSuccess;
     }
-    int *c_x, *c_y; double *c_p, *c_stat, *adj, *rev; unsigned char* keep; u64 *keys, *keys2; unsigned int *vals, *vals2; i64 *keep64, *keep_pos;
+    int *c_x, *c_y; double *c_p, *c_stat;
     PWCK(S.get(7, sizeof(int) * nf, (void**)&c_x), "alloc");
     PWCK(S.get(8, sizeof(int) * nf, (void**)&c_y), "alloc");
     PWCK(S.get(9, sizeof(double) * nf, (void**)&c_p), "alloc");
@@ -229,58 +304,5 @@ static cudaError_t pairwise_fz_run(PairwiseScratch& S, const float* d_cor, i64 p
     pw_fz_rows_kernel<T, 1><<<(unsigned)p, T, 0, st>>>(d_cor, p, fc, alpha, r_lo, reliable_only ? 1 : 0, suff_all, nullptr, nullptr, row_base, c_x, c_y, c_p, c_stat);
     (*n_launch)++;
     PWCK(cudaGetLastError(), "pw_fz_rows_kernel<1>");
-    // one arena for the BH / CSR temporaries
-    size_t a_adj = sizeof(double) * nf, a_rev = sizeof(double) * nf, a_keep = (size_t)nf, a_keys = sizeof(u64) * 2 * nf, a_vals = sizeof(unsigned int) * 2 * nf, a_k64 = sizeof(i64) * nf;
-    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    size_t arena_bytes = al(a_adj) + al(a_rev) + al(a_keep) + 2 * al(a_keys) + 2 * al(a_vals) + 2 * al(a_k64);
-    unsigned char* arena; PWCK(S.get(11, arena_bytes, (void**)&arena), "alloc");
-    size_t o = 0;
-    adj = (double*)(arena + o); o += al(a_adj);
-    rev = (double*)(arena + o); o += al(a_rev);
-    keep = (unsigned char*)(arena + o); o += al(a_keep);
-    keys = (u64*)(arena + o); o += al(a_keys);
-    keys2 = (u64*)(arena + o); o += al(a_keys);
-    vals = (unsigned int*)(arena + o); o += al(a_vals);
-    vals2 = (unsigned int*)(arena + o); o += al(a_vals);
-    keep64 = (i64*)(arena + o); o += al(a_k64);
-    keep_pos = (i64*)(arena + o); o += al(a_k64);
-
-    if (fdr) {
-        pw_make_keys<<<pw_blocks(nf, T), T, 0, st>>>(c_p, keys, vals, nf); (*n_launch)++;
-        cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys2, vals, vals2, (int)nf, 0, 64, st);
-        if (need > tmp_bytes) { tmp_bytes = need; PWCK(S.get(5, tmp_bytes, &tmp), "alloc"); }
-        PWCK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)nf, 0, 64, st), "sort"); (*n_launch) += 8;
-        pw_bh_terms<<<pw_blocks(nf, T), T, 0, st>>>(keys2, rev, nf, (double)m); (*n_launch)++;
-        cub::DeviceScan::InclusiveScan(nullptr, need, rev, rev, MinOp(), (int)nf, st);
-        if (need > tmp_bytes) { tmp_bytes = need; PWCK(S.get(5, tmp_bytes, &tmp), "alloc"); }
-        PWCK(cub::DeviceScan::InclusiveScan(tmp, tmp_bytes, rev, rev, MinOp(), (int)nf, st), "minscan"); (*n_launch)++;
-        pw_bh_scatter<<<pw_blocks(nf, T), T, 0, st>>>(rev, vals2, nf, alpha, adj, keep); (*n_launch)++;
-    } else {
-        pw_nofdr_keep<<<pw_blocks(nf, T), T, 0, st>>>(c_p, nf, alpha, adj, keep); (*n_launch)++;
-    }
-    pw_flags_to_i64<<<pw_blocks(nf, T), T, 0, st>>>(keep, keep64, nf); (*n_launch)++;
-    cub::DeviceScan::ExclusiveSum(nullptr, need, keep64, keep_pos, (int)nf, st);
-    if (need > tmp_bytes) { tmp_bytes = need; PWCK(S.get(5, tmp_bytes, &tmp), "alloc"); }
-    PWCK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, keep64, keep_pos, (int)nf, st), "scan"); (*n_launch)++;
-    i64 last_pos = 0; unsigned char last_keep = 0;
-    PWCK(cudaMemcpyAsync(&last_pos, keep_pos + nf - 1, sizeof(i64), cudaMemcpyDeviceToHost, st), "d2h");
-    PWCK(cudaMemcpyAsync(&last_keep, keep + nf - 1, 1, cudaMemcpyDeviceToHost, st), "d2h");
-    PWCK(cudaStreamSynchronize(st), "sync");
-    const i64 n_keep = last_pos + last_keep, ne = 2 * n_keep;
-    out->n_entries = ne;
-    if (ne == 0) { PWCK(cudaMemsetAsync(d_off, 0, sizeof(i64) * (p + 1), st), "memset"); return cudaSuccess; }
-    pw_emit_directed<<<pw_blocks(nf, T), T, 0, st>>>(c_x, c_y, keep, keep_pos, nf, p, keys, vals); (*n_launch)++;
-    int end_bit = 1; while (((u64)1 << end_bit) < (u64)p * (u64)p && end_bit < 64) ++end_bit;
-    cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys2, vals, vals2, (int)ne, 0, end_bit, st);
-    if (need > tmp_bytes) { tmp_bytes = need; PWCK(S.get(5, tmp_bytes, &tmp), "alloc"); }
-    PWCK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)ne, 0, end_bit, st), "sort"); (*n_launch) += 8;
-    i64* d_nbr; double *d_stat, *d_adjp;
-    PWCK(S.get(12, sizeof(i64) * ne, (void**)&d_nbr), "alloc");
-    PWCK(S.get(13, sizeof(double) * ne, (void**)&d_stat), "alloc");
-    PWCK(S.get(14, sizeof(double) * ne, (void**)&d_adjp), "alloc");
-    pw_fill_csr<<<pw_blocks(ne, T), T, 0, st>>>(keys2, vals2, ne, p, c_stat, adj, d_nbr, d_stat, d_adjp); (*n_launch)++;
-    pw_row_offsets<<<pw_blocks(p + 1, T), T, 0, st>>>(keys2, ne, p, d_off); (*n_launch)++;
-    PWCK(cudaGetLastError(), "csr kernels");
-    out->d_nbr = d_nbr; out->d_stat = d_stat; out->d_adjp = d_adjp;
-    return cudaSuccess;
+    return pairwise_finish(S, c_x, c_y, c_p, c_stat, nf, m, p, alpha, fdr, st, out, n_launch, msg);
 }

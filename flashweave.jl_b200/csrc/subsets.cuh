@@ -63,12 +63,17 @@ __device__ __forceinline__ void unrank_subset(i64 idx, int m, const SubsetCounts
     }
 }
 
-// TestFn: FzTest-like {stat,pval,suff,df} operator()(int k, int za, int zb, int zc) with z* = slots.
+// TestFn: {stat,pval,suff,df} operator()(int k, int za, int zb, int zc) with z* = slots.
+// GROUP = threads that evaluate one test together (1: thread-per-test, Fisher-z; 32: warp-per-test, discrete);
+// the functor is called by all GROUP lanes and must return the same result in each.
 // All threads of the CTA must call this with identical arguments.  `out` lives in shared memory.
-template <int THREADS, int TPT, class TestFn>
+template <int THREADS, int TPT, int GROUP, class TestFn>
 __device__ void eval_subsets(const TestFn& test, const int* acc, int m, int max_k, double alpha, i64 max_tests,
                              i64* tri_off, EvalShared* sh, EvalOut* out) {
     const int tid = threadIdx.x;
+    constexpr int NG = THREADS / GROUP;              // tests in flight per pass
+    const int grp = tid / GROUP;
+    const bool leader = (tid % GROUP) == 0;
     const SubsetCounts sc = subset_counts(m, max_k);
     if (sc.c3 > 0) for (int i = tid; i <= m; i += THREADS) tri_off[i] = sc.c3 - choose3(m - i);
     if (tid == 0) sh->fail_idx = (u64)FW_INF_IDX;
@@ -79,10 +84,10 @@ __device__ void eval_subsets(const TestFn& test, const int* acc, int m, int max_
     i64 best_idx = -1; double b_stat = 0.0, b_p = -1.0; i64 b_df = 0;
     i64 executed = 0;
     bool any_fail = false;
-    for (i64 base = 0; base < limit; base += (i64)THREADS * TPT) {
+    for (i64 base = 0; base < limit; base += (i64)NG * TPT) {
 #pragma unroll
         for (int u = 0; u < TPT; ++u) {
-            i64 idx = base + (i64)u * THREADS + tid;
+            i64 idx = base + (i64)u * NG + grp;
             if (idx < limit && my_fail == FW_INF_IDX) {
                 int k, a, b, c;
                 unrank_subset(idx, m, sc, tri_off, k, a, b, c);
@@ -93,15 +98,15 @@ __device__ void eval_subsets(const TestFn& test, const int* acc, int m, int max_
                 else if (r.pval >= b_p) { best_idx = idx; b_stat = r.stat; b_p = r.pval; b_df = r.df; }
             }
         }
-        i64 end = base + (i64)THREADS * TPT;
+        i64 end = base + (i64)NG * TPT;
         executed = end < limit ? end : limit;
         any_fail = __syncthreads_or(my_fail != FW_INF_IDX);
         if (any_fail) break;
     }
     if (any_fail) {
-        if (my_fail != FW_INF_IDX) atomicMin(&sh->fail_idx, (u64)my_fail);
+        if (my_fail != FW_INF_IDX && leader) atomicMin(&sh->fail_idx, (u64)my_fail);
         __syncthreads();
-        if ((u64)my_fail == sh->fail_idx) {
+        if ((u64)my_fail == sh->fail_idx && leader) {
             int k, a, b, c;
             unrank_subset(my_fail, m, sc, tri_off, k, a, b, c);
             out->stat = f_stat; out->pval = f_p; out->df = f_df; out->suff = f_suff;

@@ -92,3 +92,79 @@ def test_random_discrete_tests(fw, synth, kind):
             assert _same(g, w), (kind, x_, y_, z_, hps, nom, g, w)
             n_pow += int(g[3])
         assert 0 < n_pow < len(X)
+
+
+@pytest.mark.parametrize("kind", ["mi", "mi_nz"])
+def test_discrete_pairwise_stage(fw, synth, kind):
+    b, t = _tables(synth, 50)
+    x = b if kind == "mi" else t
+    eng = fw.Engine(0)
+    eng.set_data_colmajor(x, kind)
+    ora = fwo.Oracle(x.T, kind)
+    p = x.shape[0]
+    for fdr, nom in [(True, 20), (False, 20), (True, 160)]:
+        got = eng.pw_univar_neighbors(alpha=0.01, hps=5, n_obs_min=nom, FDR=fdr)
+        off, nbr, st, ap, rs, rp = ora.pairwise(alpha=0.01, hps=5, n_obs_min=nom, fdr=fdr, want_raw=True)
+        assert (got.offsets == off).all() and (got.nbr == nbr).all(), (kind, fdr, nom)
+        assert np.allclose(got.stat, st, rtol=1e-12, atol=1e-15) and np.allclose(got.pval, ap, rtol=1e-10, atol=1e-300)
+        s = eng.pairwise_stats()
+        assert s["n_tests"] == p * (p - 1) // 2 and s["n_reliable"] == int((~np.isnan(rp)).sum()) and s["n_raw_sig"] == int((rp < 0.01).sum())
+
+
+@pytest.mark.parametrize("kind", ["mi", "mi_nz"])
+def test_discrete_test_subsets(fw, synth, kind):
+    b, t = _tables(synth, 60)
+    x = b if kind == "mi" else t
+    eng = fw.Engine(0)
+    eng.set_data_colmajor(x, kind)
+    ora = fwo.Oracle(x.T, kind)
+    rng = np.random.default_rng(9)
+    p = x.shape[0]
+    jobs = []
+    for _ in range(150):
+        m = int(rng.integers(1, 9))
+        v = rng.choice(p, size=2 + m, replace=False)
+        jobs.append((int(v[0]), int(v[1]), [int(z) for z in v[2:]]))
+    jobs += [(0, 1, [2, 3, 4, 6, 7]), (8, 10, [11, 12, 13, 14, 15]), (0, 1, list(range(2, 30)))]
+    for max_k, max_tests, hps in [(3, 0, 5), (2, 0, 5), (1, 0, 5), (3, 7, 5), (3, 0, 1)]:
+        got = eng.test_subsets_batch([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs], max_k=max_k, alpha=0.01, hps=hps, max_tests=max_tests)
+        for (X, Y, Z), g in zip(jobs, got):
+            w = ora.test_subsets(X, Y, Z, max_k=max_k, alpha=0.01, hps=hps, max_tests=max_tests)
+            assert _same(g[0], w[0]) and g[1] == w[1] and g[2] == w[2], (kind, X, Y, Z, max_k, max_tests, g, w)
+    g = eng.test_subsets(0, 1, [], max_k=3)
+    assert np.isnan(g[0][0]) and g[0][2] == -1 and g[1] == (-1,) and g[2] == -1
+
+
+@pytest.mark.parametrize("kind", ["mi", "mi_nz"])
+def test_discrete_hiton_pc_and_graph(fw, synth, hmp, golden_dir, kind):
+    graphs = json.load(open(os.path.join(golden_dir, "learning_expected.json")))
+    b, t = _tables(synth, 70)
+    for name, x in [("hmp", np.ascontiguousarray(hmp[kind].T.astype(np.int32))), ("syn", b if kind == "mi" else t)]:
+        eng = fw.Engine(0)
+        eng.set_data_colmajor(x, kind)
+        ora = fwo.Oracle(x.T, kind)
+        p = x.shape[0]
+        nom = 160 if name == "hmp" else 40
+        uni = eng.pw_univar_neighbors(alpha=0.01, n_obs_min=nom)
+        for max_k in (3, 1):
+            res = eng.si_HITON_PC(np.arange(p), max_k=max_k, alpha=0.01, hps=5, n_obs_min=nom)
+            for T in range(p):
+                a, bb = uni.offsets[T], uni.offsets[T + 1]
+                wn, ws, wp, wt = ora.hiton_pc(T, uni.nbr[a:bb], uni.stat[a:bb], uni.pval[a:bb], max_k=max_k, alpha=0.01, hps=5, n_obs_min=nom)
+                gn, gs, gp = res.pc(T)
+                assert list(gn) == list(wn), (kind, name, T, max_k, list(gn), list(wn))
+                assert np.allclose(gs, ws, rtol=1e-12, atol=1e-15) and np.allclose(gp, wp, rtol=1e-10, atol=1e-300)
+                assert res.num_tests[T] == wt
+        if name == "hmp":
+            # the golden graphs: max_k = 0 identical; max_k = 3 in "single" mode == oracle "single" (mi: the known +11 edges)
+            r0 = eng.LGL(max_k=0)
+            want0 = {(a_, b_) for a_, b_, _ in graphs[f"exp_{kind}_maxk0"]}
+            assert {(a_, b_) for a_, b_, _ in r0["edges"]} == want0
+            r3 = eng.LGL(max_k=3, n_obs_min=160)
+            w3 = fwo.Oracle(x.T, kind).lgl(max_k=3, n_obs_min=160, mode="single")
+            assert [(a_, b_) for a_, b_, _ in r3["edges"]] == [(a_, b_) for a_, b_, _ in w3["edges"]]
+            assert np.allclose([e[2] for e in r3["edges"]], [e[2] for e in w3["edges"]], rtol=1e-12, atol=1e-15)
+            assert r3["cond_tests"] == w3["cond_tests"]
+            want3 = {(a_, b_) for a_, b_, _ in graphs[f"exp_{kind}_maxk3"]}
+            got3 = {(a_, b_) for a_, b_, _ in r3["edges"]}
+            assert len(got3 ^ want3) == (11 if kind == "mi" else 0)
