@@ -130,7 +130,12 @@ def test_discrete_test_subsets(fw, synth, kind):
         got = eng.test_subsets_batch([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs], max_k=max_k, alpha=0.01, hps=hps, max_tests=max_tests)
         for (X, Y, Z), g in zip(jobs, got):
             w = ora.test_subsets(X, Y, Z, max_k=max_k, alpha=0.01, hps=hps, max_tests=max_tests)
-            assert _same(g[0], w[0]) and g[1] == w[1] and g[2] == w[2], (kind, X, Y, Z, max_k, max_tests, g, w)
+            assert _same(g[0], w[0]) and g[2] == w[2], (kind, X, Y, Z, max_k, max_tests, g, w)
+            if g[1] != w[1]:
+                # two subsets with mathematically equal statistics (permuted tables): which one wins the
+                # `pval >= lowest.pval` scan (tests.jl:338) is decided by last-ulp summation noise
+                alt = ora.test_cond(X, Y, list(g[1]), hps=hps, max_k=3)
+                assert _same(alt, w[0]), (kind, X, Y, Z, max_k, g, w, alt)
     g = eng.test_subsets(0, 1, [], max_k=3)
     assert np.isnan(g[0][0]) and g[0][2] == -1 and g[1] == (-1,) and g[2] == -1
 
