@@ -159,6 +159,7 @@ def main_ours(a, rank, world, local_rank):
     import fwload
     fw = fwload.load()
     synth = fwload.load_sub("synth")
+    par = fwload.load_sub("parallel")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
@@ -191,8 +192,7 @@ def main_ours(a, rank, world, local_rank):
         th = time.perf_counter()
         if rank == 0:
             d_x.copy_(host_x, non_blocking=True)                     # H2D from pinned host memory
-        if dist is not None:
-            dist.broadcast(d_x, src=0)                               # the one collective: table over NVLink
+        par.broadcast_table(dist, d_x, src=0)                        # the one collective: table over NVLink
         torch.cuda.synchronize()
         h2d_ms.append((time.perf_counter() - th) * 1e3)
         eng.adopt_data_device(d_x.data_ptr(), n, p, "fz")
@@ -201,7 +201,7 @@ def main_ours(a, rank, world, local_rank):
         off = np.zeros(p + 1, np.int64)
         eng._ck(eng.L.fw_pairwise_copy(eng.h, off.ctypes.data_as(fw.C.c_void_p), None, None, None))
         order = np.argsort(np.diff(off), kind="stable").astype(np.int64)      # learning.jl:97-98
-        shard = fw.shard_targets(order, rank, world)                           # target i -> rank i mod N
+        shard = par.shard_targets(order, rank, world)                          # target i -> rank i mod N
         res = eng.si_HITON_PC(shard, max_k=a.max_k, alpha=a.alpha, n_obs_min=20, want_tpc=False)
         return shard, res
 
