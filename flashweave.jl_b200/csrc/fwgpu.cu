@@ -62,6 +62,8 @@ struct fw_ctx {
     DevBuf<unsigned int> d_planes; DevBuf<int> d_levels, d_maxvals, d_nnz, d_bad;
     std::vector<int> h_levels, h_maxvals;
     int disc_L = 0, disc_W = 0;
+    // fz_nz: non-zero planes of the continuous table (fznz.cuh), built on first use
+    DevBuf<unsigned int> d_nzmask; DevBuf<int> d_nnz_f; bool nz_ready = false;
 
     // cor_mat
     DevBuf<float> d_cor; i64 cor_p = 0;
@@ -113,18 +115,41 @@ static MiTable make_mi_table(const fw_ctx* c, int kind) {
     return t;
 }
 
+static int ensure_nz_table(fw_ctx* ctx, NzTable* t) {
+    if (ctx->data_kind != 0) return fail(ctx, FW_ERR_STATE, "fz_nz: no continuous table resident (call fw_set_data_f32 first)");
+    const int W = (int)((ctx->n + 31) / 32);
+    if (!ctx->nz_ready) {
+        cudaError_t e = ctx->d_nzmask.reserve((size_t)ctx->p * W);
+        if (e == cudaSuccess) e = ctx->d_nnz_f.reserve(ctx->p);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_nnz_f.ptr, 0, sizeof(int) * ctx->p, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fz_nz: mask allocation failed: %s", cudaGetErrorString(e));
+        const int T = 256; const i64 warps = ctx->p * W; const i64 blocks = (warps * 32 + T - 1) / T;
+        nz_mask_kernel<<<(unsigned)blocks, T, 0, ctx->stream>>>(ctx->d_data_f32.ptr, ctx->n, ctx->ld, ctx->p, W, ctx->d_nzmask.ptr, ctx->d_nnz_f.ptr);
+        ctx->launches++;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "nz_mask_kernel: %s", cudaGetErrorString(e));
+        ctx->nz_ready = true;
+    }
+    t->data = ctx->d_data_f32.ptr; t->nzmask = ctx->d_nzmask.ptr; t->nnz = ctx->d_nnz_f.ptr; t->p = ctx->p; t->ld = ctx->ld; t->n = (int)ctx->n; t->W = W;
+    return FW_OK;
+}
+
 // ---- capacity classes shared by the subset-search and HITON launches -------------------------
 static const int kCaps[4] = {32, 64, 128, 224};
-static size_t hiton_smem_bytes(int cap, bool r_in_smem) {
+static size_t hiton_smem_bytes(int cap, bool r_in_smem, int nz_words = -1) {
     size_t o = r_in_smem ? sizeof(float) * (size_t)cap * cap : 0;
     o = (o + 15) & ~(size_t)15;
     o += sizeof(i64) * (cap + 1) + 4 * sizeof(double) * cap + sizeof(i64) * cap + 2 * sizeof(int) * cap;
+    o = (o + 15) & ~(size_t)15;
+    if (nz_words >= 0) o += sizeof(i64) * cap + 2 * sizeof(double) * cap + sizeof(unsigned int) * nz_words;
     return o + 16;
 }
-static size_t subsets_smem_bytes(int cap, bool r_in_smem) {
+static size_t subsets_smem_bytes(int cap, bool r_in_smem, int nz_words = -1) {
     size_t o = r_in_smem ? sizeof(float) * (size_t)cap * cap : 0;
     o = (o + 15) & ~(size_t)15;
     o += sizeof(i64) * (cap + 1) + sizeof(int) * cap;
+    o = (o + 15) & ~(size_t)15;
+    if (nz_words >= 0) o += sizeof(i64) * cap + 2 * sizeof(double) * cap + sizeof(unsigned int) * nz_words;
     return o + 16;
 }
 
@@ -220,14 +245,14 @@ int32_t fw_set_data_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, in
     CK(cudaSetDevice(ctx->device));
     CK(ctx->d_data_f32.reserve((size_t)n * p));
     CK(cudaMemcpy2DAsync(ctx->d_data_f32.ptr, n * sizeof(float), host, ld * sizeof(float), n * sizeof(float), p, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n;
+    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n; ctx->nz_ready = false;
     return FW_OK;
 }
 int32_t fw_adopt_data_f32_device(fw_ctx* ctx, const float* dev, int64_t n, int64_t p, int64_t ld) {
     if (!ctx) return FW_ERR_INVALID;
     NEED(dev && n > 0 && p > 0 && ld >= n, FW_ERR_INVALID, "fw_adopt_data_f32_device: bad arguments");
     ctx->d_data_f32.adopt(const_cast<float*>(dev), (size_t)ld * p);
-    ctx->n = n; ctx->p = p; ctx->ld = ld; ctx->data_kind = 0; ctx->n_obs = n;
+    ctx->n = n; ctx->p = p; ctx->ld = ld; ctx->data_kind = 0; ctx->n_obs = n; ctx->nz_ready = false;
     return FW_OK;
 }
 int32_t fw_set_data_i32(fw_ctx* ctx, const int32_t* host, int64_t n, int64_t p, int64_t ld) {
@@ -321,17 +346,20 @@ int32_t fw_cor_matrix(fw_ctx* ctx, float* host_out) {
 int32_t fw_test_batch(fw_ctx* ctx, int32_t kind, int64_t n_tests, const int64_t* X, const int64_t* Y,
                       const int32_t* k, const int64_t* Zs, int64_t hps, int64_t n_obs_min, fw_test_result* out) {
     if (!ctx) return FW_ERR_INVALID;
-    NEED(kind == FW_FZ || kind == FW_MI || kind == FW_MI_NZ, FW_ERR_UNSUPPORTED, "fw_test_batch: kind %d is not built yet", kind);
+    NEED(kind >= FW_MI && kind <= FW_FZ_NZ, FW_ERR_INVALID, "fw_test_batch: unknown test kind %d", kind);
     NEED(n_tests >= 0 && (n_tests == 0 || (X && Y && k && Zs && out)), FW_ERR_INVALID, "fw_test_batch: NULL argument");
-    const bool disc = kind != FW_FZ;
+    const bool disc = kind == FW_MI || kind == FW_MI_NZ;
+    const bool nzk = kind == FW_FZ_NZ;
+    NzTable nzt;
+    if (nzk) { int st_ = ensure_nz_table(ctx, &nzt); if (st_ != FW_OK) return st_; }
     if (disc) NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_test_batch: no discrete table resident (fw_set_data_i32)");
-    else {
+    else if (!nzk) {
         NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_test_batch: no cor_mat resident (fw_cor_matrix / fw_set_cor_f32)");
         NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_test_batch: number of observations unknown (fw_set_data_f32 / fw_set_n_obs)");
     }
     if (n_tests == 0) return FW_OK;
     CK(cudaSetDevice(ctx->device));
-    const i64 p = disc ? ctx->p : ctx->cor_p, base = ctx->index_base;
+    const i64 p = (disc || nzk) ? ctx->p : ctx->cor_p, base = ctx->index_base;
     std::vector<i64> hx(n_tests), hy(n_tests), hz((size_t)n_tests * 3);
     for (i64 t = 0; t < n_tests; ++t) {
         NEED(k[t] >= 0 && k[t] <= 3, FW_ERR_UNSUPPORTED, "fw_test_batch: |Zs| = %d not in 0..3", k[t]);
@@ -355,6 +383,9 @@ int32_t fw_test_batch(fw_ctx* ctx, int32_t kind, int64_t n_tests, const int64_t*
         size_t smem = (size_t)WARPS * t.L * t.L * t.L * t.L * t.L * sizeof(int);
         i64 blocks = std::min<i64>((n_tests + WARPS - 1) / WARPS, (i64)ctx->sm_count * 8);
         mi_test_batch_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, smem, ctx->stream>>>(t, n_tests, dx.ptr, dy.ptr, dk.ptr, dz.ptr, hps, n_obs_min, dout.ptr);
+    } else if (nzk) {
+        i64 blocks = std::min<i64>(n_tests, (i64)ctx->sm_count * 8);
+        fznz_test_batch_kernel<256><<<(unsigned)blocks, 256, sizeof(unsigned int) * nzt.W, ctx->stream>>>(nzt, n_tests, dx.ptr, dy.ptr, dk.ptr, dz.ptr, n_obs_min, dout.ptr);
     } else {
         FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
         int threads = 128; i64 blocks = (n_tests + threads - 1) / threads;
@@ -372,18 +403,21 @@ int32_t fw_test_subsets_batch(fw_ctx* ctx, int32_t kind, int64_t n_jobs, const i
                               int32_t max_k, double alpha, int64_t hps, int64_t n_obs_min, int64_t max_tests,
                               fw_test_result* out_result, int64_t* out_Zs, int32_t* out_k, int64_t* num_tests, double* frac) {
     if (!ctx) return FW_ERR_INVALID;
-    NEED(kind == FW_FZ || kind == FW_MI || kind == FW_MI_NZ, FW_ERR_UNSUPPORTED, "fw_test_subsets: kind %d is not built yet", kind);
+    NEED(kind >= FW_MI && kind <= FW_FZ_NZ, FW_ERR_INVALID, "fw_test_subsets: unknown test kind %d", kind);
     NEED(max_k >= 1 && max_k <= 3, FW_ERR_UNSUPPORTED, "fw_test_subsets: max_k = %d not in 1..3", max_k);
     NEED(n_jobs >= 0 && (n_jobs == 0 || (X && Y && z_off && out_result && out_Zs && out_k && num_tests && frac)), FW_ERR_INVALID, "fw_test_subsets: NULL argument");
-    const bool disc = kind != FW_FZ;
+    const bool disc = kind == FW_MI || kind == FW_MI_NZ;
+    const bool nzk = kind == FW_FZ_NZ;
+    NzTable nzt;
+    if (nzk) { int st_ = ensure_nz_table(ctx, &nzt); if (st_ != FW_OK) return st_; }
     if (disc) NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_test_subsets: no discrete table resident (fw_set_data_i32)");
-    else {
+    else if (!nzk) {
         NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_test_subsets: no cor_mat resident");
         NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_test_subsets: number of observations unknown");
     }
     if (n_jobs == 0) return FW_OK;
     CK(cudaSetDevice(ctx->device));
-    const i64 p = disc ? ctx->p : ctx->cor_p, base = ctx->index_base;
+    const i64 p = (disc || nzk) ? ctx->p : ctx->cor_p, base = ctx->index_base;
     const i64 nz = z_off[n_jobs];
     NEED(nz == 0 || z_idx, FW_ERR_INVALID, "fw_test_subsets: z_idx is NULL");
     std::vector<i64> hx(n_jobs), hy(n_jobs), hz((size_t)std::max<i64>(nz, 1));
@@ -442,6 +476,8 @@ int32_t fw_test_subsets_batch(fw_ctx* ctx, int32_t kind, int64_t n_jobs, const i
     a.max_k = max_k; a.alpha = alpha; a.max_tests = max_tests; a.fc = make_fz_consts(ctx->n_obs, n_obs_min);
     a.out = dres.ptr; a.out_Zs = dZs.ptr; a.out_k = dk.ptr; a.num_tests = dnt.ptr; a.frac = dfr.ptr; a.executed_total = ctx->d_exec.ptr;
     a.counter = ctx->d_counter.ptr;
+    if (nzk) { a.nzt = nzt; a.n_obs_min = n_obs_min; }
+    const int nzw = nzk ? nzt.W : -1;
     size_t sel_off = 0;
     for (int c = 0; c < 5; ++c) {
         if (cls[c].empty()) continue;
@@ -452,19 +488,23 @@ int32_t fw_test_subsets_batch(fw_ctx* ctx, int32_t kind, int64_t n_jobs, const i
         int grid = 1;
         if (c < 4) {
             a.cap = kCaps[c]; a.gscratch = nullptr;
-            size_t smem = subsets_smem_bytes(a.cap, true);
-            if (c < 2) { CK(grid_for(subsets_fz_kernel<128, 2>, 128, smem, ctx->sm_count, n_sel, &grid)); subsets_fz_kernel<128, 2><<<grid, 128, smem, ctx->stream>>>(a); }
-            else { CK(grid_for(subsets_fz_kernel<256, 2>, 256, smem, ctx->sm_count, n_sel, &grid)); subsets_fz_kernel<256, 2><<<grid, 256, smem, ctx->stream>>>(a); }
+            size_t smem = subsets_smem_bytes(a.cap, true, nzw);
+            NEED(smem <= 220 * 1024, FW_ERR_UNSUPPORTED, "fw_test_subsets: job does not fit shared memory (n = %lld rows, %d slots)", (long long)ctx->n, a.cap);
+            if (nzk) { CK(grid_for(subsets_fz_kernel<256, 2, true>, 256, smem, ctx->sm_count, n_sel, &grid)); subsets_fz_kernel<256, 2, true><<<grid, 256, smem, ctx->stream>>>(a); }
+            else if (c < 2) { CK(grid_for(subsets_fz_kernel<128, 2, false>, 128, smem, ctx->sm_count, n_sel, &grid)); subsets_fz_kernel<128, 2, false><<<grid, 128, smem, ctx->stream>>>(a); }
+            else { CK(grid_for(subsets_fz_kernel<256, 2, false>, 256, smem, ctx->sm_count, n_sel, &grid)); subsets_fz_kernel<256, 2, false><<<grid, 256, smem, ctx->stream>>>(a); }
         } else {
             a.cap = max_need;
-            size_t smem = subsets_smem_bytes(a.cap, false);
+            size_t smem = subsets_smem_bytes(a.cap, false, nzw);
             NEED(smem <= 200 * 1024, FW_ERR_UNSUPPORTED, "fw_test_subsets: |Z_total| = %d exceeds the supported maximum", max_need - 2);
-            CK(grid_for(subsets_fz_kernel<256, 2>, 256, smem, ctx->sm_count, n_sel, &grid));
+            if (nzk) CK(grid_for(subsets_fz_kernel<256, 2, true>, 256, smem, ctx->sm_count, n_sel, &grid));
+            else CK(grid_for(subsets_fz_kernel<256, 2, false>, 256, smem, ctx->sm_count, n_sel, &grid));
             size_t per = (size_t)a.cap * a.cap;
             while (grid > 1 && per * grid * sizeof(float) > ((size_t)4 << 30)) grid = (grid + 1) / 2;
             CK(gs.reserve(per * grid));
             a.gscratch = gs.ptr;
-            subsets_fz_kernel<256, 2><<<grid, 256, smem, ctx->stream>>>(a);
+            if (nzk) subsets_fz_kernel<256, 2, true><<<grid, 256, smem, ctx->stream>>>(a);
+            else subsets_fz_kernel<256, 2, false><<<grid, 256, smem, ctx->stream>>>(a);
         }
         ctx->launches++;
         CK(cudaGetLastError());
@@ -498,15 +538,18 @@ int32_t fw_test_subsets(fw_ctx* ctx, int32_t kind, int64_t X, int64_t Y, const i
 int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_t n_obs_min,
                     int32_t fdr, int32_t correct_reliable_only, int64_t* n_entries) {
     if (!ctx) return FW_ERR_INVALID;
-    NEED(kind == FW_FZ || kind == FW_MI || kind == FW_MI_NZ, FW_ERR_UNSUPPORTED, "fw_pairwise: kind %d is not built yet", kind);
-    const bool disc = kind != FW_FZ;
+    NEED(kind >= FW_MI && kind <= FW_FZ_NZ, FW_ERR_INVALID, "fw_pairwise: unknown test kind %d", kind);
+    const bool disc = kind == FW_MI || kind == FW_MI_NZ;
+    const bool nzk = kind == FW_FZ_NZ;
+    NzTable nzt;
+    if (nzk) { int st_ = ensure_nz_table(ctx, &nzt); if (st_ != FW_OK) return st_; }
     if (disc) NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_pairwise: no discrete table resident (fw_set_data_i32)");
-    else {
+    else if (!nzk) {
         NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_pairwise: no cor_mat resident (fw_cor_matrix / fw_set_cor_f32)");
         NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_pairwise: number of observations unknown");
     }
     CK(cudaSetDevice(ctx->device));
-    const i64 p = disc ? ctx->p : ctx->cor_p;
+    const i64 p = (disc || nzk) ? ctx->p : ctx->cor_p;
     PairwiseOut po;
     std::string msg; int nl = 0;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -514,6 +557,8 @@ int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_
     if (disc) {
         MiTable t = make_mi_table(ctx, kind);
         e = pairwise_mi_run(ctx->pw, t, hps, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0, ctx->stream, &po, &nl, &msg);
+    } else if (nzk) {
+        e = pairwise_fznz_run(ctx->pw, nzt, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0, ctx->stream, &po, &nl, &msg);
     } else {
         FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
         e = pairwise_fz_run(ctx->pw, ctx->d_cor.ptr, p, fc, ctx->n_obs, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0,
@@ -614,11 +659,14 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
                     int64_t* tpc_count, int64_t* tpc_nbr, double* tpc_stat, double* tpc_p,
                     int64_t* num_tests, int64_t* tests_executed_total) {
     if (!ctx) return FW_ERR_INVALID;
-    NEED(kind == FW_FZ || kind == FW_MI || kind == FW_MI_NZ, FW_ERR_UNSUPPORTED, "fw_hiton_pc: kind %d is not built yet", kind);
+    NEED(kind >= FW_MI && kind <= FW_FZ_NZ, FW_ERR_INVALID, "fw_hiton_pc: unknown test kind %d", kind);
     NEED(max_k >= 0 && max_k <= 3, FW_ERR_UNSUPPORTED, "fw_hiton_pc: max_k = %d not in 0..3", max_k);
-    const bool disc = kind != FW_FZ;
+    const bool disc = kind == FW_MI || kind == FW_MI_NZ;
+    const bool nzk = kind == FW_FZ_NZ;
+    NzTable nzt;
+    if (nzk) { int st_ = ensure_nz_table(ctx, &nzt); if (st_ != FW_OK) return st_; }
     if (disc) NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_hiton_pc: no discrete table resident (fw_set_data_i32)");
-    else {
+    else if (!nzk) {
         NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_hiton_pc: no cor_mat resident");
         NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_hiton_pc: number of observations unknown");
     }
@@ -626,7 +674,7 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
     NEED(n_targets >= 0 && (n_targets == 0 || targets), FW_ERR_INVALID, "fw_hiton_pc: NULL targets");
     if (n_targets == 0) { if (pc_off) pc_off[0] = 0; if (tests_executed_total) *tests_executed_total = 0; return FW_OK; }
     CK(cudaSetDevice(ctx->device));
-    const i64 p = disc ? ctx->p : ctx->cor_p, base = ctx->index_base;
+    const i64 p = (disc || nzk) ? ctx->p : ctx->cor_p, base = ctx->index_base;
     NEED((i64)ctx->h_uni_off.size() == p + 1, FW_ERR_STATE, "fw_hiton_pc: neighbour lists and cor_mat disagree on the number of variables");
 
     std::vector<i64> ht(n_targets), hoff(n_targets + 1);
@@ -722,14 +770,16 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         }
     }
     HitonArgs a;
-    a.cor = ctx->d_cor.ptr; a.p = p;
+    a.cor = nzk ? nullptr : ctx->d_cor.ptr; a.p = p;
     a.uni_off = ctx->d_uni_off.ptr; a.uni_nbr = ctx->d_uni_nbr.ptr; a.uni_stat = ctx->d_uni_stat.ptr; a.uni_p = ctx->d_uni_p.ptr;
     a.targets = dt.ptr; a.out_off = doff.ptr; a.counter = ctx->d_counter.ptr;
-    a.max_k = max_k; a.alpha = alpha; a.max_tests = max_tests; a.fc = make_fz_consts(ctx->n_obs, n_obs_min);
+    a.max_k = max_k; a.alpha = alpha; a.max_tests = max_tests; a.fc = make_fz_consts(ctx->n_obs < 0 ? 0 : ctx->n_obs, n_obs_min);
     a.cand_order = dorder.ptr;
     a.pc_nbr = dpcn.ptr; a.pc_stat = dpcs.ptr; a.pc_p = dpcp.ptr; a.pc_count = dpcc.ptr;
     a.tpc_nbr = dtpcn.ptr; a.tpc_stat = dtpcs.ptr; a.tpc_p = dtpcp.ptr; a.tpc_count = dtpcc.ptr;
     a.num_tests = dnt.ptr; a.executed_total = ctx->d_exec.ptr; a.status = dstatus.ptr;
+    if (nzk) { a.nzt = nzt; a.n_obs_min = n_obs_min; }
+    const int nzw = nzk ? nzt.W : -1;
 
     // capacity classes: a target needs at most (#candidates + 2) slots; start optimistic (<= 64) and
     // escalate the few targets whose accepted set outgrows the class
@@ -752,20 +802,24 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         int grid = 1;
         if (c < 4) {
             a.cap = kCaps[c]; a.gscratch = nullptr;
-            size_t smem = hiton_smem_bytes(a.cap, true);
-            if (c < 2) { CK(grid_for(hiton_fz_kernel<128, 2>, 128, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<128, 2><<<grid, 128, smem, ctx->stream>>>(a); }
-            else { CK(grid_for(hiton_fz_kernel<256, 2>, 256, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<256, 2><<<grid, 256, smem, ctx->stream>>>(a); }
+            size_t smem = hiton_smem_bytes(a.cap, true, nzw);
+            NEED(smem <= 220 * 1024, FW_ERR_UNSUPPORTED, "fw_hiton_pc: target does not fit shared memory (n = %lld rows, %d slots)", (long long)ctx->n, a.cap);
+            if (nzk) { CK(grid_for(hiton_fz_kernel<256, 2, true>, 256, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<256, 2, true><<<grid, 256, smem, ctx->stream>>>(a); }
+            else if (c < 2) { CK(grid_for(hiton_fz_kernel<128, 2, false>, 128, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<128, 2, false><<<grid, 128, smem, ctx->stream>>>(a); }
+            else { CK(grid_for(hiton_fz_kernel<256, 2, false>, 256, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<256, 2, false><<<grid, 256, smem, ctx->stream>>>(a); }
         } else {
             i64 need = 0; for (int t : sel) need = std::max<i64>(need, hoff[t + 1] - hoff[t] + 2);
             NEED(need <= 3000, FW_ERR_UNSUPPORTED, "fw_hiton_pc: a target has %lld candidates; more than 2998 accepted neighbours are not supported", (long long)need - 2);
             a.cap = (int)need;
-            size_t smem = hiton_smem_bytes(a.cap, false);
-            CK(grid_for(hiton_fz_kernel<256, 2>, 256, smem, ctx->sm_count, n_sel, &grid));
+            size_t smem = hiton_smem_bytes(a.cap, false, nzw);
+            if (nzk) CK(grid_for(hiton_fz_kernel<256, 2, true>, 256, smem, ctx->sm_count, n_sel, &grid));
+            else CK(grid_for(hiton_fz_kernel<256, 2, false>, 256, smem, ctx->sm_count, n_sel, &grid));
             size_t per = (size_t)a.cap * a.cap;
             while (grid > 1 && per * grid * sizeof(float) > ((size_t)8 << 30)) grid = (grid + 1) / 2;
             CK(gs.reserve(per * grid));
             a.gscratch = gs.ptr;
-            hiton_fz_kernel<256, 2><<<grid, 256, smem, ctx->stream>>>(a);
+            if (nzk) hiton_fz_kernel<256, 2, true><<<grid, 256, smem, ctx->stream>>>(a);
+            else hiton_fz_kernel<256, 2, false><<<grid, 256, smem, ctx->stream>>>(a);
         }
         ctx->launches++;
         CK(cudaGetLastError());

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "fz.cuh"
 #include "subsets.cuh"
+#include "fznz.cuh"
 
 struct HitonArgs {
     // resident inputs
@@ -34,6 +35,8 @@ struct HitonArgs {
     i64* tpc_nbr; double* tpc_stat; double* tpc_p; i64* tpc_count;
     i64* num_tests; u64* executed_total;      // executed_total[0] = all, [1..3] = by |Zs|
     int* status;                             // per target: 0 ok, 1 capacity overflow (re-run with larger cap)
+    // fz_nz only: the table and its non-zero planes; correlations are recomputed per (T, candidate) view
+    NzTable nzt; i64 n_obs_min;
 };
 
 struct FzSlotTest {
@@ -43,7 +46,7 @@ struct FzSlotTest {
     }
 };
 
-template <int THREADS, int TPT>
+template <int THREADS, int TPT, bool NZ>
 __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -61,9 +64,14 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
     i64* member = reinterpret_cast<i64*>(smem + o); o += sizeof(i64) * cap;
     int* acc = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;
     int* pc_slot = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;
+    o = (o + 15) & ~(size_t)15;
+    // fz_nz scratch: slot -> variable, per-variable (mean, norm), row mask of the current view
+    i64* slotvar = reinterpret_cast<i64*>(smem + o); if (NZ) o += sizeof(i64) * cap;
+    double* mom = reinterpret_cast<double*>(smem + o); if (NZ) o += sizeof(double) * 2 * cap;
+    unsigned int* vmask = reinterpret_cast<unsigned int*>(smem + o);
     __shared__ EvalShared sh;
     __shared__ EvalOut ev;
-    __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_accept;
+    __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_accept, s_cnt;
     __shared__ i64 s_ntests;
     __shared__ u64 s_exec, s_exk[3];
 
@@ -109,11 +117,15 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
             const int ui = order[ci];
             const i64 cand = a.uni_nbr[e0 + ui];
             const int ys = M + 1;
-            // gather the candidate's correlations with T and the members into slot ys
-            for (int s = tid; s <= M; s += THREADS) {
-                i64 other = (s == 0) ? T : member[s - 1];
-                float v = __ldg(a.cor + cand * a.p + other);
-                R[ys * ld + s] = v; R[s * ld + ys] = v;
+            if constexpr (!NZ) {
+                // gather the candidate's correlations with T and the members into slot ys
+                for (int s = tid; s <= M; s += THREADS) {
+                    i64 other = (s == 0) ? T : member[s - 1];
+                    float v = __ldg(a.cor + cand * a.p + other);
+                    R[ys * ld + s] = v; R[s * ld + ys] = v;
+                }
+            } else {
+                for (int s = tid; s <= M + 1; s += THREADS) slotvar[s] = (s == 0) ? T : (s == ys ? cand : member[s - 1]);
             }
             if (tid == 0) s_accept = 0;
             __syncthreads();
@@ -125,10 +137,19 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
                 for (int s = tid + THREADS; s < M; s += THREADS) acc[s] = s + 1;
                 __syncthreads();
                 FzSlotTest tf; tf.r.R = R; tf.r.ld = ld; tf.x = 0; tf.y = ys; tf.fc = a.fc;
-                eval_subsets<THREADS, TPT, 1>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
-                if (tid == 0) {
-                    s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
-                    if (ev.sig) { tpc_stat[M] = ev.stat; tpc_p[M] = ev.pval; s_accept = 1; }
+                bool run = true;
+                if constexpr (NZ) {
+                    // cor_subset! on the rows where T != 0 and candidate != 0 (tests.jl:293-308; hiton.jl:41-50,85)
+                    const int rows = fznz_subcor_block<THREADS>(a.nzt, slotvar, M + 2, 0, ys, R, ld, vmask, mom, &s_cnt);
+                    run = !(a.n_obs_min > (i64)rows);                     // else (0, 1, 0, false), zero tests: rejected
+                    tf.fc = nz_consts(rows, a.n_obs_min);
+                }
+                if (run) {
+                    eval_subsets<THREADS, TPT, 1>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                    if (tid == 0) {
+                        s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
+                        if (ev.sig) { tpc_stat[M] = ev.stat; tpc_p[M] = ev.pval; s_accept = 1; }
+                    }
                 }
             }
             __syncthreads();
@@ -158,10 +179,20 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
                 if (tid == 0) { pcs_stat[s_npc] = tpc_stat[c - 1]; pcs_p[s_npc] = tpc_p[c - 1]; s_accept = 1; }   // support_dict = TPC_dict
             } else {
                 FzSlotTest tf; tf.r.R = R; tf.r.ld = ld; tf.x = 0; tf.y = c; tf.fc = a.fc;
-                eval_subsets<THREADS, TPT, 1>(tf, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
-                if (tid == 0) {
-                    s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
-                    if (ev.sig) { pcs_stat[s_npc] = ev.stat; pcs_p[s_npc] = ev.pval; s_accept = 1; }
+                bool run = true;
+                if constexpr (NZ) {
+                    for (int s = tid; s <= M; s += THREADS) slotvar[s] = (s == 0) ? T : member[s - 1];
+                    __syncthreads();
+                    const int rows = fznz_subcor_block<THREADS>(a.nzt, slotvar, M + 1, 0, c, R, ld, vmask, mom, &s_cnt);
+                    run = !(a.n_obs_min > (i64)rows);
+                    tf.fc = nz_consts(rows, a.n_obs_min);
+                }
+                if (run) {
+                    eval_subsets<THREADS, TPT, 1>(tf, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                    if (tid == 0) {
+                        s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
+                        if (ev.sig) { pcs_stat[s_npc] = ev.stat; pcs_p[s_npc] = ev.pval; s_accept = 1; }
+                    }
                 }
             }
             __syncthreads();
@@ -199,9 +230,10 @@ struct SubsetsArgs {
     int max_k; double alpha; i64 max_tests; FzConsts fc;
     int cap; float* gscratch;
     DevResult* out; i64* out_Zs; int* out_k; i64* num_tests; double* frac; u64* executed_total;
+    NzTable nzt; i64 n_obs_min;             // fz_nz only
 };
 
-template <int THREADS, int TPT>
+template <int THREADS, int TPT, bool NZ>
 __global__ void __launch_bounds__(THREADS) subsets_fz_kernel(SubsetsArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -212,9 +244,13 @@ __global__ void __launch_bounds__(THREADS) subsets_fz_kernel(SubsetsArgs a) {
     o = (o + 15) & ~(size_t)15;
     i64* tri_off = reinterpret_cast<i64*>(smem + o); o += sizeof(i64) * (cap + 1);
     int* acc = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;
+    o = (o + 15) & ~(size_t)15;
+    i64* slotvar = reinterpret_cast<i64*>(smem + o); if (NZ) o += sizeof(i64) * cap;
+    double* mom = reinterpret_cast<double*>(smem + o); if (NZ) o += sizeof(double) * 2 * cap;
+    unsigned int* vmask = reinterpret_cast<unsigned int*>(smem + o);
     __shared__ EvalShared sh;
     __shared__ EvalOut ev;
-    __shared__ int s_ji;
+    __shared__ int s_ji, s_cnt;
     float* R = a.gscratch ? a.gscratch + (size_t)blockIdx.x * cap * cap : Rs;
     const int ld = cap;
     for (;;) {
@@ -226,16 +262,31 @@ __global__ void __launch_bounds__(THREADS) subsets_fz_kernel(SubsetsArgs a) {
         const i64 z0 = a.z_off[job];
         const int m = (int)(a.z_off[job + 1] - z0);
         const int nv = m + 2;
-        // gather the (m+2)^2 sub-block: slot 0 = X, 1 = Y, 2.. = Z_total
-        for (int e = tid; e < nv * nv; e += THREADS) {
-            int i = e / nv, j = e % nv;
-            i64 vi = i == 0 ? a.X[job] : (i == 1 ? a.Y[job] : a.z_idx[z0 + i - 2]);
-            i64 vj = j == 0 ? a.X[job] : (j == 1 ? a.Y[job] : a.z_idx[z0 + j - 2]);
-            R[i * ld + j] = __ldg(a.cor + vi * a.p + vj);
-        }
-        for (int s = tid; s < m; s += THREADS) acc[s] = s + 2;
-        __syncthreads();
         FzSlotTest tf; tf.r.R = R; tf.r.ld = ld; tf.x = 0; tf.y = 1; tf.fc = a.fc;
+        for (int s = tid; s < m; s += THREADS) acc[s] = s + 2;
+        if constexpr (!NZ) {
+            // gather the (m+2)^2 sub-block: slot 0 = X, 1 = Y, 2.. = Z_total
+            for (int e = tid; e < nv * nv; e += THREADS) {
+                int i = e / nv, j = e % nv;
+                i64 vi = i == 0 ? a.X[job] : (i == 1 ? a.Y[job] : a.z_idx[z0 + i - 2]);
+                i64 vj = j == 0 ? a.X[job] : (j == 1 ? a.Y[job] : a.z_idx[z0 + j - 2]);
+                R[i * ld + j] = __ldg(a.cor + vi * a.p + vj);
+            }
+            __syncthreads();
+        } else {
+            for (int s = tid; s < nv; s += THREADS) slotvar[s] = s == 0 ? a.X[job] : (s == 1 ? a.Y[job] : a.z_idx[z0 + s - 2]);
+            __syncthreads();
+            const int rows = fznz_subcor_block<THREADS>(a.nzt, slotvar, nv, 0, 1, R, ld, vmask, mom, &s_cnt);
+            if (a.n_obs_min > (i64)rows) {                                  // tests.jl:293-296
+                if (tid == 0) {
+                    a.out[job] = make_result(0.0, 1.0, 0, false);
+                    for (int i = 0; i < 3; ++i) a.out_Zs[job * 3 + i] = -1;
+                    a.out_k[job] = 0; a.num_tests[job] = 0; a.frac[job] = 0.0;
+                }
+                continue;
+            }
+            tf.fc = nz_consts(rows, a.n_obs_min);
+        }
         eval_subsets<THREADS, TPT, 1>(tf, acc, m, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
         if (tid == 0) {
             a.out[job] = make_result(ev.stat, ev.pval, ev.df, ev.suff != 0);

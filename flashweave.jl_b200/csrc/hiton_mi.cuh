@@ -283,3 +283,57 @@ static cudaError_t pairwise_mi_run(PairwiseScratch& S, const MiTable& t, i64 hps
     PWCK(cudaStreamSynchronize(st), "sync");      // the arena in slot 11 is re-used by pairwise_finish
     return pairwise_finish(S, o_x, o_y, o_p, o_s, nf, m, p, alpha, fdr, st, out, n_launch, msg);
 }
+
+// pw_univar_neighbors for fz_nz (tests.jl:436-532): per-pair correlations on the co-non-zero rows
+static cudaError_t pairwise_fznz_run(PairwiseScratch& S, const NzTable& t, i64 n_obs_min, double alpha, bool fdr, bool reliable_only,
+                                     cudaStream_t st, PairwiseOut* out, int* n_launch, std::string* msg) {
+    const int T = 256, WARPS = 8;
+    const i64 p = t.p, n_pairs = p * (p - 1) / 2;
+    out->n_tests = n_pairs;
+    u64* counters; PWCK(S.get(0, sizeof(u64) * 4, (void**)&counters), "alloc");
+    i64 cap = std::max<i64>((i64)1 << 16, std::min<i64>(n_pairs, n_pairs / 8 + 1024));
+    int *c_x, *c_y; double *c_p, *c_stat;
+    u64 h_cnt[2] = {0, 0};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        PWCK(S.get(7, sizeof(int) * cap, (void**)&c_x), "alloc");
+        PWCK(S.get(8, sizeof(int) * cap, (void**)&c_y), "alloc");
+        PWCK(S.get(9, sizeof(double) * cap, (void**)&c_p), "alloc");
+        PWCK(S.get(10, sizeof(double) * cap, (void**)&c_stat), "alloc");
+        PWCK(cudaMemsetAsync(counters, 0, sizeof(u64) * 4, st), "memset");
+        pw_fznz_rows_kernel<WARPS><<<(unsigned)p, WARPS * 32, 0, st>>>(t, n_obs_min, alpha, reliable_only ? 1 : 0, counters, cap, c_x, c_y, c_p, c_stat);
+        (*n_launch)++;
+        PWCK(cudaGetLastError(), "pw_fznz_rows_kernel");
+        PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 2, cudaMemcpyDeviceToHost, st), "d2h");
+        PWCK(cudaStreamSynchronize(st), "sync");
+        if ((i64)h_cnt[0] <= cap) break;
+        cap = (i64)h_cnt[0];
+    }
+    const i64 nf = (i64)h_cnt[0];
+    out->n_raw_sig = nf;
+    out->n_reliable = reliable_only ? (i64)h_cnt[1] : n_pairs;
+    const i64 m = reliable_only ? (i64)h_cnt[1] : n_pairs;
+    i64* d_off; PWCK(S.get(6, sizeof(i64) * (p + 1), (void**)&d_off), "alloc");
+    out->d_off = d_off;
+    if (nf == 0) {
+        PWCK(cudaMemsetAsync(d_off, 0, sizeof(i64) * (p + 1), st), "memset");
+        out->n_entries = 0; out->d_nbr = nullptr; out->d_stat = nullptr; out->d_adjp = nullptr;
+        return cudaSuccess;
+    }
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    unsigned char* arena; PWCK(S.get(11, 2 * al(sizeof(u64) * nf) + 2 * al(sizeof(unsigned int) * nf), (void**)&arena), "alloc");
+    u64* keys = (u64*)arena; u64* keys2 = (u64*)(arena + al(sizeof(u64) * nf));
+    unsigned int* vals = (unsigned int*)(arena + 2 * al(sizeof(u64) * nf)); unsigned int* vals2 = (unsigned int*)(arena + 2 * al(sizeof(u64) * nf) + al(sizeof(unsigned int) * nf));
+    pw_pair_keys<<<pw_blocks(nf, T), T, 0, st>>>(c_x, c_y, p, keys, vals, nf); (*n_launch)++;
+    int end_bit = 1; while (((u64)1 << end_bit) < (u64)p * (u64)p && end_bit < 64) ++end_bit;
+    void* tmp = nullptr; size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys2, vals, vals2, (int)nf, 0, end_bit, st);
+    PWCK(S.get(5, need, &tmp), "alloc");
+    PWCK(cub::DeviceRadixSort::SortPairs(tmp, need, keys, keys2, vals, vals2, (int)nf, 0, end_bit, st), "sort"); (*n_launch) += 8;
+    unsigned char* ord; PWCK(S.get(15, 2 * al(sizeof(int) * nf) + 2 * al(sizeof(double) * nf), (void**)&ord), "alloc");
+    int* o_x = (int*)ord; int* o_y = (int*)(ord + al(sizeof(int) * nf));
+    double* o_p = (double*)(ord + 2 * al(sizeof(int) * nf)); double* o_s = (double*)(ord + 2 * al(sizeof(int) * nf) + al(sizeof(double) * nf));
+    pw_gather_pairs<<<pw_blocks(nf, T), T, 0, st>>>(vals2, c_x, c_y, c_p, c_stat, o_x, o_y, o_p, o_s, nf); (*n_launch)++;
+    PWCK(cudaGetLastError(), "pw_gather_pairs");
+    PWCK(cudaStreamSynchronize(st), "sync");
+    return pairwise_finish(S, o_x, o_y, o_p, o_s, nf, m, p, alpha, fdr, st, out, n_launch, msg);
+}

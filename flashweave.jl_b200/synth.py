@@ -57,3 +57,11 @@ def three_level(x_pn, zero_frac=0.4, seed=0):
         med = np.median(nzv)
         out[v][present[v]] = 1 + (nzv > med)
     return out
+
+
+def with_zeros(x_pn, zero_frac=0.4, seed=0):
+    """fz_nz-style table: structural zeros (absent taxa) punched into a continuous table; non-zeros keep their value."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = x_pn.copy()
+    out[rng.random(x_pn.shape) < zero_frac] = 0.0
+    return out
