@@ -41,3 +41,18 @@ __device__ __forceinline__ void unrank2(i64 q, int n, int& a, int& b) {
     a = aa;
     b = (int)(q - ((i64)aa * n - (i64)aa * (aa + 1) / 2)) + aa + 1;
 }
+// 32-bit variant for n <= 4096 (q < 2^23: exactly representable in fp32, the estimate is off by at most 1)
+__device__ __forceinline__ void unrank2_small(int q, int n, int& a, int& b) {
+    const float fn = 2.0f * (float)n - 1.0f;
+    const float disc = fmaf(fn, fn, -8.0f * (float)q);
+    int aa = (int)((fn - sqrtf(fmaxf(disc, 0.0f))) * 0.5f);
+    aa = max(0, min(aa, n - 2));
+    int off = aa * n - ((aa * (aa + 1)) >> 1);
+    if (off > q) { --aa; off = aa * n - ((aa * (aa + 1)) >> 1); }
+    if (off > q) { --aa; off = aa * n - ((aa * (aa + 1)) >> 1); }
+    int off1 = (aa + 1) * n - (((aa + 1) * (aa + 2)) >> 1);
+    if (aa < n - 2 && off1 <= q) { ++aa; off = off1; off1 = (aa + 1) * n - (((aa + 1) * (aa + 2)) >> 1); }
+    if (aa < n - 2 && off1 <= q) { ++aa; off = off1; }
+    a = aa;
+    b = q - off + aa + 1;
+}

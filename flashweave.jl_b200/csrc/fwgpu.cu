@@ -136,12 +136,14 @@ static int ensure_nz_table(fw_ctx* ctx, NzTable* t) {
 
 // ---- capacity classes shared by the subset-search and HITON launches -------------------------
 static const int kCaps[4] = {32, 64, 128, 224};
-static size_t hiton_smem_bytes(int cap, bool r_in_smem, int nz_words = -1) {
+static size_t hiton_smem_bytes(int cap, bool r_in_smem, int nz_words = -1, bool cache = false) {
     size_t o = r_in_smem ? sizeof(float) * (size_t)cap * cap : 0;
     o = (o + 15) & ~(size_t)15;
     o += sizeof(i64) * (cap + 1) + 4 * sizeof(double) * cap + sizeof(i64) * cap + 2 * sizeof(int) * cap;
     o = (o + 15) & ~(size_t)15;
     if (nz_words >= 0) o += sizeof(i64) * cap + 2 * sizeof(double) * cap + sizeof(unsigned int) * nz_words;
+    o = (o + 15) & ~(size_t)15;
+    if (cache) o += (sizeof(double) + 3 * sizeof(float)) * (size_t)cap * cap + sizeof(float) * cap;
     return o + 16;
 }
 static size_t subsets_smem_bytes(int cap, bool r_in_smem, int nz_words = -1) {
@@ -490,21 +492,21 @@ int32_t fw_test_subsets_batch(fw_ctx* ctx, int32_t kind, int64_t n_jobs, const i
             a.cap = kCaps[c]; a.gscratch = nullptr;
             size_t smem = subsets_smem_bytes(a.cap, true, nzw);
             NEED(smem <= 220 * 1024, FW_ERR_UNSUPPORTED, "fw_test_subsets: job does not fit shared memory (n = %lld rows, %d slots)", (long long)ctx->n, a.cap);
-            if (nzk) { CK(grid_for(subsets_fz_kernel<256, 2, true>, 256, smem, ctx->sm_count, n_sel, &grid)); subsets_fz_kernel<256, 2, true><<<grid, 256, smem, ctx->stream>>>(a); }
-            else if (c < 2) { CK(grid_for(subsets_fz_kernel<128, 2, false>, 128, smem, ctx->sm_count, n_sel, &grid)); subsets_fz_kernel<128, 2, false><<<grid, 128, smem, ctx->stream>>>(a); }
-            else { CK(grid_for(subsets_fz_kernel<256, 2, false>, 256, smem, ctx->sm_count, n_sel, &grid)); subsets_fz_kernel<256, 2, false><<<grid, 256, smem, ctx->stream>>>(a); }
+            if (nzk) { CK(grid_for(subsets_fz_kernel<256, 2, true, false>, 256, smem, ctx->sm_count, n_sel, &grid)); subsets_fz_kernel<256, 2, true, false><<<grid, 256, smem, ctx->stream>>>(a); }
+            else if (c < 2) { CK(grid_for(subsets_fz_kernel<128, 2, false, false>, 128, smem, ctx->sm_count, n_sel, &grid)); subsets_fz_kernel<128, 2, false, false><<<grid, 128, smem, ctx->stream>>>(a); }
+            else { CK(grid_for(subsets_fz_kernel<256, 2, false, false>, 256, smem, ctx->sm_count, n_sel, &grid)); subsets_fz_kernel<256, 2, false, false><<<grid, 256, smem, ctx->stream>>>(a); }
         } else {
             a.cap = max_need;
             size_t smem = subsets_smem_bytes(a.cap, false, nzw);
             NEED(smem <= 200 * 1024, FW_ERR_UNSUPPORTED, "fw_test_subsets: |Z_total| = %d exceeds the supported maximum", max_need - 2);
-            if (nzk) CK(grid_for(subsets_fz_kernel<256, 2, true>, 256, smem, ctx->sm_count, n_sel, &grid));
-            else CK(grid_for(subsets_fz_kernel<256, 2, false>, 256, smem, ctx->sm_count, n_sel, &grid));
+            if (nzk) CK(grid_for(subsets_fz_kernel<256, 2, true, true>, 256, smem, ctx->sm_count, n_sel, &grid));
+            else CK(grid_for(subsets_fz_kernel<256, 2, false, true>, 256, smem, ctx->sm_count, n_sel, &grid));
             size_t per = (size_t)a.cap * a.cap;
             while (grid > 1 && per * grid * sizeof(float) > ((size_t)4 << 30)) grid = (grid + 1) / 2;
             CK(gs.reserve(per * grid));
             a.gscratch = gs.ptr;
-            if (nzk) subsets_fz_kernel<256, 2, true><<<grid, 256, smem, ctx->stream>>>(a);
-            else subsets_fz_kernel<256, 2, false><<<grid, 256, smem, ctx->stream>>>(a);
+            if (nzk) subsets_fz_kernel<256, 2, true, true><<<grid, 256, smem, ctx->stream>>>(a);
+            else subsets_fz_kernel<256, 2, false, true><<<grid, 256, smem, ctx->stream>>>(a);
         }
         ctx->launches++;
         CK(cudaGetLastError());
@@ -802,24 +804,26 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         int grid = 1;
         if (c < 4) {
             a.cap = kCaps[c]; a.gscratch = nullptr;
-            size_t smem = hiton_smem_bytes(a.cap, true, nzw);
+            const bool cache = !nzk && c == 0;            // per-candidate level-1/level-2 tables fit next to R in the 32-slot class
+            size_t smem = hiton_smem_bytes(a.cap, true, nzw, cache);
             NEED(smem <= 220 * 1024, FW_ERR_UNSUPPORTED, "fw_hiton_pc: target does not fit shared memory (n = %lld rows, %d slots)", (long long)ctx->n, a.cap);
-            if (nzk) { CK(grid_for(hiton_fz_kernel<256, 2, true>, 256, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<256, 2, true><<<grid, 256, smem, ctx->stream>>>(a); }
-            else if (c < 2) { CK(grid_for(hiton_fz_kernel<128, 2, false>, 128, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<128, 2, false><<<grid, 128, smem, ctx->stream>>>(a); }
-            else { CK(grid_for(hiton_fz_kernel<256, 2, false>, 256, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<256, 2, false><<<grid, 256, smem, ctx->stream>>>(a); }
+            if (nzk) { CK(grid_for(hiton_fz_kernel<256, 2, true, false, false>, 256, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<256, 2, true, false, false><<<grid, 256, smem, ctx->stream>>>(a); }
+            else if (c == 0) { CK(grid_for(hiton_fz_kernel<128, 2, false, false, true>, 128, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<128, 2, false, false, true><<<grid, 128, smem, ctx->stream>>>(a); }
+            else if (c == 1) { CK(grid_for(hiton_fz_kernel<128, 2, false, false, false>, 128, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<128, 2, false, false, false><<<grid, 128, smem, ctx->stream>>>(a); }
+            else { CK(grid_for(hiton_fz_kernel<256, 2, false, false, false>, 256, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<256, 2, false, false, false><<<grid, 256, smem, ctx->stream>>>(a); }
         } else {
             i64 need = 0; for (int t : sel) need = std::max<i64>(need, hoff[t + 1] - hoff[t] + 2);
             NEED(need <= 3000, FW_ERR_UNSUPPORTED, "fw_hiton_pc: a target has %lld candidates; more than 2998 accepted neighbours are not supported", (long long)need - 2);
             a.cap = (int)need;
             size_t smem = hiton_smem_bytes(a.cap, false, nzw);
-            if (nzk) CK(grid_for(hiton_fz_kernel<256, 2, true>, 256, smem, ctx->sm_count, n_sel, &grid));
-            else CK(grid_for(hiton_fz_kernel<256, 2, false>, 256, smem, ctx->sm_count, n_sel, &grid));
+            if (nzk) CK(grid_for(hiton_fz_kernel<256, 2, true, true, false>, 256, smem, ctx->sm_count, n_sel, &grid));
+            else CK(grid_for(hiton_fz_kernel<256, 2, false, true, false>, 256, smem, ctx->sm_count, n_sel, &grid));
             size_t per = (size_t)a.cap * a.cap;
             while (grid > 1 && per * grid * sizeof(float) > ((size_t)8 << 30)) grid = (grid + 1) / 2;
             CK(gs.reserve(per * grid));
             a.gscratch = gs.ptr;
-            if (nzk) hiton_fz_kernel<256, 2, true><<<grid, 256, smem, ctx->stream>>>(a);
-            else hiton_fz_kernel<256, 2, false><<<grid, 256, smem, ctx->stream>>>(a);
+            if (nzk) hiton_fz_kernel<256, 2, true, true, false><<<grid, 256, smem, ctx->stream>>>(a);
+            else hiton_fz_kernel<256, 2, false, true, false><<<grid, 256, smem, ctx->stream>>>(a);
         }
         ctx->launches++;
         CK(cudaGetLastError());

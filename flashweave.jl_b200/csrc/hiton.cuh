@@ -46,15 +46,90 @@ struct FzSlotTest {
     }
 };
 
-template <int THREADS, int TPT, bool NZ>
-__global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
+// ---- per-candidate tables (capacity class 32): every conditioning subset of one candidate shares its level-1 terms with all
+// subsets that start with the same Z1, and its (X,Y|Z1,Z2) level-2 term with all subsets that start with the same (Z1,Z2).
+// Caching them in shared memory leaves 1 level-1 + 2 level-2 + 1 level-3 step per k = 3 test (was 6 + 3 + 1) with bit-identical
+// arithmetic (same operations, same order, just not repeated).  A Float64 literal (special) anywhere in the tables disables the
+// cache for that candidate, so the generic typed path keeps handling the degenerate cases.
+struct FzTables {
+    float* SQ;      // SQ[z*ld + s] = sqrt(1f0 - r(s,z)^2)
+    float* BX;      // BX[z*ld + s] = pcor(X, s | z)   (level 1, Float32)
+    float* BY;      // BY[z*ld + s] = pcor(Y, s | z)
+    float* A1;      // A1[z]        = pcor(X, Y | z)
+    double* A2;     // A2[z1*ld + z2] = pcor(X, Y | z1, z2) for z1 before z2 in the accepted list (level 2, Float64)
+    int ld;
+};
+
+template <int THREADS>
+__device__ bool fz_build_tables(const float* R, int ld, int xs, int ys, const int* acc, int m, const FzTables& T, int* s_special) {
+    const int tid = threadIdx.x;
+    if (tid == 0) *s_special = 0;
+    // SQ for z in acc, s in acc + {x, y}
+    for (int e = tid; e < m * (m + 2); e += THREADS) {
+        const int ia = e / (m + 2), ib = e % (m + 2);
+        const int z = acc[ia], sl = ib < m ? acc[ib] : (ib == m ? xs : ys);
+        if (sl != z) T.SQ[z * ld + sl] = sq1mf(R[sl * ld + z]);
+    }
+    __syncthreads();
+    bool ok = true;
+    for (int e = tid; e < m * m; e += THREADS) {
+        const int ia = e / m, ib = e % m;
+        const int z = acc[ia];
+        if (ia == ib) {
+            float a1;
+            ok &= p1f(R[xs * ld + ys], R[xs * ld + z], R[ys * ld + z], T.SQ[z * ld + xs], T.SQ[z * ld + ys], a1);
+            T.A1[z] = a1;
+        } else {
+            const int sl = acc[ib];
+            float bx, by;
+            ok &= p1f(R[xs * ld + sl], R[xs * ld + z], R[sl * ld + z], T.SQ[z * ld + xs], T.SQ[z * ld + sl], bx);
+            ok &= p1f(R[ys * ld + sl], R[ys * ld + z], R[sl * ld + z], T.SQ[z * ld + ys], T.SQ[z * ld + sl], by);
+            T.BX[z * ld + sl] = bx; T.BY[z * ld + sl] = by;
+        }
+    }
+    if (!ok) *s_special = 1;
+    __syncthreads();
+    for (int e = tid; e < m * m; e += THREADS) {
+        const int ia = e / m, ib = e % m;
+        if (ia < ib) { const int z1 = acc[ia], z2 = acc[ib]; T.A2[z1 * ld + z2] = p2f(T.A1[z1], T.BX[z1 * ld + z2], T.BY[z1 * ld + z2]); }
+    }
+    __syncthreads();
+    return *s_special == 0;
+}
+
+struct FzCachedTest {
+    CorSlots r; FzTables T; int x, y; FzConsts fc;
+    __device__ __forceinline__ FzTest operator()(int k, int za, int zb, int zc) const {
+        FzTest t; t.df = 0;
+        if (!fc.rows_ok) { t.stat = 0.0; t.pval = 1.0; t.suff = false; return t; }
+        if (k == 1) t.stat = (double)T.A1[za];
+        else if (k == 2) t.stat = T.A2[za * T.ld + zb];
+        else {
+            float z3z2;
+            const bool ok = p1f(r(zc, zb), r(zc, za), r(zb, za), T.SQ[za * T.ld + zc], T.SQ[za * T.ld + zb], z3z2);
+            if (ok) {
+                const double B = p2f(T.BX[za * T.ld + zc], T.BX[za * T.ld + zb], z3z2);     // pcor(X, Z3 | Z1, Z2)
+                const double C = p2f(T.BY[za * T.ld + zc], T.BY[za * T.ld + zb], z3z2);     // pcor(Y, Z3 | Z1, Z2)
+                t.stat = p3d(T.A2[za * T.ld + zb], B, C);
+            } else t.stat = pcor_generic(r, x, y, za, zb, zc, 3);
+        }
+        t.pval = fz_pval_dev(t.stat, fc);
+        t.suff = true;
+        return t;
+    }
+};
+
+// GS: R lives in global scratch (the unbounded capacity class); otherwise it is a plain shared-memory array, which lets
+// the compiler emit LDS instead of generic loads in the test arithmetic.
+template <int THREADS, int TPT, bool NZ, bool GS, bool CACHE>
+__global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? 8 : 1) hiton_fz_kernel(HitonArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     const int cap = a.cap;
     // carve shared memory
     size_t o = 0;
     float* Rs = reinterpret_cast<float*>(smem + o);
-    if (!a.gscratch) o += sizeof(float) * (size_t)cap * cap;
+    if (!GS) o += sizeof(float) * (size_t)cap * cap;
     o = (o + 15) & ~(size_t)15;
     i64* tri_off = reinterpret_cast<i64*>(smem + o); o += sizeof(i64) * (cap + 1);
     double* tpc_stat = reinterpret_cast<double*>(smem + o); o += sizeof(double) * cap;
@@ -69,13 +144,23 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
     i64* slotvar = reinterpret_cast<i64*>(smem + o); if (NZ) o += sizeof(i64) * cap;
     double* mom = reinterpret_cast<double*>(smem + o); if (NZ) o += sizeof(double) * 2 * cap;
     unsigned int* vmask = reinterpret_cast<unsigned int*>(smem + o);
+    if (NZ) o += sizeof(unsigned int) * a.nzt.W;
+    o = (o + 15) & ~(size_t)15;
+    FzTables tb;
+    tb.ld = cap;
+    tb.A2 = reinterpret_cast<double*>(smem + o); if (CACHE) o += sizeof(double) * (size_t)cap * cap;
+    tb.SQ = reinterpret_cast<float*>(smem + o); if (CACHE) o += sizeof(float) * (size_t)cap * cap;
+    tb.BX = reinterpret_cast<float*>(smem + o); if (CACHE) o += sizeof(float) * (size_t)cap * cap;
+    tb.BY = reinterpret_cast<float*>(smem + o); if (CACHE) o += sizeof(float) * (size_t)cap * cap;
+    tb.A1 = reinterpret_cast<float*>(smem + o);
     __shared__ EvalShared sh;
     __shared__ EvalOut ev;
-    __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_accept, s_cnt;
+    __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_accept, s_cnt, s_special;
     __shared__ i64 s_ntests;
     __shared__ u64 s_exec, s_exk[3];
 
-    float* R = a.gscratch ? a.gscratch + (size_t)blockIdx.x * cap * cap : Rs;
+    float* R;
+    if constexpr (GS) R = a.gscratch + (size_t)blockIdx.x * cap * cap; else R = Rs;
     const int ld = cap;
 
     for (;;) {
@@ -145,7 +230,14 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
                     tf.fc = nz_consts(rows, a.n_obs_min);
                 }
                 if (run) {
-                    eval_subsets<THREADS, TPT, 1>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                    bool cached = false;
+                    if constexpr (CACHE) cached = (M >= 3 && a.max_k >= 3) && fz_build_tables<THREADS>(R, ld, 0, ys, acc, M, tb, &s_special);
+                    if (cached) {
+                        FzCachedTest tc; tc.r = tf.r; tc.T = tb; tc.x = 0; tc.y = ys; tc.fc = tf.fc;
+                        eval_subsets<THREADS, TPT, 1>(tc, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                    } else {
+                        eval_subsets<THREADS, TPT, 1>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                    }
                     if (tid == 0) {
                         s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
                         if (ev.sig) { tpc_stat[M] = ev.stat; tpc_p[M] = ev.pval; s_accept = 1; }
@@ -188,7 +280,14 @@ __global__ void __launch_bounds__(THREADS) hiton_fz_kernel(HitonArgs a) {
                     tf.fc = nz_consts(rows, a.n_obs_min);
                 }
                 if (run) {
-                    eval_subsets<THREADS, TPT, 1>(tf, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                    bool cached = false;
+                    if constexpr (CACHE) cached = (macc >= 3 && a.max_k >= 3) && fz_build_tables<THREADS>(R, ld, 0, c, acc, macc, tb, &s_special);
+                    if (cached) {
+                        FzCachedTest tc; tc.r = tf.r; tc.T = tb; tc.x = 0; tc.y = c; tc.fc = tf.fc;
+                        eval_subsets<THREADS, TPT, 1>(tc, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                    } else {
+                        eval_subsets<THREADS, TPT, 1>(tf, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                    }
                     if (tid == 0) {
                         s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
                         if (ev.sig) { pcs_stat[s_npc] = ev.stat; pcs_p[s_npc] = ev.pval; s_accept = 1; }
@@ -233,14 +332,14 @@ struct SubsetsArgs {
     NzTable nzt; i64 n_obs_min;             // fz_nz only
 };
 
-template <int THREADS, int TPT, bool NZ>
+template <int THREADS, int TPT, bool NZ, bool GS>
 __global__ void __launch_bounds__(THREADS) subsets_fz_kernel(SubsetsArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     const int cap = a.cap;
     size_t o = 0;
     float* Rs = reinterpret_cast<float*>(smem + o);
-    if (!a.gscratch) o += sizeof(float) * (size_t)cap * cap;
+    if (!GS) o += sizeof(float) * (size_t)cap * cap;
     o = (o + 15) & ~(size_t)15;
     i64* tri_off = reinterpret_cast<i64*>(smem + o); o += sizeof(i64) * (cap + 1);
     int* acc = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;
@@ -251,7 +350,8 @@ __global__ void __launch_bounds__(THREADS) subsets_fz_kernel(SubsetsArgs a) {
     __shared__ EvalShared sh;
     __shared__ EvalOut ev;
     __shared__ int s_ji, s_cnt;
-    float* R = a.gscratch ? a.gscratch + (size_t)blockIdx.x * cap * cap : Rs;
+    float* R;
+    if constexpr (GS) R = a.gscratch + (size_t)blockIdx.x * cap * cap; else R = Rs;
     const int ld = cap;
     for (;;) {
         __syncthreads();

@@ -49,6 +49,20 @@ __device__ __forceinline__ SubsetCounts subset_counts(int m, int max_k) {
 
 // index -> (k, positions) in the reference's enumeration order.  tri_off[i] = number of
 // triples whose first position is < i (shared-memory table, m+1 entries).
+// 32-bit variant, valid when sc.total < 2^31 and m <= 4096
+__device__ __forceinline__ void unrank_subset32(int idx, int m, int c3, int c2, const i64* tri_off, int& k, int& a, int& b, int& c) {
+    if (idx < c3) {
+        int lo = 0, hi = m - 3;
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((int)tri_off[mid] <= idx) lo = mid; else hi = mid - 1; }
+        int pa, pb;
+        unrank2_small(idx - (int)tri_off[lo], m - lo - 1, pa, pb);
+        k = 3; a = lo; b = lo + 1 + pa; c = lo + 1 + pb;
+    } else if (idx < c3 + c2) {
+        unrank2_small(idx - c3, m, a, b); k = 2; c = 0;
+    } else {
+        k = 1; a = idx - c3 - c2; b = 0; c = 0;
+    }
+}
 __device__ __forceinline__ void unrank_subset(i64 idx, int m, const SubsetCounts& sc, const i64* tri_off, int& k, int& a, int& b, int& c) {
     if (idx < sc.c3) {
         int lo = 0, hi = m - 3;              // largest i with tri_off[i] <= idx
@@ -84,13 +98,16 @@ __device__ void eval_subsets(const TestFn& test, const int* acc, int m, int max_
     i64 best_idx = -1; double b_stat = 0.0, b_p = -1.0; i64 b_df = 0;
     i64 executed = 0;
     bool any_fail = false;
+    const bool small = sc.total < ((i64)1 << 30) && m <= 4096;     // 32-bit index arithmetic in the hot loop
+    const int c3s = (int)(small ? sc.c3 : 0), c2s = (int)(small ? sc.c2 : 0);
     for (i64 base = 0; base < limit; base += (i64)NG * TPT) {
 #pragma unroll
         for (int u = 0; u < TPT; ++u) {
             i64 idx = base + (i64)u * NG + grp;
             if (idx < limit && my_fail == FW_INF_IDX) {
                 int k, a, b, c;
-                unrank_subset(idx, m, sc, tri_off, k, a, b, c);
+                if (small) unrank_subset32((int)idx, m, c3s, c2s, tri_off, k, a, b, c);
+                else unrank_subset(idx, m, sc, tri_off, k, a, b, c);
                 auto r = test(k, acc[a], acc[b], acc[c]);
                 bool sig = (r.pval < alpha) && r.suff;
                 bool stop = !sig || (max_tests > 0 && idx + 1 >= max_tests);
