@@ -192,12 +192,102 @@ __device__ void mi_count_warp(const MiTable& t, i64 X, i64 Y, const i64* Z, int 
     __syncwarp();
 }
 
+// ---- binary fast path (L = 2, kind "mi", both variables with 2 levels) ------------------------------------------------------
+// Words outer / strata inner: per word the 2^K stratum masks come from a mask tree over the Z planes, and each stratum needs
+// only popc(m), popc(m&x), popc(m&y), popc(m&x&y) (the other cells follow by inclusion-exclusion).  After the warp reduction
+// lane c owns cell (a = c&1, b = (c>>1)&1, stratum = c>>2); margins are 2 shuffles away, so the MI / df epilogue needs no
+// shared-memory table.  Same integers, same formulas as the generic path (statfuns.jl:163-305).
+template <int K>
+__device__ MiResult mi_test_warp_bin(const MiTable& t, i64 X, i64 Y, const i64* Z, i64 hps, i64 n_obs_min) {
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    constexpr int S = 1 << K;
+    int cn[S], cx[S], cy[S], cxy[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { cn[s] = 0; cx[s] = 0; cy[s] = 0; cxy[s] = 0; }
+    const unsigned int* px = t.planes + (size_t)X * t.W;
+    const unsigned int* py = t.planes + (size_t)Y * t.W;
+    const unsigned int* pz0 = K > 0 ? t.planes + (size_t)Z[0] * t.W : nullptr;
+    const unsigned int* pz1 = K > 1 ? t.planes + (size_t)Z[1] * t.W : nullptr;
+    const unsigned int* pz2 = K > 2 ? t.planes + (size_t)Z[2] * t.W : nullptr;
+    for (int w = lane; w < t.W; w += 32) {
+        const unsigned int valid = (w == t.W - 1) ? t.tail_mask : 0xffffffffu;
+        const unsigned int x = __ldg(px + w), y = __ldg(py + w);
+        unsigned int m[S];
+        m[0] = valid;
+        if (K > 0) { const unsigned int z = __ldg(pz0 + w); m[1] = m[0] & z; m[0] &= ~z; }
+        if (K > 1) { const unsigned int z = __ldg(pz1 + w);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) { m[s + 2] = m[s] & z; m[s] &= ~z; } }
+        if (K > 2) { const unsigned int z = __ldg(pz2 + w);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { m[s + 4] = m[s] & z; m[s] &= ~z; } }
+        const unsigned int xy = x & y;
+#pragma unroll
+        for (int s = 0; s < S; ++s) { cn[s] += __popc(m[s]); cx[s] += __popc(m[s] & x); cy[s] += __popc(m[s] & y); cxy[s] += __popc(m[s] & xy); }
+    }
+    int mine = 0;                                   // N(X = a, Y = b | stratum) for this lane's cell
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int n = __reduce_add_sync(full, cn[s]), nx = __reduce_add_sync(full, cx[s]);
+        const int ny = __reduce_add_sync(full, cy[s]), nxy = __reduce_add_sync(full, cxy[s]);
+        if ((lane >> 2) == s) {
+            const int a = lane & 1, b = (lane >> 1) & 1;
+            mine = a ? (b ? nxy : nx - nxy) : (b ? ny - nxy : n - nx - ny + nxy);
+        }
+    }
+    const int a = lane & 1, b = (lane >> 1) & 1;
+    const int mik = mine + __shfl_xor_sync(full, mine, 2);       // sum over b
+    const int mjk = mine + __shfl_xor_sync(full, mine, 1);       // sum over a
+    const int mk = mik + __shfl_xor_sync(full, mik, 1);
+    const i64 n_obs = __reduce_add_sync(full, mine);
+    const unsigned int present = __ballot_sync(full, mk > 0 && (lane & 3) == 0);
+    const int levels_z = K > 0 ? __popc(present) : 1;
+    MiResult r;
+    bool ok;
+    if (K > 0) ok = ((double)n_obs / (double)(4 * levels_z)) > (double)hps;                       // tests.jl:210
+    else ok = !(n_obs < n_obs_min) && (((double)n_obs / 4.0) > (double)hps);                      // tests.jl:58
+    if (!ok) { r.stat = 0.0; r.pval = 1.0; r.df = 0; r.suff = false; return r; }
+    double pos = 0.0, neg = 0.0; int n_pos = 0, n_neg = 0;
+    if (mine != 0 && mik != 0 && mjk != 0) {
+        const double num = K > 0 ? (double)((i64)mk * mine) : (double)(n_obs * mine);
+        const double tt = log(num / (double)((i64)mik * mjk)) * (double)mine;
+        if (a == b) { pos = tt; n_pos = mine; } else { neg = tt; n_neg = mine; }
+    }
+    for (int o = 16; o > 0; o >>= 1) { pos += __shfl_xor_sync(full, pos, o); neg += __shfl_xor_sync(full, neg, o); }
+    n_pos = __reduce_add_sync(full, n_pos); n_neg = __reduce_add_sync(full, n_neg);
+    // df: strata whose 2x2 slice has two non-empty rows and two non-empty columns (statfuns.jl:281-305)
+    const unsigned int rows_nz = __ballot_sync(full, mik > 0 && b == 0);      // bits 4s + a
+    const unsigned int cols_nz = __ballot_sync(full, mjk > 0 && a == 0);      // bits 4s + 2b
+    int df = 0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const unsigned int rb = (rows_nz >> (4 * s)) & 3u, cb = (cols_nz >> (4 * s)) & 5u;
+        df += (rb == 3u && cb == 5u) ? 1 : 0;
+    }
+    const i64 n_mi = K > 0 ? (i64)(n_pos + n_neg) : n_obs;
+    double mi = (pos + neg) / (double)n_mi;
+    if (neg * ((double)n_neg / (double)n_mi) > pos * ((double)n_pos / (double)n_mi)) mi *= -1.0;
+    r.stat = mi; r.df = df; r.pval = mi_pval_dev(fabs(mi), df, n_obs); r.suff = true;
+    return r;
+}
+
 // full single test, one warp: tests.jl:28-77 (k = 0; the caller's X-trimmed view, tests.jl:412-416) and :184-229 (k >= 1;
 // the view trimmed for X and Y as hiton.jl:41-50,85 does)
 __device__ MiResult mi_test_warp(const MiTable& t, i64 X, i64 Y, const i64* Z, int k, i64 hps, i64 n_obs_min, int* tab) {
     MiResult r;
     const bool trim_x = mi_needs_nz_view(t, X);
     const int lvx = t.levels[X], lvy = t.levels[Y];
+    if (t.L == 2 && !t.nz && lvx == 2 && lvy == 2) {
+        if (k == 0) {
+            // weak pre-check of tests.jl:9-20: rows / ((2-2)(2-2)) = Inf > hps unless there are no rows
+            if ((i64)t.n < n_obs_min || t.n == 0) { r.stat = 0.0; r.pval = 1.0; r.df = 0; r.suff = false; return r; }
+            return mi_test_warp_bin<0>(t, X, Y, Z, hps, n_obs_min);
+        }
+        if (k == 1) return mi_test_warp_bin<1>(t, X, Y, Z, hps, n_obs_min);
+        if (k == 2) return mi_test_warp_bin<2>(t, X, Y, Z, hps, n_obs_min);
+        return mi_test_warp_bin<3>(t, X, Y, Z, hps, n_obs_min);
+    }
     if (k == 0) {
         // tests.jl:86-92 and the weak pre-check sufficient_power(X, Y, data, ...) of tests.jl:9-20 on the X-trimmed view
         if (lvx < 2) { r.stat = 0.0; r.pval = 1.0; r.df = 0; r.suff = false; return r; }
