@@ -117,7 +117,8 @@ def cpu_reference_run(a, steps, warmup, blocks):
     synth = fwload.load_sub("synth")
     p_s = min(a.p, blocks * a.B)
     x = synth.clique(p_s, a.n, B=a.B, seed=synth.BASE_SEED + 3)
-    threads = fwo.num_threads()
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the oracle sets its own thread count)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     rates, e2e_rates, secs_all, tests = [], [], [], 0
     for it in range(warmup + steps):
         ora = fwo.Oracle(x.T, "fz", cont32=True)
@@ -269,13 +270,16 @@ def main_ours(a, rank, world, local_rank):
     pk = peaks()
     k_ms = float(np.mean(kern_ms))
     alg_bytes = float(12 * exec_k[0] + 24 * exec_k[1] + 40 * exec_k[2])      # 4*C(k+2,2) B per test
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_hiton_traffic.json")
-    if os.path.exists(tpath):
+    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this workload (profiles/)
+    traffic = traffic_cor = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and p == 50000 and n == 10000 and world == 1:
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("hiton_fz_kernel_C4_dram_bytes_per_launch")
+            traffic_cor = tj.get("cor_tc_kernel_C4_dram_bytes_per_launch")
         except Exception:
-            traffic = None
+            pass
     roofline = {"kernel": "hiton_fz_kernel (si_HITON_PC conditional phase; dominant kernel of the timed `value` region)",
                 "bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["which"],
@@ -284,7 +288,8 @@ def main_ours(a, rank, world, local_rank):
     cor_ms = float(np.mean(phase["cor_ms"]))
     roofline_cor = {"kernel": "cor_mat GEMM (fw_cor_matrix; dominant kernel of the e2e region)", "bound": "tensor",
                     "achieved": 2.0 * n * p * p / (cor_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": 2.0 * n * p * p / (cor_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": None, "peak_source": pk["which"], "kernel_ms": cor_ms}
+                    "frac": 2.0 * n * p * p / (cor_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": traffic_cor, "peak_source": pk["which"], "kernel_ms": cor_ms,
+                    "note": "useful flop = 2*n*p^2 (the 3-term bf16 split and the symmetric half do not change the numerator); includes the standardise+split kernel"}
 
     line = {
         "metric": "CI-tests/sec (cond_tests_ref/s, HITON-PC conditional phase)", "value": value, "unit": "tests/s",

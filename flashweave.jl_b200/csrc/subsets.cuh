@@ -100,9 +100,11 @@ __device__ void eval_subsets(const TestFn& test, const int* acc, int m, int max_
     bool any_fail = false;
     const bool small = sc.total < ((i64)1 << 30) && m <= 4096;     // 32-bit index arithmetic in the hot loop
     const int c3s = (int)(small ? sc.c3 : 0), c2s = (int)(small ? sc.c2 : 0);
-    for (i64 base = 0; base < limit; base += (i64)NG * TPT) {
-#pragma unroll
-        for (int u = 0; u < TPT; ++u) {
+    // chunk schedule: a first small chunk (NG tests) catches the early exits of the reference cheaply; later chunks are
+    // NG*TPT tests, so an all-significant scan pays few barriers
+    int tpt = 1;
+    for (i64 base = 0; base < limit;) {
+        for (int u = 0; u < tpt; ++u) {
             i64 idx = base + (i64)u * NG + grp;
             if (idx < limit && my_fail == FW_INF_IDX) {
                 int k, a, b, c;
@@ -115,10 +117,11 @@ __device__ void eval_subsets(const TestFn& test, const int* acc, int m, int max_
                 else if (r.pval >= b_p) { best_idx = idx; b_stat = r.stat; b_p = r.pval; b_df = r.df; }
             }
         }
-        i64 end = base + (i64)NG * TPT;
+        i64 end = base + (i64)NG * tpt;
         executed = end < limit ? end : limit;
         any_fail = __syncthreads_or(my_fail != FW_INF_IDX);
         if (any_fail) break;
+        base = end; tpt = TPT;
     }
     if (any_fail) {
         if (my_fail != FW_INF_IDX && leader) atomicMin(&sh->fail_idx, (u64)my_fail);
