@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "fw_create", "fw_destroy", "fw_last_error", "fw_set_index_base", "fw_stream", "fw_synchronize", "fw_launch_count", "fw_last_timing",
     "fw_hiton_exec_by_k",
     "fw_set_data_f32", "fw_set_data_i32", "fw_adopt_data_f32_device", "fw_set_n_obs", "fw_levels", "fw_cor_matrix",
-    "fw_set_cor_f32", "fw_adopt_cor_device", "fw_cor_device_ptr", "fw_test_batch", "fw_test_subsets", "fw_test_subsets_batch",
+    "fw_set_cor_f32", "fw_adopt_cor_device", "fw_cor_device_ptr", "fw_adopt_cor_device_rows", "fw_cor_prepare", "fw_cor_rows", "fw_cor_symmetrize", "fw_test_batch", "fw_test_subsets", "fw_test_subsets_batch",
     "fw_pairwise", "fw_pairwise_copy", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_capacity",
     "fw_build_info",
 ]
@@ -90,6 +90,10 @@ def load_library():
         "fw_set_cor_f32": (i32, [vp, vp, i64]),
         "fw_adopt_cor_device": (i32, [vp, vp, i64]),
         "fw_cor_device_ptr": (vp, [vp]),
+        "fw_adopt_cor_device_rows": (i32, [vp, vp, i64, i64]),
+        "fw_cor_prepare": (i32, [vp, vp]),
+        "fw_cor_rows": (i32, [vp, i32, i32]),
+        "fw_cor_symmetrize": (i32, [vp]),
         "fw_test_batch": (i32, [vp, i32, i64, vp, vp, vp, vp, i64, i64, vp]),
         "fw_test_subsets": (i32, [vp, i32, i64, i64, vp, i64, i32, dbl, i64, i64, i64, vp, vp, vp, vp, vp]),
         "fw_test_subsets_batch": (i32, [vp, i32, i64, vp, vp, vp, vp, i32, dbl, i64, i64, i64, vp, vp, vp, vp, vp]),
@@ -280,6 +284,22 @@ class Engine:
     def cor_device_ptr(self):
         return self.L.fw_cor_device_ptr(self.h)
 
+    # row-sharded cor_mat (multi-GPU): see parallel.sharded_cor
+    def adopt_cor_device_rows(self, dev_ptr, p, rows_allocated):
+        self._ck(self.L.fw_adopt_cor_device_rows(self.h, C.c_void_p(dev_ptr), p, rows_allocated))
+        self.p = p
+
+    def cor_prepare(self):
+        nb = C.c_int32(0)
+        self._ck(self.L.fw_cor_prepare(self.h, C.byref(nb)))
+        return int(nb.value)
+
+    def cor_rows(self, tile_row_begin, tile_row_end):
+        self._ck(self.L.fw_cor_rows(self.h, tile_row_begin, tile_row_end))
+
+    def cor_symmetrize(self):
+        self._ck(self.L.fw_cor_symmetrize(self.h))
+
     # -- tests ------------------------------------------------------------------------------
     def test_batch(self, X, Y, Zs=None, k=None, hps=5, n_obs_min=0, kind=None):
         X, Y = _i64(X), _i64(Y)
@@ -359,13 +379,15 @@ class Engine:
 
     # -- HITON-PC ---------------------------------------------------------------------------------
     def si_HITON_PC(self, targets, max_k=3, alpha=0.01, hps=5, n_obs_min=0, max_tests=10_000_000, kind=None, want_tpc=True,
-                    buffers=None):
+                    buffers=None, reuse_buffers=False):
         """si_HITON_PC for each target (hiton.jl:283-400; parallel="single" semantics: no whitelist)."""
         t = _i64(np.atleast_1d(targets))
         nt = len(t)
         cap = C.c_int64(0)
         self._ck(self.L.fw_hiton_pc_capacity(self.h, nt, _p(t), C.byref(cap)))
         cp = max(int(cap.value), 1)
+        if buffers is None and reuse_buffers:
+            buffers = getattr(self, "_hbuf", None)        # grow-only host buffers: the returned views alias them until the next call
         if buffers is not None and buffers["cap"] >= cp and buffers["nt"] >= nt:
             b = buffers
         else:
@@ -373,6 +395,8 @@ class Engine:
                  "pcn": np.zeros(cp, np.int64), "pcs": np.zeros(cp), "pcp": np.zeros(cp),
                  "tpcc": np.zeros(max(nt, 1), np.int64), "tpcn": np.zeros(cp, np.int64), "tpcs": np.zeros(cp), "tpcp": np.zeros(cp),
                  "ntests": np.zeros(max(nt, 1), np.int64)}
+            if reuse_buffers:
+                self._hbuf = b
         ex = C.c_int64(0)
         tp = want_tpc
         self._ck(self.L.fw_hiton_pc(self.h, KINDS[kind or self.kind], nt, _p(t), max_k, alpha, hps, n_obs_min, max_tests,

@@ -125,8 +125,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// Tiles: upper-triangular tile rows [bi0, bi0 + nbi) of an nb x nb tile grid (blockIdx.x enumerates them row-major).  mirror != 0
+// also writes the transposed tile (single-GPU mode); mirror == 0 (row-sharded mode) leaves the lower triangle to
+// cor_symmetrize_kernel after the ranks have exchanged their row blocks, and only mirrors inside diagonal tiles.
 __global__ void __launch_bounds__(NTHREADS, 1) cor_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                                                             float* __restrict__ C, i64 p, int num_kb, int nb) {
+                                                             float* __restrict__ C, i64 p, int num_kb, int nb, int bi0, int mirror) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B tiles need 1024-byte alignment
@@ -140,7 +143,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) cor_tc_kernel(const __grid_consta
     // tile of the upper triangle: row bi has nb - bi tiles
     int bi, bj;
     {
-        const long long t = blockIdx.x;
+        // global index of this tile in the row-major enumeration of the whole upper triangle
+        const long long t = (long long)blockIdx.x + ((long long)bi0 * nb - (long long)bi0 * (bi0 - 1) / 2);
         const double f = 2.0 * nb + 1.0;
         int r = (int)((f - sqrt(f * f - 8.0 * (double)t)) * 0.5);
         if (r < 0) r = 0;
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cor_tc_kernel(const __grid_consta
                 const bool ok = row < p && col < p && (!diag || col >= row);
                 if (ok) {
                     C[row * p + col] = x;
-                    C[col * p + row] = x;                              // mirror (coalesced across the warp: consecutive rows)
+                    if (mirror || diag) C[col * p + row] = x;          // mirror (coalesced across the warp: consecutive rows)
                 }
             }
         }
@@ -302,7 +306,10 @@ struct Scratch {
     ~Scratch() { if (z) cudaFree(z); }
 };
 
-static cudaError_t run(Scratch& S, const float* d_data, i64 n, i64 p, i64 ld, float* d_cor, cudaStream_t st, int* n_launch, std::string* msg) {
+struct Prepared { CUtensorMap tm_hi, tm_lo; i64 kp = 0, p_pad = 0; int nb = 0; bool valid = false; };
+
+// standardise + split the resident table (once per table) and build the TMA descriptors
+static cudaError_t prepare(Scratch& S, Prepared& P, const float* d_data, i64 n, i64 p, i64 ld, cudaStream_t st, int* n_launch, std::string* msg) {
     const i64 kp = (n + BK - 1) / BK * BK;
     const i64 p_pad = (p + BM - 1) / BM * BM;
     cudaError_t e = S.reserve((size_t)2 * p_pad * kp);
@@ -312,17 +319,48 @@ static cudaError_t run(Scratch& S, const float* d_data, i64 n, i64 p, i64 ld, fl
     standardize_split_kernel<256><<<(unsigned)p_pad, 256, 0, st>>>(d_data, n, ld, p, kp, zhi, zlo);
     (*n_launch)++;
     e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "standardize_split_kernel"; return e; }
-    CUtensorMap tm_hi, tm_lo;
-    e = encode_map(&tm_hi, zhi, kp, p_pad, msg); if (e != cudaSuccess) return e;
-    e = encode_map(&tm_lo, zlo, kp, p_pad, msg); if (e != cudaSuccess) return e;
+    e = encode_map(&P.tm_hi, zhi, kp, p_pad, msg); if (e != cudaSuccess) return e;
+    e = encode_map(&P.tm_lo, zlo, kp, p_pad, msg); if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(cor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute(cor_tc_kernel)"; return e; }
-    const int nb = (int)(p_pad / BM);
-    const long long tiles = (long long)nb * (nb + 1) / 2;
-    cor_tc_kernel<<<(unsigned)tiles, NTHREADS, SMEM_BYTES, st>>>(tm_hi, tm_lo, d_cor, p, (int)(kp / BK), nb);
-    (*n_launch)++;
-    e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "cor_tc_kernel"; return e; }
+    P.kp = kp; P.p_pad = p_pad; P.nb = (int)(p_pad / BM); P.valid = true;
     return cudaSuccess;
+}
+
+// upper-triangular tiles of tile rows [bi0, bi1)
+static cudaError_t run_rows(const Prepared& P, float* d_cor, i64 p, int bi0, int bi1, bool mirror, cudaStream_t st, int* n_launch, std::string* msg) {
+    if (bi1 > P.nb) bi1 = P.nb;
+    if (bi0 >= bi1) return cudaSuccess;
+    const long long first = (long long)bi0 * P.nb - (long long)bi0 * (bi0 - 1) / 2;
+    const long long last = (long long)bi1 * P.nb - (long long)bi1 * (bi1 - 1) / 2;
+    cor_tc_kernel<<<(unsigned)(last - first), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(P.kp / BK), P.nb, bi0, mirror ? 1 : 0);
+    (*n_launch)++;
+    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "cor_tc_kernel"; return e; }
+    return cudaSuccess;
+}
+
+static cudaError_t run(Scratch& S, const float* d_data, i64 n, i64 p, i64 ld, float* d_cor, cudaStream_t st, int* n_launch, std::string* msg) {
+    Prepared P;
+    cudaError_t e = prepare(S, P, d_data, n, p, ld, st, n_launch, msg);
+    if (e != cudaSuccess) return e;
+    return run_rows(P, d_cor, p, 0, P.nb, true, st, n_launch, msg);
+}
+
+// lower triangle <- upper triangle (after the row blocks of all ranks are in place): 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256) cor_symmetrize_kernel(float* __restrict__ C, i64 p) {
+    __shared__ float tile[32][33];
+    const int bx = blockIdx.x, by = blockIdx.y;         // source tile (rows by, cols bx) with bx >= by
+    if (bx < by) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const i64 row = (i64)by * 32 + r, col = (i64)bx * 32 + tx;
+        tile[r][tx] = (row < p && col < p) ? C[row * p + col] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const i64 row = (i64)bx * 32 + r, col = (i64)by * 32 + tx;      // destination (transposed position)
+        if (row < p && col < p && row > col) C[row * p + col] = tile[tx][r];
+    }
 }
 
 }  // namespace cortc

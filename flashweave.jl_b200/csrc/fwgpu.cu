@@ -82,6 +82,7 @@ struct fw_ctx {
     DevBuf<int> d_counter; DevBuf<u64> d_exec;
     PairwiseScratch pw;
     cortc::Scratch tc;
+    cortc::Prepared tcp;                 // standardised table + TMA descriptors of the row-sharded cor_mat path
     // fw_hiton_pc work buffers (grow-only, reused across calls)
     struct HitonBufs {
         DevBuf<i64> dt, doff, dpcn, dtpcn, dpcc, dtpcc, dnt; DevBuf<double> dpcs, dpcp, dtpcs, dtpcp; DevBuf<int> dsel, dorder, dstatus; DevBuf<float> gs;
@@ -321,7 +322,56 @@ int32_t fw_adopt_cor_device(fw_ctx* ctx, const float* dev_cor, int64_t p) {
     ctx->cor_p = p; if (ctx->p == 0) ctx->p = p;
     return FW_OK;
 }
+int32_t fw_adopt_cor_device_rows(fw_ctx* ctx, const float* dev_cor, int64_t p, int64_t rows_allocated) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(dev_cor && p > 0 && rows_allocated >= p, FW_ERR_INVALID, "fw_adopt_cor_device_rows: bad arguments");
+    ctx->d_cor.adopt(const_cast<float*>(dev_cor), (size_t)rows_allocated * p);
+    ctx->cor_p = p; if (ctx->p == 0) ctx->p = p;
+    return FW_OK;
+}
 void* fw_cor_device_ptr(fw_ctx* ctx) { return ctx ? (void*)ctx->d_cor.ptr : nullptr; }
+
+// ---- row-sharded cor_mat (multi-GPU) -------------------------------------------------------------
+// fw_cor_prepare: standardise + split the resident table once.  fw_cor_rows: the upper-triangular 128x128 tiles of tile rows
+// [tile_row_begin, tile_row_end) into the resident / adopted cor_mat buffer (which must hold at least tile_row_end*128 rows of
+// p floats).  After the ranks have exchanged their row blocks (NCCL all-gather on the adopted buffer), fw_cor_symmetrize copies
+// the upper triangle to the lower one; the result is bit-identical to fw_cor_matrix on one GPU.
+int32_t fw_cor_prepare(fw_ctx* ctx, int32_t* n_tile_rows) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(ctx->data_kind == 0, FW_ERR_STATE, "fw_cor_prepare: no continuous table resident (call fw_set_data_f32 first)");
+    CK(cudaSetDevice(ctx->device));
+    std::string msg; int nl = 0;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    cudaError_t e = cortc::prepare(ctx->tc, ctx->tcp, ctx->d_data_f32.ptr, ctx->n, ctx->p, ctx->ld, ctx->stream, &nl, &msg);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_cor_prepare: %s: %s", msg.c_str(), cudaGetErrorString(e));
+    if (n_tile_rows) *n_tile_rows = ctx->tcp.nb;
+    return FW_OK;
+}
+int32_t fw_cor_rows(fw_ctx* ctx, int32_t tile_row_begin, int32_t tile_row_end) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(ctx->tcp.valid, FW_ERR_STATE, "fw_cor_rows: call fw_cor_prepare first");
+    NEED(ctx->d_cor.ptr && ctx->cor_p == ctx->p, FW_ERR_STATE, "fw_cor_rows: no cor_mat buffer (fw_adopt_cor_device)");
+    NEED(tile_row_begin >= 0 && tile_row_end >= tile_row_begin, FW_ERR_INVALID, "fw_cor_rows: bad tile-row range");
+    NEED(ctx->d_cor.cap >= (size_t)std::min<i64>((i64)tile_row_end * 128, ctx->p) * ctx->p, FW_ERR_INVALID, "fw_cor_rows: cor_mat buffer too small");
+    CK(cudaSetDevice(ctx->device));
+    std::string msg; int nl = 0;
+    cudaError_t e = cortc::run_rows(ctx->tcp, ctx->d_cor.ptr, ctx->p, tile_row_begin, tile_row_end, false, ctx->stream, &nl, &msg);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_cor_rows: %s: %s", msg.c_str(), cudaGetErrorString(e));
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_valid[0] = true;
+    return FW_OK;
+}
+int32_t fw_cor_symmetrize(fw_ctx* ctx) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_cor_symmetrize: no cor_mat resident");
+    CK(cudaSetDevice(ctx->device));
+    const unsigned nb = (unsigned)((ctx->cor_p + 31) / 32);
+    cortc::cor_symmetrize_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->d_cor.ptr, ctx->cor_p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return FW_OK;
+}
 
 int32_t fw_cor_matrix(fw_ctx* ctx, float* host_out) {
     if (!ctx) return FW_ERR_INVALID;

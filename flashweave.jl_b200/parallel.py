@@ -53,3 +53,38 @@ class MergedResult:
 
     def pc(self, i):
         return self._pc[i]
+
+
+# ---- row-sharded correlation matrix -------------------------------------------------------------------------------------
+def cor_groups(n_tile_rows, world):
+    """Split the tile rows of the upper-triangular cor_mat GEMM into 2*world equal contiguous groups; rank r owns group r
+    (long tile rows) and group 2*world-1-r (short ones), so every rank computes the same number of 128x128 tiles.
+    Returns (rows_per_group, padded tile-row count)."""
+    g = 2 * world
+    h = (n_tile_rows + g - 1) // g
+    return h, h * g
+
+
+def sharded_cor(dist, eng, cor_tensor, rev_group):
+    """cor_mat = Float32.(cor(data)) computed by all ranks together (learning.jl:42-44): every rank computes the upper tiles of
+    its two tile-row groups into `cor_tensor` (a [rows_pad, p] float32 CUDA tensor adopted by the engine), the row blocks are
+    exchanged by two in-place all-gathers over NVLink (the second in reversed rank order, `rev_group`), and the lower triangle
+    is filled from the upper one.  Bit-identical to Engine.cor() on one GPU."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    nb = eng.cor_prepare()
+    h, nb_pad = cor_groups(nb, world)
+    rows_pad, p = cor_tensor.shape
+    assert rows_pad >= nb_pad * 128, (rows_pad, nb_pad)
+    eng.cor_rows(rank * h, (rank + 1) * h)
+    gb = 2 * world - 1 - rank
+    eng.cor_rows(gb * h, (gb + 1) * h)
+    eng.synchronize()
+    hr = h * 128
+    top = cor_tensor[: world * hr]
+    bot = cor_tensor[world * hr: 2 * world * hr]
+    dist.all_gather_into_tensor(top, top[rank * hr:(rank + 1) * hr])
+    rr = world - 1 - rank                                   # this rank's position in the reversed group
+    dist.all_gather_into_tensor(bot, bot[rr * hr:(rr + 1) * hr], group=rev_group)
+    torch.cuda.synchronize()
+    eng.cor_symmetrize()

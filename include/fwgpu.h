@@ -90,6 +90,15 @@ int32_t fw_set_cor_f32(fw_ctx* ctx, const float* host_cor, int64_t p);
 int32_t fw_adopt_cor_device(fw_ctx* ctx, const float* dev_cor, int64_t p);
 /* device pointer of the resident cor_mat (p*p floats), e.g. to broadcast it with NCCL */
 void* fw_cor_device_ptr(fw_ctx* ctx);
+/* Row-sharded cor_mat for several GPUs (same src/learning.jl:42-44 result, split over ranks): adopt a buffer of
+ * rows_allocated >= p rows, standardise the table once (fw_cor_prepare returns the number of 128-row tile rows), compute the
+ * upper-triangular tiles of this rank's tile rows (fw_cor_rows), exchange the row blocks with NCCL (all-gather on the adopted
+ * buffer, done by the host language), then copy the upper triangle to the lower one (fw_cor_symmetrize).  The result is
+ * bit-identical to fw_cor_matrix on one GPU. */
+int32_t fw_adopt_cor_device_rows(fw_ctx* ctx, const float* dev_cor, int64_t p, int64_t rows_allocated);
+int32_t fw_cor_prepare(fw_ctx* ctx, int32_t* n_tile_rows);
+int32_t fw_cor_rows(fw_ctx* ctx, int32_t tile_row_begin, int32_t tile_row_end);
+int32_t fw_cor_symmetrize(fw_ctx* ctx);
 
 /* ---- single tests ---------------------------------------------------------------------- */
 /* test(X, Y, Zs, data, test_obj, ...) for a batch of independent tests
