@@ -184,12 +184,11 @@ def main_ours(a, rank, world, local_rank):
         gen_s = time.time() - t0
     d_x = torch.empty((p, n), dtype=torch.float32, device="cuda")
     eng = fw.Engine(local_rank)
-    d_cor = rev_group = None
+    d_cor = None
     if dist is not None:
         # row-sharded cor_mat: every rank computes 1/N of the tiles, two in-place all-gathers, symmetrise (parallel.sharded_cor)
         h, nb_pad = par.cor_groups((p + 127) // 128, world)
         d_cor = torch.empty((nb_pad * 128, p), dtype=torch.float32, device="cuda")
-        rev_group = dist.new_group(list(reversed(range(world))))
     ext = torch.cuda.ExternalStream(eng.stream)
 
     h2d_ms = []
@@ -209,7 +208,7 @@ def main_ours(a, rank, world, local_rank):
             eng.cor(want_host=False)                                 # cor_mat = Float32.(cor(data))
         else:
             eng.adopt_cor_device_rows(d_cor.data_ptr(), p, d_cor.shape[0])
-            par.sharded_cor(dist, eng, d_cor, rev_group)
+            par.sharded_cor(dist, eng, d_cor)
         eng.synchronize()
         cor_wall_ms.append((time.perf_counter() - tc) * 1e3)
         eng.pw_univar_neighbors(alpha=a.alpha, n_obs_min=20, want_host=False)

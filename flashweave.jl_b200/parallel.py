@@ -65,11 +65,11 @@ def cor_groups(n_tile_rows, world):
     return h, h * g
 
 
-def sharded_cor(dist, eng, cor_tensor, rev_group):
+def sharded_cor(dist, eng, cor_tensor, rev_group=None):
     """cor_mat = Float32.(cor(data)) computed by all ranks together (learning.jl:42-44): every rank computes the upper tiles of
     its two tile-row groups into `cor_tensor` (a [rows_pad, p] float32 CUDA tensor adopted by the engine), the row blocks are
-    exchanged by two in-place all-gathers over NVLink (the second in reversed rank order, `rev_group`), and the lower triangle
-    is filled from the upper one.  Bit-identical to Engine.cor() on one GPU."""
+    exchanged by two all-gathers over NVLink (the top half in place, the bottom half into views placed in reversed rank
+    order), and the lower triangle is filled from the upper one.  Bit-identical to Engine.cor() on one GPU."""
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
     nb = eng.cor_prepare()
@@ -84,7 +84,8 @@ def sharded_cor(dist, eng, cor_tensor, rev_group):
     top = cor_tensor[: world * hr]
     bot = cor_tensor[world * hr: 2 * world * hr]
     dist.all_gather_into_tensor(top, top[rank * hr:(rank + 1) * hr])
-    rr = world - 1 - rank                                   # this rank's position in the reversed group
-    dist.all_gather_into_tensor(bot, bot[rr * hr:(rr + 1) * hr], group=rev_group)
+    # rank i owns bottom group world-1-i: receive its block at that position
+    views = [bot[(world - 1 - i) * hr:(world - i) * hr] for i in range(world)]
+    dist.all_gather(views, views[rank])
     torch.cuda.synchronize()
     eng.cor_symmetrize()

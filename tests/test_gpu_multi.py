@@ -37,9 +37,8 @@ def _worker(rank, world, port, q):
     eng.adopt_data_device(d_x.data_ptr(), n, p, "fz")
     h, nb_pad = par.cor_groups((p + 127) // 128, world)
     d_cor = torch.full((nb_pad * 128, p), float("nan"), dtype=torch.float32, device="cuda")
-    rev = dist.new_group(list(reversed(range(world))))
     eng.adopt_cor_device_rows(d_cor.data_ptr(), p, d_cor.shape[0])
-    par.sharded_cor(dist, eng, d_cor, rev)
+    par.sharded_cor(dist, eng, d_cor)
     eng.synchronize()
     sharded = d_cor[:p].cpu().numpy()
     # single-GPU result on the same device
