@@ -175,9 +175,28 @@ def main_ours(a, rank, world, local_rank):
         torch.cuda.synchronize()
 
     p, n = a.p, a.n
-    # ---- setup (untimed): synthetic table on rank 0's pinned host memory -----------------------------
+    # ---- setup (untimed): synthetic table in pinned host memory ---------------------------------------------------
+    # N = 1: rank 0's pinned buffer.  N > 1: one copy in POSIX shared memory (what FlashWeave's SharedArray gives its local
+    # workers, src/learning.jl:553-560), page-locked by every rank, so each rank uploads its 1/N slice over its own PCIe link.
     host_x = None
-    if rank == 0:
+    gen_s = 0.0
+    shm_path = None
+    split_h2d = world > 1 and p % world == 0
+    if split_h2d:
+        shm_path = "/dev/shm/fw_bench_table_%s.bin" % os.environ.get("MASTER_PORT", "0")
+        if rank == 0:
+            t0 = time.time()
+            mm = np.memmap(shm_path, mode="w+", shape=(p, n), dtype=np.float32)
+            mm[:] = synth.clique(p, n, B=a.B, seed=synth.BASE_SEED + 3)
+            mm.flush(); del mm
+            gen_s = time.time() - t0
+        dist.barrier()
+        mm = np.memmap(shm_path, mode="r+", shape=(p, n), dtype=np.float32)
+        host_x = torch.from_numpy(mm)
+        rc = torch.cuda.cudart().cudaHostRegister(host_x.data_ptr(), host_x.numel() * 4, 0)
+        if int(rc) != 0:
+            raise SystemExit("cudaHostRegister of the shared table failed: %s" % rc)
+    elif rank == 0:
         t0 = time.time()
         host_x = torch.empty((p, n), dtype=torch.float32, pin_memory=True)
         host_x.numpy()[:] = synth.clique(p, n, B=a.B, seed=synth.BASE_SEED + 3)
@@ -197,9 +216,14 @@ def main_ours(a, rank, world, local_rank):
     def pipeline():
         """e2e: host table -> neighbour lists of this rank's target shard, through the C ABI."""
         th = time.perf_counter()
-        if rank == 0:
-            d_x.copy_(host_x, non_blocking=True)                     # H2D from pinned host memory
-        par.broadcast_table(dist, d_x, src=0)                        # the one collective: table over NVLink
+        if split_h2d:
+            r0, r1 = rank * (p // world), (rank + 1) * (p // world)
+            d_x[r0:r1].copy_(host_x[r0:r1], non_blocking=True)       # H2D of this rank's slice from pinned (shared) host memory
+            dist.all_gather_into_tensor(d_x, d_x[r0:r1])             # the table over NVLink, in place
+        else:
+            if rank == 0:
+                d_x.copy_(host_x, non_blocking=True)                 # H2D from pinned host memory
+            par.broadcast_table(dist, d_x, src=0)                    # the one collective: table over NVLink
         torch.cuda.synchronize()
         h2d_ms.append((time.perf_counter() - th) * 1e3)
         eng.adopt_data_device(d_x.data_ptr(), n, p, "fz")
@@ -238,7 +262,7 @@ def main_ours(a, rank, world, local_rank):
             phase[k].append(lt[k])
     e2e_launches = (eng.launch_count() - launches0) / max(a.steps, 1)
     tests_rank = int(res.num_tests.sum())
-    h2d = (p * n * 4 if rank == 0 else 0) + len(shard) * 8
+    h2d = (p * n * 4 // world if split_h2d else (p * n * 4 if rank == 0 else 0)) + len(shard) * 8
     d2h = int(res.off[-1]) * 24 + len(shard) * 24 + (p + 1) * 8
 
     # ---- device-resident region (the contract's K timed steps) -------------------------------------------
@@ -271,6 +295,14 @@ def main_ours(a, rank, world, local_rank):
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
     else:
         mx, sm = stats, stats
+    if split_h2d:
+        torch.cuda.cudart().cudaHostUnregister(host_x.data_ptr())
+        dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(shm_path)
+            except OSError:
+                pass
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
