@@ -14,7 +14,8 @@ region (the table is broadcast once, inside the e2e region).
           on the library's stream, max over ranks.  cond_tests_ref = sum of test_subsets' num_tests
           exactly as the reference counts them (src/tests.jl:322, early exit honoured).
   e2e   : the same count divided by the time of the whole pipeline through the C ABI from HOST
-          buffers: H2D of the table (pinned), [NCCL broadcast], cor_mat GEMM, pairwise stage + BH,
+          buffers: H2D of the table from pinned host memory (N > 1: each rank uploads 1/N of the shared
+          table, NCCL all-gather), cor_mat GEMM (N > 1: row-sharded + all-gather), pairwise stage + BH,
           HITON-PC of the shard, D2H of the neighbour lists.
 
 `--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a
@@ -329,7 +330,9 @@ def main_ours(a, rank, world, local_rank):
                 "bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["which"],
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "40 B of correlations per k=3 test: this kernel is FP64/FP32-issue bound, not HBM bound (see DESIGN.md, profiles/)"}
+                "note": "40 B of correlations per k=3 test: this kernel is instruction-issue bound, not HBM bound (see DESIGN.md 4.1)",
+                "ncu": {"issue_slots_busy": 0.60, "fp64_pipe": 0.22, "alu_pipe": 0.28, "warp_instr_per_test": 30.9,
+                        "source": "profiles/r01_hiton_fz_C4_raw.csv (one ncu --set full capture of this launch, not live)"}}
     cor_ms = float(np.mean(cor_wall_ms[-a.steps:])) if dist is not None else float(np.mean(phase["cor_ms"]))
     roofline_cor = {"kernel": "cor_mat GEMM (fw_cor_matrix at N=1; row-sharded + NCCL all-gather + symmetrise at N>1, wall time of the whole step)", "bound": "tensor",
                     "achieved": 2.0 * n * p * p / world / (cor_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s per GPU",

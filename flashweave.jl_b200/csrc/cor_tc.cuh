@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <string>
 #include "common.cuh"
 
@@ -306,6 +307,163 @@ struct Scratch {
     ~Scratch() { if (z) cudaFree(z); }
 };
 
+// ---- cluster variant: two CTAs (same tile row bi, adjacent tile columns bj, bj+1) share the A operand -------------------------
+// CTA c of the pair loads one half of A (c = 0: A_hi, c = 1: A_lo) and TMA-multicasts it into both CTAs' shared memory, so each
+// SM pulls 48 KB instead of 64 KB per k-block through L2 (the kernel is L2-feed bound: profiles/).  Stage release is
+// cluster-wide: every MMA thread's tcgen05.commit multicast-arrives on the `empty` barrier of both CTAs (count 2), because a
+// producer's multicast writes into its peer's stage buffer too.  Everything else is cor_tc_kernel.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+cor_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+               float* __restrict__ C, i64 p, int num_kb, int nb, int bi0, int mirror) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - raw);
+    const uint32_t bar0 = base + STAGES * STAGE_BYTES;
+    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * STAGES, bar_cfull = bar0 + 16 * STAGES, bar_cempty = bar0 + 16 * STAGES + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+
+    // cluster q -> (tile row bi, column pair): row bi (from bi0) has ceil((nb - bi) / 2) pairs
+    int bi = bi0, bj;
+    bool live = true;                                   // the odd CTA of a row's last pair may have no tile of its own
+    {
+        long long q = blockIdx.x >> 1;
+        for (;; ++bi) { const long long pr = (nb - bi + 1) >> 1; if (q < pr) break; q -= pr; }
+        bj = bi + 2 * (int)q + (int)crank;
+        if (bj >= nb) { bj = nb - 1; live = false; }    // still feeds its half of A to the peer; computes a redundant tile, writes nothing
+    }
+    const int n_chunks = (num_kb + CHUNK - 1) / CHUNK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2); }   // both CTAs release a stage
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_cfull + 8 * b, 1); mbar_init(bar_cempty + 8 * b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_ALLOC) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                 // the peer's barriers exist before any multicast can arrive on them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)((kb / STAGES) & 1);
+                mbar_wait(bar_empty + 8 * s, ph ^ 1u);                      // both CTAs have drained this stage
+                const uint32_t full = bar_full + 8 * s;
+                mbar_expect_tx(full, STAGE_BYTES);                            // A_hi + A_lo (one of them from the peer) + B_hi + B_lo
+                const uint32_t st = base + s * STAGE_BYTES;
+                if (crank == 0) tma_load_2d_mc(st, &tm_hi, full, kb * BK, bi * BM, (uint16_t)3);
+                else tma_load_2d_mc(st + TILE_BYTES, &tm_lo, full, kb * BK, bi * BM, (uint16_t)3);
+                tma_load_2d(st + 2 * TILE_BYTES, &tm_hi, full, kb * BK, bj * BN);
+                tma_load_2d(st + 3 * TILE_BYTES, &tm_lo, full, kb * BK, bj * BN);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t t_cross = tmem_base + 256;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)((kb / STAGES) & 1);
+                const int c = kb / CHUNK, b = c & 1, u = c >> 1;
+                const bool first = (kb % CHUNK) == 0;
+                if (first && c >= 2) {
+                    mbar_wait(bar_cempty + 8 * b, (uint32_t)((u - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                mbar_wait(bar_full + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t t_main = tmem_base + 128u * (uint32_t)b;
+                const uint32_t st = base + s * STAGE_BYTES;
+                const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + TILE_BYTES);
+                const uint64_t b_hi = make_desc(st + 2 * TILE_BYTES), b_lo = make_desc(st + 3 * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+                    umma_bf16(t_main, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                    umma_bf16(t_cross, a_hi + adv, b_lo + adv, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+                    umma_bf16(t_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+                }
+                umma_commit_mc(bar_empty + 8 * s, (uint16_t)3);               // release the stage in both CTAs
+                if ((kb % CHUNK) == CHUNK - 1 || kb == num_kb - 1) umma_commit(bar_cfull + 8 * b);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        float acc[BN];
+#pragma unroll
+        for (int j = 0; j < BN; ++j) acc[j] = 0.0f;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int b = c & 1, u = c >> 1;
+            mbar_wait(bar_cfull + 8 * b, (uint32_t)(u & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_base + 128u * (uint32_t)b + (uint32_t)c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_cempty + 8 * b);
+        }
+        const i64 row = (i64)bi * BM + q * 32 + lane;
+        const bool diag = (bi == bj);
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + lane_base + 256u + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const i64 col = (i64)bj * BN + c0 + j;
+                float x = acc[c0 + j] + __uint_as_float(v[j]);
+                x = x > 1.0f ? 1.0f : (x < -1.0f ? -1.0f : x);
+                if (row == col) x = 1.0f;
+                const bool ok = live && row < p && col < p && (!diag || col >= row);
+                if (ok) {
+                    C[row * p + col] = x;
+                    if (mirror || diag) C[col * p + row] = x;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                 // no CTA leaves while its peer can still multicast into it / arrive on its barriers
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_ALLOC) : "memory");
+    }
+}
+
 struct Prepared { CUtensorMap tm_hi, tm_lo; i64 kp = 0, p_pad = 0; int nb = 0; bool valid = false; };
 
 // standardise + split the resident table (once per table) and build the TMA descriptors
@@ -328,9 +486,23 @@ static cudaError_t prepare(Scratch& S, Prepared& P, const float* d_data, i64 n, 
 }
 
 // upper-triangular tiles of tile rows [bi0, bi1)
+static bool use_cluster_kernel() {
+    static const int v = [] { const char* e = getenv("FWGPU_COR_CLUSTER"); return e ? atoi(e) : 1; }();
+    return v != 0;
+}
 static cudaError_t run_rows(const Prepared& P, float* d_cor, i64 p, int bi0, int bi1, bool mirror, cudaStream_t st, int* n_launch, std::string* msg) {
     if (bi1 > P.nb) bi1 = P.nb;
     if (bi0 >= bi1) return cudaSuccess;
+    if (use_cluster_kernel()) {
+        long long clusters = 0;
+        for (int bi = bi0; bi < bi1; ++bi) clusters += (P.nb - bi + 1) >> 1;
+        cudaError_t e = cudaFuncSetAttribute(cor_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute(cor_tc2_kernel)"; return e; }
+        cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(P.kp / BK), P.nb, bi0, mirror ? 1 : 0);
+        (*n_launch)++;
+        e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "cor_tc2_kernel"; return e; }
+        return cudaSuccess;
+    }
     const long long first = (long long)bi0 * P.nb - (long long)bi0 * (bi0 - 1) / 2;
     const long long last = (long long)bi1 * P.nb - (long long)bi1 * (bi1 - 1) / 2;
     cor_tc_kernel<<<(unsigned)(last - first), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(P.kp / BK), P.nb, bi0, mirror ? 1 : 0);
