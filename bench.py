@@ -14,9 +14,10 @@ region (the table is broadcast once, inside the e2e region).
           on the library's stream, max over ranks.  cond_tests_ref = sum of test_subsets' num_tests
           exactly as the reference counts them (src/tests.jl:322, early exit honoured).
   e2e   : the same count divided by the time of the whole pipeline through the C ABI from HOST
-          buffers: H2D of the table from pinned host memory (N > 1: each rank uploads 1/N of the shared
-          table, NCCL all-gather), cor_mat GEMM (N > 1: row-sharded + all-gather), pairwise stage + BH,
-          HITON-PC of the shard, D2H of the neighbour lists.
+          buffers: H2D of the table from pinned host memory (N = 1: column chunks hidden behind the
+          cor_mat GEMM, fw_upload_cor_f32; N > 1: each rank uploads 1/N of the shared table, NCCL
+          all-gather, row-sharded GEMM + all-gather), pairwise stage + BH, HITON-PC of the shard,
+          D2H of the neighbour lists.
 
 `--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a
 bounded sample of the same workload (the reference itself is Julia and cannot run here).
@@ -217,7 +218,13 @@ def main_ours(a, rank, world, local_rank):
     def pipeline():
         """e2e: host table -> neighbour lists of this rank's target shard, through the C ABI."""
         th = time.perf_counter()
-        if split_h2d:
+        if dist is None:
+            # one GPU: the upload is chunked and hidden behind the cor_mat GEMM inside one C-ABI call
+            eng.upload_and_cor(host_x.data_ptr(), n=n, p=p)
+            eng.synchronize()
+            h2d_ms.append(0.0)
+            cor_wall_ms.append((time.perf_counter() - th) * 1e3)
+        elif split_h2d:
             r0, r1 = rank * (p // world), (rank + 1) * (p // world)
             d_x[r0:r1].copy_(host_x[r0:r1], non_blocking=True)       # H2D of this rank's slice from pinned (shared) host memory
             dist.all_gather_into_tensor(d_x, d_x[r0:r1])             # the table over NVLink, in place
@@ -225,17 +232,15 @@ def main_ours(a, rank, world, local_rank):
             if rank == 0:
                 d_x.copy_(host_x, non_blocking=True)                 # H2D from pinned host memory
             par.broadcast_table(dist, d_x, src=0)                    # the one collective: table over NVLink
-        torch.cuda.synchronize()
-        h2d_ms.append((time.perf_counter() - th) * 1e3)
-        eng.adopt_data_device(d_x.data_ptr(), n, p, "fz")
-        tc = time.perf_counter()
-        if dist is None:
-            eng.cor(want_host=False)                                 # cor_mat = Float32.(cor(data))
-        else:
+        if dist is not None:
+            torch.cuda.synchronize()
+            h2d_ms.append((time.perf_counter() - th) * 1e3)
+            eng.adopt_data_device(d_x.data_ptr(), n, p, "fz")
+            tc = time.perf_counter()
             eng.adopt_cor_device_rows(d_cor.data_ptr(), p, d_cor.shape[0])
-            par.sharded_cor(dist, eng, d_cor)
-        eng.synchronize()
-        cor_wall_ms.append((time.perf_counter() - tc) * 1e3)
+            par.sharded_cor(dist, eng, d_cor)                        # cor_mat = Float32.(cor(data)), 1/N of the tiles per rank
+            eng.synchronize()
+            cor_wall_ms.append((time.perf_counter() - tc) * 1e3)
         eng.pw_univar_neighbors(alpha=a.alpha, n_obs_min=20, want_host=False)
         off = np.zeros(p + 1, np.int64)
         eng._ck(eng.L.fw_pairwise_copy(eng.h, off.ctypes.data_as(fw.C.c_void_p), None, None, None))
@@ -262,6 +267,13 @@ def main_ours(a, rank, world, local_rank):
         for k in phase:
             phase[k].append(lt[k])
     e2e_launches = (eng.launch_count() - launches0) / max(a.steps, 1)
+    # the cor_mat GEMM alone (table already resident), for its tensor-core roofline
+    gemm_ms = []
+    if dist is None:
+        for _ in range(3):
+            eng.cor(want_host=False); eng.synchronize()
+            gemm_ms.append(eng.last_timing()["cor_ms"])
+        eng.pw_univar_neighbors(alpha=a.alpha, n_obs_min=20, want_host=False)
     tests_rank = int(res.num_tests.sum())
     h2d = (p * n * 4 // world if split_h2d else (p * n * 4 if rank == 0 else 0)) + len(shard) * 8
     d2h = int(res.off[-1]) * 24 + len(shard) * 24 + (p + 1) * 8
@@ -333,8 +345,8 @@ def main_ours(a, rank, world, local_rank):
                 "note": "40 B of correlations per k=3 test: this kernel is instruction-issue bound, not HBM bound (see DESIGN.md 4.1)",
                 "ncu": {"issue_slots_busy": 0.60, "fp64_pipe": 0.22, "alu_pipe": 0.28, "warp_instr_per_test": 30.9,
                         "source": "profiles/r01_hiton_fz_C4_raw.csv (one ncu --set full capture of this launch, not live)"}}
-    cor_ms = float(np.mean(cor_wall_ms[-a.steps:])) if dist is not None else float(np.mean(phase["cor_ms"]))
-    roofline_cor = {"kernel": "cor_mat GEMM (fw_cor_matrix at N=1; row-sharded + NCCL all-gather + symmetrise at N>1, wall time of the whole step)", "bound": "tensor",
+    cor_ms = float(np.mean(cor_wall_ms[-a.steps:])) if dist is not None else float(min(gemm_ms))
+    roofline_cor = {"kernel": "cor_mat GEMM (N=1: fw_cor_matrix on the resident table, timed alone; N>1: row-sharded + NCCL all-gather + symmetrise, wall time of the whole step)", "bound": "tensor",
                     "achieved": 2.0 * n * p * p / world / (cor_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s per GPU",
                     "frac": 2.0 * n * p * p / world / (cor_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": traffic_cor, "peak_source": pk["which"], "kernel_ms": cor_ms,
                     "note": "useful flop = 2*n*p^2 (the 3-term bf16 split and the symmetric half do not change the numerator); includes the standardise+split kernel"}

@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "fw_create", "fw_destroy", "fw_last_error", "fw_set_index_base", "fw_stream", "fw_synchronize", "fw_launch_count", "fw_last_timing",
     "fw_hiton_exec_by_k",
     "fw_set_data_f32", "fw_set_data_i32", "fw_adopt_data_f32_device", "fw_set_n_obs", "fw_levels", "fw_cor_matrix",
-    "fw_set_cor_f32", "fw_adopt_cor_device", "fw_cor_device_ptr", "fw_adopt_cor_device_rows", "fw_cor_prepare", "fw_cor_rows", "fw_cor_symmetrize", "fw_test_batch", "fw_test_subsets", "fw_test_subsets_batch",
+    "fw_set_cor_f32", "fw_adopt_cor_device", "fw_cor_device_ptr", "fw_adopt_cor_device_rows", "fw_cor_prepare", "fw_cor_rows", "fw_cor_symmetrize", "fw_upload_cor_f32", "fw_test_batch", "fw_test_subsets", "fw_test_subsets_batch",
     "fw_pairwise", "fw_pairwise_copy", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_capacity",
     "fw_build_info",
 ]
@@ -94,6 +94,7 @@ def load_library():
         "fw_cor_prepare": (i32, [vp, vp]),
         "fw_cor_rows": (i32, [vp, i32, i32]),
         "fw_cor_symmetrize": (i32, [vp]),
+        "fw_upload_cor_f32": (i32, [vp, vp, i64, i64, i64, vp]),
         "fw_test_batch": (i32, [vp, i32, i64, vp, vp, vp, vp, i64, i64, vp]),
         "fw_test_subsets": (i32, [vp, i32, i64, i64, vp, i64, i32, dbl, i64, i64, i64, vp, vp, vp, vp, vp]),
         "fw_test_subsets_batch": (i32, [vp, i32, i64, vp, vp, vp, vp, i32, dbl, i64, i64, i64, vp, vp, vp, vp, vp]),
@@ -253,6 +254,22 @@ class Engine:
         mv = np.zeros(self.p, np.int32)
         self._ck(self.L.fw_levels(self.h, _p(lv), _p(mv)))
         return lv, mv
+
+    def upload_and_cor(self, host_ptr_or_array, n=None, p=None, want_host=False):
+        """set_data + cor in one call with the upload hidden behind the GEMM (fz).  Accepts a C-contiguous [p, n] float32 array
+        or a raw host pointer (pinned memory gives full PCIe speed) together with n and p."""
+        if isinstance(host_ptr_or_array, np.ndarray):
+            a = host_ptr_or_array
+            assert a.dtype == np.float32 and a.flags.c_contiguous
+            p, n = a.shape
+            ptr = a.ctypes.data
+            self._keep = [a]
+        else:
+            ptr = int(host_ptr_or_array)
+        out = np.empty((p, p), np.float32) if want_host else None
+        self._ck(self.L.fw_upload_cor_f32(self.h, C.c_void_p(ptr), n, p, n, _p(out)))
+        self.kind, self.n, self.p = "fz", n, p
+        return out
 
     def set_n_obs(self, n):
         self._ck(self.L.fw_set_n_obs(self.h, n))

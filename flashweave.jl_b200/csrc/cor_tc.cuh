@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <algorithm>
 #include <cstdlib>
 #include <string>
 #include "common.cuh"
@@ -61,8 +62,8 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 // one CTA per column: standardise and split into bf16 hi/lo, K-major rows of length kp (zero padded)
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) standardize_split_kernel(const float* __restrict__ data, i64 n, i64 ld, i64 p, i64 kp,
-                                                                    __nv_bfloat16* __restrict__ zhi, __nv_bfloat16* __restrict__ zlo) {
-    const i64 col = blockIdx.x;
+                                                                    __nv_bfloat16* __restrict__ zhi, __nv_bfloat16* __restrict__ zlo, i64 col0) {
+    const i64 col = col0 + blockIdx.x;
     __nv_bfloat16* hi = zhi + col * kp;
     __nv_bfloat16* lo = zlo + col * kp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -326,7 +327,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 cor_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-               float* __restrict__ C, i64 p, int num_kb, int nb, int bi0, int mirror) {
+               float* __restrict__ C, i64 p, int num_kb, int nb, int bi0, int mirror, int bjlo, int bjhi) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -338,14 +339,16 @@ cor_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     uint32_t crank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
 
-    // cluster q -> (tile row bi, column pair): row bi (from bi0) has ceil((nb - bi) / 2) pairs
+    // cluster q -> (tile row bi, column pair): row bi (from bi0) covers tile columns [max(bi, bjlo), bjhi) in pairs
+    // (row-range mode: bjlo = 0, bjhi = nb; column-band mode of the upload-overlapped path: bi0 = 0, rows up to bjhi)
     int bi = bi0, bj;
     bool live = true;                                   // the odd CTA of a row's last pair may have no tile of its own
     {
         long long q = blockIdx.x >> 1;
-        for (;; ++bi) { const long long pr = (nb - bi + 1) >> 1; if (q < pr) break; q -= pr; }
-        bj = bi + 2 * (int)q + (int)crank;
-        if (bj >= nb) { bj = nb - 1; live = false; }    // still feeds its half of A to the peer; computes a redundant tile, writes nothing
+        for (;; ++bi) { const int lo = bi > bjlo ? bi : bjlo; const long long pr = (bjhi - lo + 1) >> 1; if (q < pr) break; q -= pr; }
+        const int lo = bi > bjlo ? bi : bjlo;
+        bj = lo + 2 * (int)q + (int)crank;
+        if (bj >= bjhi) { bj = bjhi - 1; live = false; }    // still feeds its half of A to the peer; computes a redundant tile, writes nothing
     }
     const int n_chunks = (num_kb + CHUNK - 1) / CHUNK;
 
@@ -474,7 +477,7 @@ static cudaError_t prepare(Scratch& S, Prepared& P, const float* d_data, i64 n, 
     if (e != cudaSuccess) { *msg = "scratch allocation"; return e; }
     __nv_bfloat16* zhi = S.z;
     __nv_bfloat16* zlo = S.z + (size_t)p_pad * kp;
-    standardize_split_kernel<256><<<(unsigned)p_pad, 256, 0, st>>>(d_data, n, ld, p, kp, zhi, zlo);
+    standardize_split_kernel<256><<<(unsigned)p_pad, 256, 0, st>>>(d_data, n, ld, p, kp, zhi, zlo, 0);
     (*n_launch)++;
     e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "standardize_split_kernel"; return e; }
     e = encode_map(&P.tm_hi, zhi, kp, p_pad, msg); if (e != cudaSuccess) return e;
@@ -498,7 +501,7 @@ static cudaError_t run_rows(const Prepared& P, float* d_cor, i64 p, int bi0, int
         for (int bi = bi0; bi < bi1; ++bi) clusters += (P.nb - bi + 1) >> 1;
         cudaError_t e = cudaFuncSetAttribute(cor_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute(cor_tc2_kernel)"; return e; }
-        cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(P.kp / BK), P.nb, bi0, mirror ? 1 : 0);
+        cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(P.kp / BK), P.nb, bi0, mirror ? 1 : 0, 0, P.nb);
         (*n_launch)++;
         e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "cor_tc2_kernel"; return e; }
         return cudaSuccess;
@@ -516,6 +519,53 @@ static cudaError_t run(Scratch& S, const float* d_data, i64 n, i64 p, i64 ld, fl
     cudaError_t e = prepare(S, P, d_data, n, p, ld, st, n_launch, msg);
     if (e != cudaSuccess) return e;
     return run_rows(P, d_cor, p, 0, P.nb, true, st, n_launch, msg);
+}
+
+// Upload-overlapped cor_mat (one GPU): the host table is copied in column chunks on `copy_st`; as soon as chunk c has landed the
+// compute stream standardises its columns and runs the tiles (bi <= bj, bj in the chunk's tile columns) — a growing column band
+// of the upper triangle — so the PCIe transfer hides behind the GEMM.  Same tiles, same arithmetic as run().
+static cudaError_t run_overlapped(Scratch& S, const float* host, float* d_data, i64 n, i64 p, i64 host_ld, float* d_cor,
+                                  cudaStream_t st, cudaStream_t copy_st, cudaEvent_t* evs, int n_evs, int* n_launch, std::string* msg) {
+    const i64 kp = (n + BK - 1) / BK * BK;
+    const i64 p_pad = (p + BM - 1) / BM * BM;
+    const int nb = (int)(p_pad / BM);
+    cudaError_t e = S.reserve((size_t)2 * p_pad * kp);
+    if (e != cudaSuccess) { *msg = "scratch allocation"; return e; }
+    __nv_bfloat16* zhi = S.z;
+    __nv_bfloat16* zlo = S.z + (size_t)p_pad * kp;
+    Prepared P;
+    e = encode_map(&P.tm_hi, zhi, kp, p_pad, msg); if (e != cudaSuccess) return e;
+    e = encode_map(&P.tm_lo, zlo, kp, p_pad, msg); if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(cor_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute(cor_tc2_kernel)"; return e; }
+    int chunks = n_evs < 12 ? n_evs : 12;
+    if (chunks > nb) chunks = nb;
+    if (chunks < 1) chunks = 1;
+    // the copy stream must not overtake work that still reads d_data / Z from a previous call
+    e = cudaEventRecord(evs[0], st); if (e != cudaSuccess) { *msg = "event"; return e; }
+    e = cudaStreamWaitEvent(copy_st, evs[0], 0); if (e != cudaSuccess) { *msg = "wait"; return e; }
+    int t0 = 0;
+    for (int c = 0; c < chunks; ++c) {
+        const int t1 = (int)((long long)nb * (c + 1) / chunks);          // tile columns [t0, t1)
+        const i64 c0 = (i64)t0 * BM, c1 = std::min<i64>((i64)t1 * BM, p);
+        if (c1 > c0) {
+            e = cudaMemcpy2DAsync(d_data + c0 * n, n * sizeof(float), host + c0 * host_ld, host_ld * sizeof(float), n * sizeof(float), (size_t)(c1 - c0),
+                                  cudaMemcpyHostToDevice, copy_st);
+            if (e != cudaSuccess) { *msg = "cudaMemcpy2DAsync"; return e; }
+        }
+        e = cudaEventRecord(evs[c], copy_st); if (e != cudaSuccess) { *msg = "event"; return e; }
+        e = cudaStreamWaitEvent(st, evs[c], 0); if (e != cudaSuccess) { *msg = "wait"; return e; }
+        const i64 s1 = (c == chunks - 1) ? p_pad : (i64)t1 * BM;          // the last chunk also zero-fills the padding rows
+        standardize_split_kernel<256><<<(unsigned)(s1 - c0), 256, 0, st>>>(d_data, n, n, p, kp, zhi, zlo, c0);
+        (*n_launch)++;
+        long long clusters = 0;
+        for (int bi = 0; bi < t1; ++bi) { const int lo = bi > t0 ? bi : t0; clusters += (t1 - lo + 1) >> 1; }
+        cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(kp / BK), nb, 0, 1, t0, t1);
+        (*n_launch)++;
+        e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "cor_tc2_kernel (band)"; return e; }
+        t0 = t1;
+    }
+    return cudaSuccess;
 }
 
 // lower triangle <- upper triangle (after the row blocks of all ranks are in place): 32x32 tiles through shared memory

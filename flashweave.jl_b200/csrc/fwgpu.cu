@@ -48,6 +48,8 @@ struct fw_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // H2D chunks of fw_upload_cor_f32
+    cudaEvent_t chunk_ev[12] = {nullptr};
     std::string err;
     int index_base = 0;
     i64 launches = 0;
@@ -201,6 +203,8 @@ int32_t fw_create(int32_t device, fw_ctx** out) {
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     if (ctx->d_counter.reserve(16) != cudaSuccess || ctx->d_exec.reserve(16) != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_NOMEM, "scratch allocation failed"); }
     for (int i = 0; i < 8; ++i) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_CUDA, "cudaEventCreate failed"); }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_CUDA, "cudaStreamCreate failed"); }
+    for (int i = 0; i < 12; ++i) if (cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_CUDA, "cudaEventCreate failed"); }
     *out = ctx;
     return FW_OK;
 }
@@ -210,6 +214,8 @@ int32_t fw_destroy(fw_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 12; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     delete ctx;
     return FW_OK;
 }
@@ -330,6 +336,27 @@ int32_t fw_adopt_cor_device_rows(fw_ctx* ctx, const float* dev_cor, int64_t p, i
     return FW_OK;
 }
 void* fw_cor_device_ptr(fw_ctx* ctx) { return ctx ? (void*)ctx->d_cor.ptr : nullptr; }
+
+// fw_set_data_f32 + fw_cor_matrix in one call, with the PCIe upload hidden behind the GEMM (column chunks on a copy stream)
+int32_t fw_upload_cor_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, int64_t ld, float* host_out) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(host && n > 0 && p > 0 && ld >= n, FW_ERR_INVALID, "fw_upload_cor_f32: bad arguments (n=%lld p=%lld ld=%lld)", (long long)n, (long long)p, (long long)ld);
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_data_f32.reserve((size_t)n * p));
+    if (!(ctx->d_cor.ptr && ctx->d_cor.owned && ctx->d_cor.cap >= (size_t)p * p)) CK(ctx->d_cor.reserve((size_t)p * p));
+    std::string msg; int nl = 0;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    cudaError_t e = cortc::run_overlapped(ctx->tc, host, ctx->d_data_f32.ptr, n, p, ld, ctx->d_cor.ptr, ctx->stream, ctx->copy_stream, ctx->chunk_ev, 12, &nl, &msg);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_upload_cor_f32: %s: %s", msg.c_str(), cudaGetErrorString(e));
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_valid[0] = true;
+    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n; ctx->nz_ready = false; ctx->cor_p = p; ctx->tcp.valid = false;
+    if (host_out) {
+        CK(cudaMemcpyAsync(host_out, ctx->d_cor.ptr, sizeof(float) * (size_t)p * p, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return FW_OK;
+}
 
 // ---- row-sharded cor_mat (multi-GPU) -------------------------------------------------------------
 // fw_cor_prepare: standardise + split the resident table once.  fw_cor_rows: the upper-triangular 128x128 tiles of tile rows

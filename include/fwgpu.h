@@ -85,6 +85,9 @@ int32_t fw_levels(fw_ctx* ctx, int32_t* levels, int32_t* max_vals);
 /* cor_mat = convert(Matrix{Float32}, cor(data)), src/learning.jl:42-44.  Computed on the
  * tensor cores from the resident table and kept resident; host_out may be NULL. */
 int32_t fw_cor_matrix(fw_ctx* ctx, float* host_out);
+/* fw_set_data_f32 followed by fw_cor_matrix as one call: the table is uploaded in column chunks on a copy stream while the
+ * tiles whose operands have arrived are already being computed (same result, the PCIe transfer hides behind the GEMM). */
+int32_t fw_upload_cor_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, int64_t ld, float* host_out);
 /* install a caller-provided cor_mat (the `cor_mat` field of FzTest/FzTestCond, src/types.jl:126-136) */
 int32_t fw_set_cor_f32(fw_ctx* ctx, const float* host_cor, int64_t p);
 int32_t fw_adopt_cor_device(fw_ctx* ctx, const float* dev_cor, int64_t p);

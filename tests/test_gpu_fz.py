@@ -222,6 +222,11 @@ def test_cor_matrix_tolerance(fw, synth):
         want = np.corrcoef(x.astype(np.float64))
         assert np.abs(got - want).max() <= 1e-5          # north_star tolerance on correlations
         assert (np.diag(got) == 1.0).all() and (got == got.T).all() and np.abs(got).max() <= 1.0
+        # upload hidden behind the GEMM (column bands): same matrix bit for bit
+        eng2 = fw.Engine(0)
+        got2 = eng2.upload_and_cor(x, want_host=True)
+        assert (got2 == got).all()
+        assert eng2.test_batch([0], [1], [(2, 3)])[0] == eng.test_batch([0], [1], [(2, 3)])[0]
     # constant column -> NaN row/column, unit diagonal (Statistics.cov2cor!)
     x = synth.clique(40, 200, B=8, seed=4)
     x[5] = 2.0
