@@ -65,3 +65,38 @@ def with_zeros(x_pn, zero_frac=0.4, seed=0):
     out = x_pn.copy()
     out[rng.random(x_pn.shape) < zero_frac] = 0.0
     return out
+
+
+def hetero(p, n, B=24, H=8, n_meta=10, dropout=0.1, seed=BASE_SEED + 4):
+    """C5: heterogeneous fz_nz table + meta variables.  H habitats, sample -> habitat uniform; every
+    block of B OTUs is present in a habitat w.p. 0.5 (at least one); absent => structural 0.0, plus `dropout` random
+    zeros; non-zero entries keep the clique-B latent value.  The last n_meta rows are meta variables that are never
+    zero: H habitat indicators coded {1, 2} (the reference's "+1 shift", preprocessing.jl:537-545) and the rest
+    continuous N(0,1) + 0.5 * (block-0 latent factor).  Returns ([p, n] float32, meta_mask[p] bool)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n_otu = p - n_meta
+    out = np.empty((p, n), np.float32)
+    hab = rng.integers(0, H, size=n)
+    nb = (n_otu + B - 1) // B
+    f0 = None
+    for b in range(nb):
+        lo, hi = b * B, min((b + 1) * B, n_otu)
+        f = rng.standard_normal(n, dtype=np.float32)
+        if b == 0:
+            f0 = f
+        e = rng.standard_normal((hi - lo, n), dtype=np.float32)
+        blk = 0.8 * f[None, :] + 0.6 * e
+        blk[blk == 0.0] = 1e-3
+        pres = rng.random(H) < 0.5
+        if not pres.any():
+            pres[rng.integers(0, H)] = True
+        blk[:, ~pres[hab]] = 0.0
+        blk[rng.random(blk.shape) < dropout] = 0.0
+        out[lo:hi] = blk
+    for h in range(min(H, n_meta)):
+        out[n_otu + h] = 1.0 + (hab == h)
+    for j in range(min(H, n_meta), n_meta):
+        out[n_otu + j] = rng.standard_normal(n, dtype=np.float32) + 0.5 * f0
+    mask = np.zeros(p, bool)
+    mask[n_otu:] = True
+    return out, mask

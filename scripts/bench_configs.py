@@ -45,3 +45,9 @@ if "C3c" in which:
 if "C5s" in which:
     lat = synth.clique(4800, 10000, B=24, seed=synth.BASE_SEED + 4)
     run("C5-shaped (reduced p) 4800x10000 fz_nz max_k=3", synth.with_zeros(lat, zero_frac=0.4, seed=7), "fz_nz", 3, reps=2)
+if "C5m" in which:
+    x, _ = synth.hetero(9610, 10000, B=24, seed=synth.BASE_SEED + 4)
+    run("C5 (reduced p) hetero+meta 9610x10000 fz_nz max_k=3", x, "fz_nz", 3, reps=2)
+if "C5" in which:
+    x, _ = synth.hetero(50010, 10000, B=24, seed=synth.BASE_SEED + 4)
+    run("C5 hetero+meta 50010x10000 fz_nz max_k=3", x, "fz_nz", 3, reps=1)
