@@ -57,7 +57,8 @@ class TestResult(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libfwgpu.so")
+    # FW_LIB_PATH: kernel-tuning experiments load an alternative build of the same library (scripts/); never a fallback
+    return os.environ.get("FW_LIB_PATH") or os.path.join(_HERE, "libfwgpu.so")
 
 
 def load_library():

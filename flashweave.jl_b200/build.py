@@ -33,7 +33,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, os.path.join(CSRC, "fwgpu.cu")]
+    extra = os.environ.get("FW_NVCC_EXTRA", "").split()          # experiments only (e.g. -DFW_HITON_MINB=6)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", os.environ.get("FW_SO_OUT", SO), os.path.join(CSRC, "fwgpu.cu")]
     env = dict(os.environ)
     # the image exports CXX/CC wrappers that nvcc cannot drive; use the system host compiler
     if os.path.exists("/usr/bin/g++"):

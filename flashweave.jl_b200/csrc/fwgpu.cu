@@ -109,6 +109,31 @@ static FzConsts make_fz_consts(i64 n_rows, i64 n_obs_min) {
     return fc;
 }
 
+// Decision band of the p-value-free scan (fz.cuh, FzConsts): the |stat| at which fz_pval crosses alpha (bisection on the same
+// formula, statfuns.jl:3-17), widened by 1e-9 relative on both sides - far more than the ulp-level differences between this
+// host evaluation and the device's log/erfc - and the |stat| beyond which the p-value drops below 1e-290.
+static double host_fz_pval(double s, const FzConsts& fc) {
+    double fz = fc.sf_pos ? fc.half_sqrt_sf * std::log((1.0 + s) / (1.0 - s)) : 0.0;
+    return std::erfc(std::fabs(fz) * 0.70710678118654752440) / 2.0 * 2.0;
+}
+static double host_fz_cross(const FzConsts& fc, double level) {       // smallest s in [0, 1] with pval(s) < level (1.0 if none)
+    if (!(host_fz_pval(1.0, fc) < level)) return 2.0;
+    double lo = 0.0, hi = 1.0;                                         // pval(lo) >= level > pval(hi)
+    for (int it = 0; it < 200; ++it) { double mid = 0.5 * (lo + hi); if (host_fz_pval(mid, fc) < level) hi = mid; else lo = mid; }
+    return hi;
+}
+static void fill_fz_band(FzConsts& fc, double alpha) {
+    fc.s_lo = -1.0; fc.s_hi = 1e300; fc.s_under = 0.0;                // exact p-value everywhere
+    if (!(alpha > 1e-280 && alpha < 1.0)) return;
+    if (!(host_fz_pval(0.0, fc) >= alpha)) return;
+    const double sa = host_fz_cross(fc, alpha);                        // 2.0: never significant
+    fc.s_lo = sa >= 2.0 ? 1e300 : sa * (1.0 - 1e-9);
+    fc.s_hi = sa >= 2.0 ? 1e300 : sa * (1.0 + 1e-9);
+    const double su = host_fz_cross(fc, 1e-290);
+    fc.s_under = su >= 2.0 ? 1e300 : su * (1.0 - 1e-9);
+    if (fc.s_under < fc.s_hi) fc.s_under = fc.s_hi;
+}
+
 static MiTable make_mi_table(const fw_ctx* c, int kind) {
     MiTable t;
     t.planes = c->d_planes.ptr; t.levels = c->d_levels.ptr; t.max_vals = c->d_maxvals.ptr; t.nnz = c->d_nnz.ptr;
@@ -146,7 +171,7 @@ static size_t hiton_smem_bytes(int cap, bool r_in_smem, int nz_words = -1, bool 
     o = (o + 15) & ~(size_t)15;
     if (nz_words >= 0) o += sizeof(i64) * cap + 2 * sizeof(double) * cap + sizeof(unsigned int) * nz_words;
     o = (o + 15) & ~(size_t)15;
-    if (cache) o += (sizeof(double) + 3 * sizeof(float)) * (size_t)cap * cap + sizeof(float) * cap;
+    if (cache) o = (size_t)fz_tab_layout((int)o).end;
     return o + 16;
 }
 static size_t subsets_smem_bytes(int cap, bool r_in_smem, int nz_words = -1) {
@@ -853,6 +878,7 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
     a.uni_off = ctx->d_uni_off.ptr; a.uni_nbr = ctx->d_uni_nbr.ptr; a.uni_stat = ctx->d_uni_stat.ptr; a.uni_p = ctx->d_uni_p.ptr;
     a.targets = dt.ptr; a.out_off = doff.ptr; a.counter = ctx->d_counter.ptr;
     a.max_k = max_k; a.alpha = alpha; a.max_tests = max_tests; a.fc = make_fz_consts(ctx->n_obs < 0 ? 0 : ctx->n_obs, n_obs_min);
+    fill_fz_band(a.fc, alpha);
     a.cand_order = dorder.ptr;
     a.pc_nbr = dpcn.ptr; a.pc_stat = dpcs.ptr; a.pc_p = dpcp.ptr; a.pc_count = dpcc.ptr;
     a.tpc_nbr = dtpcn.ptr; a.tpc_stat = dtpcs.ptr; a.tpc_p = dtpcp.ptr; a.tpc_count = dtpcc.ptr;

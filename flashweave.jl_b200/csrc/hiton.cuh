@@ -46,83 +46,288 @@ struct FzSlotTest {
     }
 };
 
-// ---- per-candidate tables (capacity class 32): every conditioning subset of one candidate shares its level-1 terms with all
-// subsets that start with the same Z1, and its (X,Y|Z1,Z2) level-2 term with all subsets that start with the same (Z1,Z2).
-// Caching them in shared memory leaves 1 level-1 + 2 level-2 + 1 level-3 step per k = 3 test (was 6 + 3 + 1) with bit-identical
-// arithmetic (same operations, same order, just not repeated).  A Float64 literal (special) anywhere in the tables disables the
-// cache for that candidate, so the generic typed path keeps handling the degenerate cases.
-struct FzTables {
-    float* SQ;      // SQ[z*ld + s] = sqrt(1f0 - r(s,z)^2)
-    float* BX;      // BX[z*ld + s] = pcor(X, s | z)   (level 1, Float32)
-    float* BY;      // BY[z*ld + s] = pcor(Y, s | z)
-    float* A1;      // A1[z]        = pcor(X, Y | z)
-    double* A2;     // A2[z1*ld + z2] = pcor(X, Y | z1, z2) for z1 before z2 in the accepted list (level 2, Float64)
-    int ld;
-};
+// ---- per-candidate tables (capacity class 32) ------------------------------------------------------------------------------
+// Every conditioning subset (Z1, Z2, Z3) of one candidate shares its level-1 terms with all subsets that start with the same
+// Z1, and its (X,Y|Z1,Z2) level-2 term with all subsets that start with the same (Z1, Z2).  They are built once per candidate
+// in shared memory, which leaves 1 level-1 + 2 level-2 + 1 level-3 step per k = 3 test (the recursion has 6 + 3 + 1) with
+// bit-identical arithmetic (same operations in the same order, just not repeated).  A Float64 literal (special) anywhere in
+// the tables disables them for that candidate, so the generic typed path keeps handling the degenerate cases.
+//
+// The tables are indexed by POSITION in the accepted list (Z1 < Z2 < Z3 by position, the reference's enumeration), only the
+// upper triangles are needed, and two float triangles share one 32 x 33 square (row stride 33: a warp whose lanes differ in
+// the first position reads stride-33 words, lanes that differ in the second read consecutive words - both conflict-free):
+//   S1: upper RP[a][b] = r(Za, Zb)                  lower SQ[a][b] = sqrt(1f0 - r(Za,Zb)^2)       (stored at [b][a])
+//   S2: upper BX[a][b] = pcor(X, Zb | Za) (Float32) lower BY[a][b] = pcor(Y, Zb | Za)
+//   S3: upper SBX[a][b] = sqrt(1f0 - BX^2)          lower SBY[a][b]
+//   A2[a][b] = pcor(X, Y | Za, Zb) (Float64), A1[a] = pcor(X, Y | Za) (Float32)
+// CLX: idx -> (a, b, c) of the idx-th triple in COLEXICOGRAPHIC order (idx = C(c,3) + C(b,2) + a), 5 bits each.  That order
+// does not depend on m, so one table serves every candidate of every target; consecutive lanes get consecutive a and the
+// same (b, c), which is what makes the reads above broadcast or conflict-free.
+constexpr int FZ_TLD = 33;
+constexpr int FZ_CACHE_CAP = 32;                       // slots; at most 30 accepted members
+constexpr int FZ_CLX_N = 30 * 29 * 28 / 6;             // 4060 triples
+constexpr int FZ_PLX_N = 30 * 29 / 2;                  // 435 pairs, colex as well: idx = C(b,2) + a
+struct FzTab { int S1, S2, S3, A2, A1, CLX, PLX, BND, end; };    // byte offsets into dynamic shared memory
+__host__ __device__ inline FzTab fz_tab_layout(int o) {
+    FzTab t;
+    o = (o + 15) & ~15;
+    t.A2 = o; o += 8 * FZ_CACHE_CAP * FZ_TLD;
+    t.S1 = o; o += 4 * FZ_CACHE_CAP * FZ_TLD;
+    t.S2 = o; o += 4 * FZ_CACHE_CAP * FZ_TLD;
+    t.S3 = o; o += 4 * FZ_CACHE_CAP * FZ_TLD;
+    t.A1 = o; o += 4 * FZ_CACHE_CAP;
+    t.BND = o; o += 16;                                 // u64: bits of the smallest |stat| seen so far in the current scan
+    t.CLX = o; o += 2 * ((FZ_CLX_N + 7) & ~7);
+    t.PLX = o; o += 2 * ((FZ_PLX_N + 7) & ~7);
+    t.end = o;
+    return t;
+}
 
 template <int THREADS>
-__device__ bool fz_build_tables(const float* R, int ld, int xs, int ys, const int* acc, int m, const FzTables& T, int* s_special) {
-    const int tid = threadIdx.x;
-    if (tid == 0) *s_special = 0;
-    // SQ for z in acc, s in acc + {x, y}
-    for (int e = tid; e < m * (m + 2); e += THREADS) {
-        const int ia = e / (m + 2), ib = e % (m + 2);
-        const int z = acc[ia], sl = ib < m ? acc[ib] : (ib == m ? xs : ys);
-        if (sl != z) T.SQ[z * ld + sl] = sq1mf(R[sl * ld + z]);
+__device__ void fz_build_colex(const FzTab tab) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned short* clx = reinterpret_cast<unsigned short*>(smem + tab.CLX);
+    for (int idx = threadIdx.x; idx < FZ_CLX_N; idx += THREADS) {
+        int c = 2; while ((c + 1) * c * (c - 1) / 6 <= idx) ++c;          // largest c with C(c,3) <= idx
+        int rem = idx - c * (c - 1) * (c - 2) / 6;
+        int b = 1; while ((b + 1) * b / 2 <= rem) ++b;                    // largest b with C(b,2) <= rem
+        int a = rem - b * (b - 1) / 2;
+        clx[idx] = (unsigned short)(a | (b << 5) | (c << 10));
     }
-    __syncthreads();
+    unsigned short* plx = reinterpret_cast<unsigned short*>(smem + tab.PLX);
+    for (int idx = threadIdx.x; idx < FZ_PLX_N; idx += THREADS) {
+        int b = 1; while ((b + 1) * b / 2 <= idx) ++b;
+        plx[idx] = (unsigned short)((idx - b * (b - 1) / 2) | (b << 5));
+    }
+}
+
+// acc[0..m) = slots of the accepted members in list order; xs / ys = slots of X (the target) and Y (the candidate)
+template <int THREADS>
+__device__ bool fz_build_tables(const float* R, int ld, int xs, int ys, const int* acc, int m, const FzTab tab, int* s_special, i64* tri_off, EvalShared* sh) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* S1 = reinterpret_cast<float*>(smem + tab.S1);
+    float* S2 = reinterpret_cast<float*>(smem + tab.S2);
+    float* S3 = reinterpret_cast<float*>(smem + tab.S3);
+    double* A2 = reinterpret_cast<double*>(smem + tab.A2);
+    float* A1 = reinterpret_cast<float*>(smem + tab.A1);
+    const unsigned short* plx = reinterpret_cast<const unsigned short*>(smem + tab.PLX);
+    const int tid = threadIdx.x;
+    const int npairs = m * (m - 1) / 2;
+    if (tid == 0) { *s_special = 0; *reinterpret_cast<u64*>(smem + tab.BND) = (u64)__double_as_longlong(1e300); sh->fail_idx = (u64)FW_INF_IDX; }
+    {   // scan state of eval_subsets_fz_cached, set up here so that it costs no barrier of its own
+        const int c3 = m * (m - 1) * (m - 2) / 6;
+        for (int i = tid; i <= m; i += THREADS) tri_off[i] = c3 - choose3(m - i);
+    }
     bool ok = true;
-    for (int e = tid; e < m * m; e += THREADS) {
-        const int ia = e / m, ib = e % m;
-        const int z = acc[ia];
-        if (ia == ib) {
-            float a1;
-            ok &= p1f(R[xs * ld + ys], R[xs * ld + z], R[ys * ld + z], T.SQ[z * ld + xs], T.SQ[z * ld + ys], a1);
-            T.A1[z] = a1;
+    for (int e = tid; e < npairs + m; e += THREADS) {
+        if (e < npairs) {
+            const int ia = plx[e] & 31, ib = plx[e] >> 5;
+            const float rr = R[acc[ia] * ld + acc[ib]];
+            S1[ia * FZ_TLD + ib] = rr; S1[ib * FZ_TLD + ia] = sq1mf(rr);
         } else {
-            const int sl = acc[ib];
-            float bx, by;
-            ok &= p1f(R[xs * ld + sl], R[xs * ld + z], R[sl * ld + z], T.SQ[z * ld + xs], T.SQ[z * ld + sl], bx);
-            ok &= p1f(R[ys * ld + sl], R[ys * ld + z], R[sl * ld + z], T.SQ[z * ld + ys], T.SQ[z * ld + sl], by);
-            T.BX[z * ld + sl] = bx; T.BY[z * ld + sl] = by;
+            const int ia = e - npairs, z = acc[ia];
+            const float rxz = R[xs * ld + z], ryz = R[ys * ld + z];
+            float a1;
+            ok &= p1f(R[xs * ld + ys], rxz, ryz, sq1mf(rxz), sq1mf(ryz), a1);
+            A1[ia] = a1;
         }
     }
-    if (!ok) *s_special = 1;
     __syncthreads();
-    for (int e = tid; e < m * m; e += THREADS) {
-        const int ia = e / m, ib = e % m;
-        if (ia < ib) { const int z1 = acc[ia], z2 = acc[ib]; T.A2[z1 * ld + z2] = p2f(T.A1[z1], T.BX[z1 * ld + z2], T.BY[z1 * ld + z2]); }
+    for (int e = tid; e < npairs; e += THREADS) {
+        const int ia = plx[e] & 31, ib = plx[e] >> 5;
+        const int z = acc[ia], sl = acc[ib];
+        const float rxz = R[xs * ld + z], ryz = R[ys * ld + z], rsz = S1[ia * FZ_TLD + ib], ssz = S1[ib * FZ_TLD + ia];
+        float bx, by;
+        ok &= p1f(R[xs * ld + sl], rxz, rsz, sq1mf(rxz), ssz, bx);           // pcor(X, s | z)
+        ok &= p1f(R[ys * ld + sl], ryz, rsz, sq1mf(ryz), ssz, by);           // pcor(Y, s | z)
+        const float sbx = sq1mf(bx), sby = sq1mf(by);
+        S2[ia * FZ_TLD + ib] = bx; S2[ib * FZ_TLD + ia] = by;
+        S3[ia * FZ_TLD + ib] = sbx; S3[ib * FZ_TLD + ia] = sby;
+        // pcor(X, Y | z, s) = p2f(A1[z], bx, by)
+        A2[ia * FZ_TLD + ib] = p2f_pre(A1[ia], bx, by, sbx, __dsqrt_rn(__dsub_rn(1.0, __dmul_rn((double)by, (double)by))));
     }
+    if (!ok) *s_special = 1;
     __syncthreads();
     return *s_special == 0;
 }
 
-struct FzCachedTest {
-    CorSlots r; FzTables T; int x, y; FzConsts fc;
-    __device__ __forceinline__ FzTest operator()(int k, int za, int zb, int zc) const {
-        FzTest t; t.df = 0;
-        if (!fc.rows_ok) { t.stat = 0.0; t.pval = 1.0; t.suff = false; return t; }
-        if (k == 1) t.stat = (double)T.A1[za];
-        else if (k == 2) t.stat = T.A2[za * T.ld + zb];
-        else {
-            float z3z2;
-            const bool ok = p1f(r(zc, zb), r(zc, za), r(zb, za), T.SQ[za * T.ld + zc], T.SQ[za * T.ld + zb], z3z2);
-            if (ok) {
-                const double B = p2f(T.BX[za * T.ld + zc], T.BX[za * T.ld + zb], z3z2);     // pcor(X, Z3 | Z1, Z2)
-                const double C = p2f(T.BY[za * T.ld + zc], T.BY[za * T.ld + zb], z3z2);     // pcor(Y, Z3 | Z1, Z2)
-                t.stat = p3d(T.A2[za * T.ld + zb], B, C);
-            } else t.stat = pcor_generic(r, x, y, za, zb, zc, 3);
-        }
-        t.pval = fz_pval_dev(t.stat, fc);
-        t.suff = true;
-        return t;
-    }
+// ---- p-value-free scan of one candidate's conditioning subsets (capacity class 32, tables built) --------------------------
+// Same contract as eval_subsets (subsets.cuh) for max_k = 3, m >= 3 and a non-binding max_tests; the returned
+// (result, Zs, num_tests) is exactly the reference's:
+//  * schedule: the first THREADS subsets of the reference order (size 3 first, lexicographic) are evaluated as one chunk -
+//    this is where the reference's early exit almost always happens (the chunk is skipped when the previous candidate of the
+//    same target had no early exit: speculation only changes `executed`, never the result); if all of them are significant, every remaining subset is
+//    evaluated in one pass (triples in colex order through CLX, then pairs and singles from the tables), each carrying its
+//    reference index, and the first failing index / the arg-max are recovered by block reductions as in eval_subsets;
+//  * significance is decided on |stat| against the band [s_lo, s_hi] around the alpha threshold (the p-value is a decreasing
+//    function of |stat|; inside the band, and for NaN, the exact p-value decides);
+//  * the running maximum p-value (ties -> later subset, tests.jl:338-341) is tracked as the minimum |stat|; whenever two values
+//    are closer than 1e-8 relative, or both p-values are below 1e-290, the exact p-values are compared instead.  Exact
+//    p-values (fp64 log + erfc) are therefore evaluated a handful of times per candidate instead of once per test.
+struct FzScanState {
+    int my_fail; double f_stat;
+    int best_idx; double best_abs, b_stat, b_p; bool bp_valid;
 };
+// slow side of the scan (a handful of calls per candidate).  *bound (shared memory) holds the smallest |stat| any thread of the
+// CTA has accepted so far in this scan: a later |stat| more than TOL above it (and >= s_hi) is significant and cannot be the
+// maximum p-value, so the caller skips it without any bookkeeping.
+__device__ __noinline__ void fz_scan_consider(FzScanState& st, int idx, double s, double alpha, const FzConsts& fc, u64* bound) {
+    constexpr double TOL = 1e-8;
+    const double t = fabs(s);
+    bool sig;
+    double p_new = -1.0;
+    if (t >= fc.s_hi) sig = true;
+    else if (t <= fc.s_lo) sig = false;
+    else { p_new = fz_pval_dev(s, fc); sig = p_new < alpha; }
+    if (!sig) { if (idx < st.my_fail) { st.my_fail = idx; st.f_stat = s; } return; }
+    bool take;
+    if (st.best_idx < 0) take = true;
+    else if (t < st.best_abs * (1.0 - TOL) && t < fc.s_under) take = true;                 // strictly larger p-value
+    else if (t > st.best_abs * (1.0 + TOL) && st.best_abs < fc.s_under) take = false;      // strictly smaller p-value
+    else {
+        // near tie (or both p-values in the underflow range): exact comparison, ties -> later subset
+        if (p_new < 0.0) p_new = fz_pval_dev(s, fc);
+        if (!st.bp_valid) { st.b_p = fz_pval_dev(st.b_stat, fc); st.bp_valid = true; }
+        take = p_new > st.b_p || (p_new == st.b_p && idx > st.best_idx);
+    }
+    if (!take) return;
+    st.best_idx = idx; st.best_abs = t; st.b_stat = s; st.b_p = p_new; st.bp_valid = p_new >= 0.0;
+    if (t < fc.s_under) atomicMin(bound, (u64)__double_as_longlong(t));       // non-negative doubles order like their bit patterns
+}
+
+template <int THREADS>
+__device__ void eval_subsets_fz_cached(const CorSlots r, const FzTab tab, int xs, int ys, const int* acc, int m,
+                                       double alpha, const FzConsts fc, i64* tri_off, EvalShared* sh, EvalOut* out, bool skip0) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const float* S1 = reinterpret_cast<const float*>(smem + tab.S1);
+    const float* S2 = reinterpret_cast<const float*>(smem + tab.S2);
+    const float* S3 = reinterpret_cast<const float*>(smem + tab.S3);
+    const double* A2 = reinterpret_cast<const double*>(smem + tab.A2);
+    const float* A1 = reinterpret_cast<const float*>(smem + tab.A1);
+    const unsigned short* clx = reinterpret_cast<const unsigned short*>(smem + tab.CLX);
+    const unsigned short* plx = reinterpret_cast<const unsigned short*>(smem + tab.PLX);
+    const int tid = threadIdx.x;
+    const int c3 = m * (m - 1) * (m - 2) / 6, c2 = m * (m - 1) / 2, total = c3 + c2 + m;
+    constexpr int NOFAIL = 0x7fffffff;
+    FzScanState st;
+    st.my_fail = NOFAIL; st.f_stat = 0.0; st.best_idx = -1; st.best_abs = 0.0; st.b_stat = 0.0; st.b_p = -1.0; st.bp_valid = false;
+    u64* bound = reinterpret_cast<u64*>(smem + tab.BND);       // reset by fz_build_tables
+
+    // one k = 3 test from the tables; (a < b < c) are positions in the accepted list
+    auto triple = [&](int a, int b, int c) -> double {
+        const int ab = a * FZ_TLD + b, ac = a * FZ_TLD + c, bc = b * FZ_TLD + c;
+        const int ba = b * FZ_TLD + a, ca = c * FZ_TLD + a;
+        float z3z2;
+        if (p1f(S1[bc], S1[ac], S1[ab], S1[ca], S1[ba], z3z2)) {                           // pcor(Z3, Z2 | Z1)
+            const double sc = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn((double)z3z2, (double)z3z2)));
+            const double B = p2f_pre(S2[ac], S2[ab], z3z2, S3[ab], sc);                    // pcor(X, Z3 | Z1, Z2)
+            const double C = p2f_pre(S2[ca], S2[ba], z3z2, S3[ba], sc);                    // pcor(Y, Z3 | Z1, Z2)
+            return p3d(A2[ab], B, C);
+        }
+        return pcor_generic(r, xs, ys, acc[a], acc[b], acc[c], 3);
+    };
+    auto consider = [&](int idx, double s) {
+        const double t = fabs(s);
+        const double bnd = __longlong_as_double((i64)*reinterpret_cast<volatile u64*>(bound));
+        if (t >= fc.s_hi && t > bnd * (1.0 + 1e-8)) return;                                // significant, cannot be the maximum p
+        fz_scan_consider(st, idx, s, alpha, fc, bound);
+    };
+
+    // ---- chunk 0: reference indices [0, THREADS); skipped (skip0, CTA-uniform) when the caller expects no early exit ----
+    const int n0 = skip0 ? 0 : (total < THREADS ? total : THREADS);
+    int executed = n0;
+    bool any_fail = false;
+    if (!skip0) {
+        if (tid < n0) {
+            int k, a, b, c;
+            unrank_subset32(tid, m, c3, c2, tri_off, k, a, b, c);
+            const double s = k == 3 ? triple(a, b, c) : (k == 2 ? A2[a * FZ_TLD + b] : (double)A1[a]);
+            consider(tid, s);
+        }
+        any_fail = __syncthreads_or(st.my_fail != NOFAIL);
+    }
+    if (!any_fail && total > n0) {
+        // ---- everything else in one pass ----
+        for (int q = tid; q < c3; q += THREADS) {
+            const unsigned int e = clx[q];
+            const int a = e & 31, b = (e >> 5) & 31, c = e >> 10;
+            const int na = m - a - 1, pa = b - a - 1;
+            // reference (lexicographic) index: triples that start before a, pairs of the suffix that start before b, then c
+            const int idx = c3 - ((na + 1) * na * (na - 1)) / 6 + pa * na - ((pa * (pa + 1)) >> 1) + (c - b - 1);
+            if (idx < n0) continue;
+            consider(idx, triple(a, b, c));
+        }
+        for (int q = tid; q < c2; q += THREADS) {
+            const int a = plx[q] & 31, b = plx[q] >> 5;
+            const int idx = c3 + a * m - ((a * (a + 1)) >> 1) + (b - a - 1);
+            if (idx < n0) continue;
+            consider(idx, A2[a * FZ_TLD + b]);
+        }
+        for (int q = tid; q < m; q += THREADS) {
+            if (c3 + c2 + q < n0) continue;
+            consider(c3 + c2 + q, (double)A1[q]);
+        }
+        executed = total;
+        any_fail = __syncthreads_or(st.my_fail != NOFAIL);
+    }
+    SubsetCounts sc; sc.c3 = c3; sc.c2 = c2; sc.c1 = m; sc.total = total;
+    if (any_fail) {
+        if (st.my_fail != NOFAIL) atomicMin(&sh->fail_idx, (u64)st.my_fail);
+        __syncthreads();
+        if (st.my_fail != NOFAIL && (u64)st.my_fail == sh->fail_idx) {
+            int k, a, b, c;
+            unrank_subset((i64)st.my_fail, m, sc, tri_off, k, a, b, c);
+            const double f_p = fz_pval_dev(st.f_stat, fc);
+            out->stat = st.f_stat; out->pval = f_p; out->df = 0; out->suff = 1;
+            out->sig = (f_p < alpha) ? 1 : 0;
+            out->k = k; out->pos[0] = a; out->pos[1] = b; out->pos[2] = c;
+            out->num_tests = (i64)st.my_fail + 1; out->total = total; out->executed = executed; executed_by_k(sc, executed, out->ex_k);
+        }
+        __syncthreads();
+        return;
+    }
+    // all significant: only threads whose minimum |stat| is within the tie tolerance of the CTA's minimum (or everything is in
+    // the underflow range, where the bound is never lowered) can hold the maximum p-value; they evaluate it exactly
+    constexpr double TOL = 1e-8;
+    const unsigned full = 0xffffffffu;
+    const double wmin = __longlong_as_double((i64)*reinterpret_cast<volatile u64*>(bound));
+    i64 bidx = -1; double b_p = -1.0, b_stat = 0.0;
+    if (st.best_idx >= 0 && (st.best_abs <= wmin * (1.0 + TOL) || st.best_abs >= fc.s_under)) {
+        b_p = st.bp_valid ? st.b_p : fz_pval_dev(st.b_stat, fc);
+        b_stat = st.b_stat; bidx = st.best_idx;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double op = __shfl_down_sync(full, b_p, off);
+        double os = __shfl_down_sync(full, b_stat, off);
+        i64 oi = __shfl_down_sync(full, bidx, off);
+        if (op > b_p || (op == b_p && oi > bidx)) { b_p = op; b_stat = os; bidx = oi; }
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane == 0) { sh->w_p[warp] = b_p; sh->w_stat[warp] = b_stat; sh->w_idx[warp] = bidx; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < THREADS / 32; ++w) {
+            double op = sh->w_p[w]; i64 oi = sh->w_idx[w];
+            if (op > b_p || (op == b_p && oi > bidx)) { b_p = op; b_stat = sh->w_stat[w]; bidx = oi; }
+        }
+        int k = 0, a = 0, b = 0, c = 0;
+        if (bidx >= 0) unrank_subset(bidx, m, sc, tri_off, k, a, b, c);
+        out->stat = b_stat; out->pval = b_p; out->df = 0; out->suff = 1;
+        out->sig = (b_p < alpha) ? 1 : 0;
+        out->k = k; out->pos[0] = a; out->pos[1] = b; out->pos[2] = c;
+        out->num_tests = total; out->total = total; out->executed = executed; executed_by_k(sc, executed, out->ex_k);
+    }
+    __syncthreads();
+}
 
 // GS: R lives in global scratch (the unbounded capacity class); otherwise it is a plain shared-memory array, which lets
 // the compiler emit LDS instead of generic loads in the test arithmetic.
 template <int THREADS, int TPT, bool NZ, bool GS, bool CACHE>
-__global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? 8 : 1) hiton_fz_kernel(HitonArgs a) {
+#ifndef FW_HITON_MINB
+#define FW_HITON_MINB 5
+#endif
+__global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW_HITON_MINB : 8) : 1) hiton_fz_kernel(HitonArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     const int cap = a.cap;
@@ -146,13 +351,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? 8 : 1) hito
     unsigned int* vmask = reinterpret_cast<unsigned int*>(smem + o);
     if (NZ) o += sizeof(unsigned int) * a.nzt.W;
     o = (o + 15) & ~(size_t)15;
-    FzTables tb;
-    tb.ld = cap;
-    tb.A2 = reinterpret_cast<double*>(smem + o); if (CACHE) o += sizeof(double) * (size_t)cap * cap;
-    tb.SQ = reinterpret_cast<float*>(smem + o); if (CACHE) o += sizeof(float) * (size_t)cap * cap;
-    tb.BX = reinterpret_cast<float*>(smem + o); if (CACHE) o += sizeof(float) * (size_t)cap * cap;
-    tb.BY = reinterpret_cast<float*>(smem + o); if (CACHE) o += sizeof(float) * (size_t)cap * cap;
-    tb.A1 = reinterpret_cast<float*>(smem + o);
+    const FzTab tb = fz_tab_layout((int)o);      // only carved (and only valid) when CACHE
     __shared__ EvalShared sh;
     __shared__ EvalOut ev;
     __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_accept, s_cnt, s_special;
@@ -162,6 +361,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? 8 : 1) hito
     float* R;
     if constexpr (GS) R = a.gscratch + (size_t)blockIdx.x * cap * cap; else R = Rs;
     const int ld = cap;
+    // the p-value-free scan assumes max_tests cannot bind: C(30,3) + C(30,2) + 30 = 4525 subsets at most in this class
+    const bool max_tests_free = a.max_tests <= 0 || a.max_tests > 4525;
+    if constexpr (CACHE) fz_build_colex<THREADS>(tb);         // first use is behind the __syncthreads() of the target loop
 
     for (;;) {
         __syncthreads();
@@ -194,6 +396,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? 8 : 1) hito
         __syncthreads();
         const int n_c = s_nc;
         bool overflow = false;
+        bool spec = false;         // CTA-uniform: the previous cached scan of this target ran to the end (no early exit)
 
         // ---- interleaving phase (hiton.jl:109-149, phase 'I') ------------------------------
         for (int ci = 0; ci < n_c; ++ci) {
@@ -231,10 +434,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? 8 : 1) hito
                 }
                 if (run) {
                     bool cached = false;
-                    if constexpr (CACHE) cached = (M >= 3 && a.max_k >= 3) && fz_build_tables<THREADS>(R, ld, 0, ys, acc, M, tb, &s_special);
+                    if constexpr (CACHE) cached = (M >= 3 && a.max_k >= 3 && max_tests_free) && fz_build_tables<THREADS>(R, ld, 0, ys, acc, M, tb, &s_special, tri_off, &sh);
                     if (cached) {
-                        FzCachedTest tc; tc.r = tf.r; tc.T = tb; tc.x = 0; tc.y = ys; tc.fc = tf.fc;
-                        eval_subsets<THREADS, TPT, 1>(tc, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                        eval_subsets_fz_cached<THREADS>(tf.r, tb, 0, ys, acc, M, a.alpha, tf.fc, tri_off, &sh, &ev, spec);
+                        spec = ev.sig && ev.num_tests == ev.total;
                     } else {
                         eval_subsets<THREADS, TPT, 1>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
                     }
@@ -281,10 +484,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? 8 : 1) hito
                 }
                 if (run) {
                     bool cached = false;
-                    if constexpr (CACHE) cached = (macc >= 3 && a.max_k >= 3) && fz_build_tables<THREADS>(R, ld, 0, c, acc, macc, tb, &s_special);
+                    if constexpr (CACHE) cached = (macc >= 3 && a.max_k >= 3 && max_tests_free) && fz_build_tables<THREADS>(R, ld, 0, c, acc, macc, tb, &s_special, tri_off, &sh);
                     if (cached) {
-                        FzCachedTest tc; tc.r = tf.r; tc.T = tb; tc.x = 0; tc.y = c; tc.fc = tf.fc;
-                        eval_subsets<THREADS, TPT, 1>(tc, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                        eval_subsets_fz_cached<THREADS>(tf.r, tb, 0, c, acc, macc, a.alpha, tf.fc, tri_off, &sh, &ev, spec);
+                        spec = ev.sig && ev.num_tests == ev.total;
                     } else {
                         eval_subsets<THREADS, TPT, 1>(tf, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
                     }
