@@ -83,6 +83,16 @@ __host__ __device__ inline FzTab fz_tab_layout(int o) {
     return t;
 }
 
+// CTA-shared state of one scan: first failing index, and the queue of exact maximum-p candidates (see eval_subsets_fz_cached)
+struct FzScanShared { u64 fail_idx; int n_cont; int c_idx[128]; double c_stat[128]; };    // THREADS <= 128
+// The accepted list of a scan without materialising it: a run of consecutive slots followed by a stored tail.  Interleaving
+// phase: slots 1..M (no tail).  Elimination phase of candidate slot c: the untested slots c+1..M, then the candidates accepted
+// so far in acceptance order (hiton.jl:134-147: the candidate is deleted from `accepted` and pushed back when it survives).
+struct AccView {
+    int n_head, head_base; const int* tail;
+    __device__ __forceinline__ int operator[](int j) const { return j < n_head ? head_base + j : tail[j - n_head]; }
+};
+
 template <int THREADS>
 __device__ void fz_build_colex(const FzTab tab) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -103,7 +113,7 @@ __device__ void fz_build_colex(const FzTab tab) {
 
 // acc[0..m) = slots of the accepted members in list order; xs / ys = slots of X (the target) and Y (the candidate)
 template <int THREADS>
-__device__ bool fz_build_tables(const float* R, int ld, int xs, int ys, const int* acc, int m, const FzTab tab, int* s_special, i64* tri_off, EvalShared* sh) {
+__device__ bool fz_build_tables(const float* R, int ld, int xs, int ys, const AccView acc, int m, const FzTab tab, i64* tri_off, FzScanShared* sh) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* S1 = reinterpret_cast<float*>(smem + tab.S1);
     float* S2 = reinterpret_cast<float*>(smem + tab.S2);
@@ -113,42 +123,39 @@ __device__ bool fz_build_tables(const float* R, int ld, int xs, int ys, const in
     const unsigned short* plx = reinterpret_cast<const unsigned short*>(smem + tab.PLX);
     const int tid = threadIdx.x;
     const int npairs = m * (m - 1) / 2;
-    if (tid == 0) { *s_special = 0; *reinterpret_cast<u64*>(smem + tab.BND) = (u64)__double_as_longlong(1e300); sh->fail_idx = (u64)FW_INF_IDX; }
+    if (tid == 0) { *reinterpret_cast<u64*>(smem + tab.BND) = (u64)__double_as_longlong(1e300); sh->fail_idx = (u64)FW_INF_IDX; sh->n_cont = 0; }
     {   // scan state of eval_subsets_fz_cached, set up here so that it costs no barrier of its own
         const int c3 = m * (m - 1) * (m - 2) / 6;
         for (int i = tid; i <= m; i += THREADS) tri_off[i] = c3 - choose3(m - i);
     }
     bool ok = true;
-    for (int e = tid; e < npairs + m; e += THREADS) {
-        if (e < npairs) {
-            const int ia = plx[e] & 31, ib = plx[e] >> 5;
-            const float rr = R[acc[ia] * ld + acc[ib]];
-            S1[ia * FZ_TLD + ib] = rr; S1[ib * FZ_TLD + ia] = sq1mf(rr);
-        } else {
-            const int ia = e - npairs, z = acc[ia];
-            const float rxz = R[xs * ld + z], ryz = R[ys * ld + z];
-            float a1;
-            ok &= p1f(R[xs * ld + ys], rxz, ryz, sq1mf(rxz), sq1mf(ryz), a1);
-            A1[ia] = a1;
-        }
-    }
-    __syncthreads();
+    const float rxy = R[xs * ld + ys];
     for (int e = tid; e < npairs; e += THREADS) {
         const int ia = plx[e] & 31, ib = plx[e] >> 5;
         const int z = acc[ia], sl = acc[ib];
-        const float rxz = R[xs * ld + z], ryz = R[ys * ld + z], rsz = S1[ia * FZ_TLD + ib], ssz = S1[ib * FZ_TLD + ia];
-        float bx, by;
-        ok &= p1f(R[xs * ld + sl], rxz, rsz, sq1mf(rxz), ssz, bx);           // pcor(X, s | z)
-        ok &= p1f(R[ys * ld + sl], ryz, rsz, sq1mf(ryz), ssz, by);           // pcor(Y, s | z)
+        const float rsz = R[z * ld + sl], ssz = sq1mf(rsz);
+        S1[ia * FZ_TLD + ib] = rsz; S1[ib * FZ_TLD + ia] = ssz;
+        const float rxz = R[xs * ld + z], ryz = R[ys * ld + z];
+        const float sxz = sq1mf(rxz), syz = sq1mf(ryz);
+        float a1, bx, by;
+        ok &= p1f(rxy, rxz, ryz, sxz, syz, a1);                              // pcor(X, Y | z)   (every thread of row ia computes the same value)
+        ok &= p1f(R[xs * ld + sl], rxz, rsz, sxz, ssz, bx);                  // pcor(X, s | z)
+        ok &= p1f(R[ys * ld + sl], ryz, rsz, syz, ssz, by);                  // pcor(Y, s | z)
         const float sbx = sq1mf(bx), sby = sq1mf(by);
         S2[ia * FZ_TLD + ib] = bx; S2[ib * FZ_TLD + ia] = by;
         S3[ia * FZ_TLD + ib] = sbx; S3[ib * FZ_TLD + ia] = sby;
+        if (ib == ia + 1) A1[ia] = a1;
         // pcor(X, Y | z, s) = p2f(A1[z], bx, by)
-        A2[ia * FZ_TLD + ib] = p2f_pre(A1[ia], bx, by, sbx, __dsqrt_rn(__dsub_rn(1.0, __dmul_rn((double)by, (double)by))));
+        A2[ia * FZ_TLD + ib] = p2f_pre(a1, bx, by, sbx, __dsqrt_rn(__dsub_rn(1.0, __dmul_rn((double)by, (double)by))));
     }
-    if (!ok) *s_special = 1;
-    __syncthreads();
-    return *s_special == 0;
+    if (tid == 0) {                                                          // the last position starts no pair
+        const int z = acc[m - 1];
+        const float rxz = R[xs * ld + z], ryz = R[ys * ld + z];
+        float a1;
+        ok &= p1f(rxy, rxz, ryz, sq1mf(rxz), sq1mf(ryz), a1);
+        A1[m - 1] = a1;
+    }
+    return __syncthreads_or(!ok) == 0;
 }
 
 // ---- p-value-free scan of one candidate's conditioning subsets (capacity class 32, tables built) --------------------------
@@ -195,9 +202,11 @@ __device__ __noinline__ void fz_scan_consider(FzScanState& st, int idx, double s
     if (t < fc.s_under) atomicMin(bound, (u64)__double_as_longlong(t));       // non-negative doubles order like their bit patterns
 }
 
-template <int THREADS>
-__device__ void eval_subsets_fz_cached(const CorSlots r, const FzTab tab, int xs, int ys, const int* acc, int m,
-                                       double alpha, const FzConsts fc, i64* tri_off, EvalShared* sh, EvalOut* out, bool skip0) {
+// out->pval = -1.0 means "deferred": the maximum was unique, so no p-value had to be evaluated to find it; the caller evaluates
+// fz_pval_dev(out->stat, fc) when it needs the number.  NEED_POS: also report the positions of the returned subset.
+template <int THREADS, bool NEED_POS>
+__device__ void eval_subsets_fz_cached(const CorSlots r, const FzTab tab, int xs, int ys, const AccView acc, int m,
+                                       double alpha, const FzConsts fc, i64* tri_off, FzScanShared* sh, EvalOut* out, bool skip0) {
     extern __shared__ __align__(16) unsigned char smem[];
     const float* S1 = reinterpret_cast<const float*>(smem + tab.S1);
     const float* S2 = reinterpret_cast<const float*>(smem + tab.S2);
@@ -275,8 +284,8 @@ __device__ void eval_subsets_fz_cached(const CorSlots r, const FzTab tab, int xs
         if (st.my_fail != NOFAIL) atomicMin(&sh->fail_idx, (u64)st.my_fail);
         __syncthreads();
         if (st.my_fail != NOFAIL && (u64)st.my_fail == sh->fail_idx) {
-            int k, a, b, c;
-            unrank_subset((i64)st.my_fail, m, sc, tri_off, k, a, b, c);
+            int k = 0, a = 0, b = 0, c = 0;
+            if constexpr (NEED_POS) unrank_subset((i64)st.my_fail, m, sc, tri_off, k, a, b, c);
             const double f_p = fz_pval_dev(st.f_stat, fc);
             out->stat = st.f_stat; out->pval = f_p; out->df = 0; out->suff = 1;
             out->sig = (f_p < alpha) ? 1 : 0;
@@ -287,38 +296,33 @@ __device__ void eval_subsets_fz_cached(const CorSlots r, const FzTab tab, int xs
         return;
     }
     // all significant: only threads whose minimum |stat| is within the tie tolerance of the CTA's minimum (or everything is in
-    // the underflow range, where the bound is never lowered) can hold the maximum p-value; they evaluate it exactly
+    // the underflow range, where the bound is never lowered) can hold the maximum p-value; they evaluate it exactly and queue
+    // it for thread 0, which picks the maximum (ties -> later subset) - usually out of a single entry
     constexpr double TOL = 1e-8;
-    const unsigned full = 0xffffffffu;
     const double wmin = __longlong_as_double((i64)*reinterpret_cast<volatile u64*>(bound));
-    i64 bidx = -1; double b_p = -1.0, b_stat = 0.0;
     if (st.best_idx >= 0 && (st.best_abs <= wmin * (1.0 + TOL) || st.best_abs >= fc.s_under)) {
-        b_p = st.bp_valid ? st.b_p : fz_pval_dev(st.b_stat, fc);
-        b_stat = st.b_stat; bidx = st.best_idx;
+        const int slot = atomicAdd(&sh->n_cont, 1);
+        sh->c_stat[slot] = st.b_stat; sh->c_idx[slot] = st.best_idx;
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        double op = __shfl_down_sync(full, b_p, off);
-        double os = __shfl_down_sync(full, b_stat, off);
-        i64 oi = __shfl_down_sync(full, bidx, off);
-        if (op > b_p || (op == b_p && oi > bidx)) { b_p = op; b_stat = os; bidx = oi; }
-    }
-    const int warp = tid >> 5, lane = tid & 31;
-    if (lane == 0) { sh->w_p[warp] = b_p; sh->w_stat[warp] = b_stat; sh->w_idx[warp] = bidx; }
     __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < THREADS / 32; ++w) {
-            double op = sh->w_p[w]; i64 oi = sh->w_idx[w];
-            if (op > b_p || (op == b_p && oi > bidx)) { b_p = op; b_stat = sh->w_stat[w]; bidx = oi; }
+        const int nc = sh->n_cont;
+        double b_p = -1.0, b_stat = sh->c_stat[0]; i64 bidx = sh->c_idx[0];
+        if (nc > 1) {
+            bidx = -1;
+            for (int w = 0; w < nc; ++w) {
+                const double op = fz_pval_dev(sh->c_stat[w], fc); const i64 oi = sh->c_idx[w];
+                if (op > b_p || (op == b_p && oi > bidx)) { b_p = op; b_stat = sh->c_stat[w]; bidx = oi; }
+            }
         }
         int k = 0, a = 0, b = 0, c = 0;
-        if (bidx >= 0) unrank_subset(bidx, m, sc, tri_off, k, a, b, c);
+        if constexpr (NEED_POS) unrank_subset(bidx, m, sc, tri_off, k, a, b, c);
         out->stat = b_stat; out->pval = b_p; out->df = 0; out->suff = 1;
-        out->sig = (b_p < alpha) ? 1 : 0;
+        out->sig = 1;                                   // every subset was significant
         out->k = k; out->pos[0] = a; out->pos[1] = b; out->pos[2] = c;
         out->num_tests = total; out->total = total; out->executed = executed; executed_by_k(sc, executed, out->ex_k);
     }
-    __syncthreads();
+    // no trailing barrier: `out` is complete for thread 0 only; the caller's next barrier publishes it
 }
 
 // GS: R lives in global scratch (the unbounded capacity class); otherwise it is a plain shared-memory array, which lets
@@ -354,7 +358,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
     const FzTab tb = fz_tab_layout((int)o);      // only carved (and only valid) when CACHE
     __shared__ EvalShared sh;
     __shared__ EvalOut ev;
-    __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_accept, s_cnt, s_special;
+    __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_cnt, s_spec;
+    __shared__ FzScanShared fsh;
     __shared__ i64 s_ntests;
     __shared__ u64 s_exec, s_exk[3];
 
@@ -379,7 +384,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
         int* order = a.cand_order + o0;
 
         // ---- prepare_interleaving_phase (hiton.jl:199-220): p < alpha, stable sort by p ----
-        if (tid == 0) { s_nc = 0; s_M = 0; s_ntests = 0; s_exec = 0; s_exk[0] = s_exk[1] = s_exk[2] = 0; }
+        if (tid == 0) { s_nc = 0; s_M = 0; s_ntests = 0; s_exec = 0; s_exk[0] = s_exk[1] = s_exk[2] = 0; s_spec = 0; }
         __syncthreads();
         for (int i = tid; i < n_uni; i += THREADS) {
             double pi = a.uni_p[e0 + i];
@@ -396,11 +401,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
         __syncthreads();
         const int n_c = s_nc;
         bool overflow = false;
-        bool spec = false;         // CTA-uniform: the previous cached scan of this target ran to the end (no early exit)
 
+        // One barrier-separated serial section per candidate: thread 0 consumes the scan result (`ev`), does the accept /
+        // reject bookkeeping of update_sig_result! (hiton.jl:53-78) and prepares the accepted list of the next candidate.
         // ---- interleaving phase (hiton.jl:109-149, phase 'I') ------------------------------
         for (int ci = 0; ci < n_c; ++ci) {
-            const int M = s_M;
+            const int M = s_M;                         // accepted so far; acc[0..M) = slots 1..M (kept by thread 0)
             if (M + 2 > cap) { overflow = true; break; }
             const int ui = order[ci];
             const i64 cand = a.uni_nbr[e0 + ui];
@@ -415,15 +421,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
             } else {
                 for (int s = tid; s <= M + 1; s += THREADS) slotvar[s] = (s == 0) ? T : (s == ys ? cand : member[s - 1]);
             }
-            if (tid == 0) s_accept = 0;
             __syncthreads();
+            bool accept = false;                       // meaningful in thread 0 only
             if (M == 0) {
                 // accepted empty: accept with the univariate result (hiton.jl:57-59)
-                if (tid == 0) { tpc_stat[0] = a.uni_stat[e0 + ui]; tpc_p[0] = a.uni_p[e0 + ui]; s_accept = 1; }
+                if (tid == 0) { tpc_stat[0] = a.uni_stat[e0 + ui]; tpc_p[0] = a.uni_p[e0 + ui]; accept = true; }
             } else {
-                if (tid < M) acc[tid] = tid + 1;
-                for (int s = tid + THREADS; s < M; s += THREADS) acc[s] = s + 1;
-                __syncthreads();
                 FzSlotTest tf; tf.r.R = R; tf.r.ld = ld; tf.x = 0; tf.y = ys; tf.fc = a.fc;
                 bool run = true;
                 if constexpr (NZ) {
@@ -434,21 +437,20 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
                 }
                 if (run) {
                     bool cached = false;
-                    if constexpr (CACHE) cached = (M >= 3 && a.max_k >= 3 && max_tests_free) && fz_build_tables<THREADS>(R, ld, 0, ys, acc, M, tb, &s_special, tri_off, &sh);
-                    if (cached) {
-                        eval_subsets_fz_cached<THREADS>(tf.r, tb, 0, ys, acc, M, a.alpha, tf.fc, tri_off, &sh, &ev, spec);
-                        spec = ev.sig && ev.num_tests == ev.total;
-                    } else {
-                        eval_subsets<THREADS, TPT, 1>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                    if constexpr (CACHE) {
+                        AccView av; av.n_head = M; av.head_base = 1; av.tail = pc_slot;
+                        cached = (M >= 3 && a.max_k >= 3 && max_tests_free) && fz_build_tables<THREADS>(R, ld, 0, ys, av, M, tb, tri_off, &fsh);
+                        if (cached) eval_subsets_fz_cached<THREADS, false>(tf.r, tb, 0, ys, av, M, a.alpha, tf.fc, tri_off, &fsh, &ev, s_spec != 0);
                     }
+                    if (!cached) eval_subsets<THREADS, TPT, 1>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
                     if (tid == 0) {
                         s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
-                        if (ev.sig) { tpc_stat[M] = ev.stat; tpc_p[M] = ev.pval; s_accept = 1; }
+                        if (ev.sig) { tpc_stat[M] = ev.stat; tpc_p[M] = ev.pval; accept = true; }
+                        s_spec = (cached && ev.sig && ev.num_tests == ev.total) ? 1 : 0;
                     }
                 }
             }
-            __syncthreads();
-            if (s_accept) { if (tid == 0) { member[M] = cand; s_M = M + 1; } }
+            if (tid == 0 && accept) { member[M] = cand; acc[M] = M + 1; s_M = M + 1; }
             __syncthreads();
         }
         if (overflow) {
@@ -457,21 +459,18 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
         }
 
         // ---- elimination phase (phase 'E', fast_elim = true) ---------------------------------
+        // accepted list of candidate slot c = AccView{untested slots c+1..M, then pc_slot[0..npc)}: deleteat!(accepted, candidate)
+        // and push!(accepted, candidate) of hiton.jl:134-147 without moving anything
         const int M = s_M;
-        for (int s = tid; s < M; s += THREADS) acc[s] = s + 1;
-        if (tid == 0) { s_macc = M; s_npc = 0; }
+        if (tid == 0) s_npc = 0;
         __syncthreads();
         for (int c = 1; c <= M; ++c) {
-            if (tid == 0) {
-                // deleteat!(accepted, findall(in(candidate), accepted))  (hiton.jl:134-136)
-                int w = 0, macc = s_macc;
-                for (int j = 0; j < macc; ++j) { int v = acc[j]; if (v != c) acc[w++] = v; }
-                s_macc = w; s_accept = 0;
-            }
-            __syncthreads();
-            const int macc = s_macc;
+            const int npc0 = s_npc;
+            const int macc = (M - c) + npc0;
+            AccView av; av.n_head = M - c; av.head_base = c + 1; av.tail = pc_slot;
+            bool accept = false;                       // thread 0 only
             if (macc == 0) {
-                if (tid == 0) { pcs_stat[s_npc] = tpc_stat[c - 1]; pcs_p[s_npc] = tpc_p[c - 1]; s_accept = 1; }   // support_dict = TPC_dict
+                if (tid == 0) { pcs_stat[npc0] = tpc_stat[c - 1]; pcs_p[npc0] = tpc_p[c - 1]; accept = true; }   // support_dict = TPC_dict
             } else {
                 FzSlotTest tf; tf.r.R = R; tf.r.ld = ld; tf.x = 0; tf.y = c; tf.fc = a.fc;
                 bool run = true;
@@ -484,26 +483,37 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
                 }
                 if (run) {
                     bool cached = false;
-                    if constexpr (CACHE) cached = (macc >= 3 && a.max_k >= 3 && max_tests_free) && fz_build_tables<THREADS>(R, ld, 0, c, acc, macc, tb, &s_special, tri_off, &sh);
-                    if (cached) {
-                        eval_subsets_fz_cached<THREADS>(tf.r, tb, 0, c, acc, macc, a.alpha, tf.fc, tri_off, &sh, &ev, spec);
-                        spec = ev.sig && ev.num_tests == ev.total;
-                    } else {
+                    if constexpr (CACHE) {
+                        cached = (macc >= 3 && a.max_k >= 3 && max_tests_free) && fz_build_tables<THREADS>(R, ld, 0, c, av, macc, tb, tri_off, &fsh);
+                        if (cached) eval_subsets_fz_cached<THREADS, false>(tf.r, tb, 0, c, av, macc, a.alpha, tf.fc, tri_off, &fsh, &ev, s_spec != 0);
+                    }
+                    if (!cached) {
+                        for (int j = tid; j < macc; j += THREADS) acc[j] = av[j];
+                        __syncthreads();
                         eval_subsets<THREADS, TPT, 1>(tf, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
                     }
                     if (tid == 0) {
                         s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
-                        if (ev.sig) { pcs_stat[s_npc] = ev.stat; pcs_p[s_npc] = ev.pval; s_accept = 1; }
+                        if (ev.sig) { pcs_stat[npc0] = ev.stat; pcs_p[npc0] = ev.pval; accept = true; }
+                        s_spec = (cached && ev.sig && ev.num_tests == ev.total) ? 1 : 0;
                     }
                 }
             }
-            __syncthreads();
-            if (tid == 0 && s_accept) { acc[s_macc] = c; s_macc = s_macc + 1; pc_slot[s_npc] = c; s_npc = s_npc + 1; }
+            if (tid == 0 && accept) { pc_slot[npc0] = c; s_npc = npc0 + 1; }
             __syncthreads();
         }
 
         // ---- update_PC_dict! (hiton.jl:249-256) and write-out ---------------------------------
         const int npc = s_npc;
+        if constexpr (CACHE) {
+            // p-values the scans did not need (unique maximum |stat| ordering) are evaluated here, one thread each
+            for (int i = tid; i < M + npc; i += THREADS) {
+                double* pp = i < M ? &tpc_p[i] : &pcs_p[i - M];
+                const double st_ = i < M ? tpc_stat[i] : pcs_stat[i - M];
+                if (*pp < 0.0) *pp = fz_pval_dev(st_, a.fc);
+            }
+            __syncthreads();
+        }
         for (int i = tid; i < npc; i += THREADS) {
             int c = pc_slot[i];
             double s = pcs_stat[i], pp = pcs_p[i];
