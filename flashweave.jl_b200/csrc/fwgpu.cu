@@ -84,6 +84,7 @@ struct fw_ctx {
     DevBuf<int> d_counter; DevBuf<u64> d_exec;
     PairwiseScratch pw;
     cortc::Scratch tc;
+    fznztc::Planes nzplanes;             // bf16 operand planes of the fz_nz pairwise pre-filter
     cortc::Prepared tcp;                 // standardised table + TMA descriptors of the row-sharded cor_mat path
     // fw_hiton_pc work buffers (grow-only, reused across calls)
     struct HitonBufs {
@@ -169,7 +170,7 @@ static size_t hiton_smem_bytes(int cap, bool r_in_smem, int nz_words = -1, bool 
     o = (o + 15) & ~(size_t)15;
     o += sizeof(i64) * (cap + 1) + 4 * sizeof(double) * cap + sizeof(i64) * cap + 2 * sizeof(int) * cap;
     o = (o + 15) & ~(size_t)15;
-    if (nz_words >= 0) o += sizeof(i64) * cap + 2 * sizeof(double) * cap + sizeof(unsigned int) * nz_words;
+    if (nz_words >= 0) o += sizeof(i64) * cap + 2 * sizeof(double) * cap + sizeof(unsigned int) * nz_words + 16 + FZNZ_GRAM_BYTES;
     o = (o + 15) & ~(size_t)15;
     if (cache) o = (size_t)fz_tab_layout((int)o).end;
     return o + 16;
@@ -179,7 +180,7 @@ static size_t subsets_smem_bytes(int cap, bool r_in_smem, int nz_words = -1) {
     o = (o + 15) & ~(size_t)15;
     o += sizeof(i64) * (cap + 1) + sizeof(int) * cap;
     o = (o + 15) & ~(size_t)15;
-    if (nz_words >= 0) o += sizeof(i64) * cap + 2 * sizeof(double) * cap + sizeof(unsigned int) * nz_words;
+    if (nz_words >= 0) o += sizeof(i64) * cap + 2 * sizeof(double) * cap + sizeof(unsigned int) * nz_words + 16 + FZNZ_GRAM_BYTES;
     return o + 16;
 }
 
@@ -489,7 +490,10 @@ int32_t fw_test_batch(fw_ctx* ctx, int32_t kind, int64_t n_tests, const int64_t*
         mi_test_batch_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, smem, ctx->stream>>>(t, n_tests, dx.ptr, dy.ptr, dk.ptr, dz.ptr, hps, n_obs_min, dout.ptr);
     } else if (nzk) {
         i64 blocks = std::min<i64>(n_tests, (i64)ctx->sm_count * 8);
-        fznz_test_batch_kernel<256><<<(unsigned)blocks, 256, sizeof(unsigned int) * nzt.W, ctx->stream>>>(nzt, n_tests, dx.ptr, dy.ptr, dk.ptr, dz.ptr, n_obs_min, dout.ptr);
+        const size_t nz_smem = sizeof(unsigned int) * nzt.W + 16 + FZNZ_GRAM_BYTES;
+        NEED(nz_smem <= 200 * 1024, FW_ERR_UNSUPPORTED, "fw_test_batch: %lld rows do not fit the fz_nz kernel's shared memory", (long long)ctx->n);
+        CK(cudaFuncSetAttribute(fznz_test_batch_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nz_smem));
+        fznz_test_batch_kernel<256><<<(unsigned)blocks, 256, nz_smem, ctx->stream>>>(nzt, n_tests, dx.ptr, dy.ptr, dk.ptr, dz.ptr, n_obs_min, dout.ptr);
     } else {
         FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
         int threads = 128; i64 blocks = (n_tests + threads - 1) / threads;
@@ -662,7 +666,7 @@ int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_
         MiTable t = make_mi_table(ctx, kind);
         e = pairwise_mi_run(ctx->pw, t, hps, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0, ctx->stream, &po, &nl, &msg);
     } else if (nzk) {
-        e = pairwise_fznz_run(ctx->pw, nzt, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0, ctx->stream, &po, &nl, &msg);
+        e = pairwise_fznz_run(ctx->pw, ctx->nzplanes, nzt, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0, ctx->stream, &po, &nl, &msg);
     } else {
         FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
         e = pairwise_fz_run(ctx->pw, ctx->d_cor.ptr, p, fc, ctx->n_obs, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0,
@@ -890,8 +894,10 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
     // escalate the few targets whose accepted set outgrows the class
     std::vector<int> pending[5];
     for (i64 t = 0; t < n_targets && !disc; ++t) {
+        // the accepted set is usually far smaller than the candidate list: up to 94 candidates start in the 32-slot class
+        // (tables + p-value-free scan) and are re-run in a larger class only if more than 30 get accepted
         i64 need = (hoff[t + 1] - hoff[t]) + 2;
-        pending[need <= 32 ? 0 : 1].push_back((int)t);
+        pending[need <= 96 ? 0 : 1].push_back((int)t);
     }
     std::vector<int> hstatus(n_targets);
     if (!disc) CK(cudaEventRecord(ctx->ev[4], ctx->stream));

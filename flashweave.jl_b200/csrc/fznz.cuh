@@ -77,9 +77,146 @@ __device__ NzUni fznz_uni_warp(const NzTable& t, i64 X, i64 Y, i64 n_obs_min) {
     return r;
 }
 
-// ---- block-cooperative cor_subset! (statfuns.jl:138-155) on the rows where var[0] != 0 and var[1] != 0 ------
-// Fills R[i*ld + j] for all slot pairs i != j < nv (slot -> variable id in var[]), NaN -> 0.  mask: W words of
-// shared memory, mom: 2*nv doubles of shared memory.  Returns the number of rows of the view (all threads).
+// ---- register-blocked Gram matrix of one job (nv <= 34 variables) ------------------------------------------------------------
+// All moments of cor_subset! in ONE pass over the table: with v = (x_0 .. x_{nv-1}, 1) the upper triangle of G = sum over the
+// view rows of v v^T holds every cross product, every sum of squares and every sum.  The rows are staged in tiles of
+// FZNZ_TROWS rows x nv variables (coalesced reads along each variable, converted to fp64 once and transposed into [row][33]
+// shared memory); a warp takes
+// every (THREADS/32)-th view row of the tile and each lane owns one B x B block of the upper triangle of G in fp64 registers
+// (B = 4; more than 32 blocks - 29 to 33 entries of v - take a second pass over the table), the next tile's global reads
+// are in flight while the current one is consumed, so a row costs 2B shared-memory reads and B*B DFMA per lane - the
+// pair-per-warp version re-read both columns from L2 for each of the nv(nv-1)/2 pairs.  Partial sums of the warps are added in
+// warp order (deterministic), then r_ab = (G_ab - S_a S_b / n) / sqrt((G_aa - S_a^2/n)(G_bb - S_b^2/n)) in fp64, rounded to
+// Float32 (cor_mat's eltype), NaN -> 0.  Same statistics as the two-pass form of Statistics.cor up to fp64 rounding.
+constexpr int FZNZ_TROWS = 128;
+constexpr int FZNZ_TLD = 33;
+constexpr int FZNZ_GMAX = 36;                           // row stride of G (9 blocks of 4)
+constexpr int FZNZ_NVMAX = 32;                          // variables of a job on this path (+ the ones column = 33 = FZNZ_TLD)
+constexpr int FZNZ_GRAM_BYTES = (FZNZ_TROWS * FZNZ_TLD + 8) * 8 + FZNZ_GMAX * FZNZ_GMAX * 8 + 32;
+
+template <int THREADS>
+__device__ void fznz_gram_block(const float* __restrict__ data, i64 ldv, int n, int W, const i64* var, int nv, int rows,
+                                float* R, int ld, const unsigned int* mask, unsigned int buf_off) {
+    extern __shared__ __align__(16) unsigned char smem[];      // buf_off: offset of the scratch from the dynamic shared-memory base (keeps LDS/STS)
+    unsigned char* buf = smem + buf_off;
+    constexpr int B = 4;
+    constexpr int NW = THREADS / 32;
+    constexpr int PF = (FZNZ_NVMAX * FZNZ_TROWS + THREADS - 1) / THREADS;                // staged values per thread and tile
+    static_assert(NW * 32 * B * B <= FZNZ_TROWS * FZNZ_TLD, "warp partials reuse the tile buffer");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* tile = reinterpret_cast<double*>(buf);                                       // [FZNZ_TROWS][FZNZ_TLD] (+ 8 of slack: blocks may over-read)
+    double* G = tile + FZNZ_TROWS * FZNZ_TLD + 8;                                        // [ne][FZNZ_GMAX], upper triangle
+    const int ne = nv + 1;                                                               // entries of v; v[nv] = 1
+    const int g = (ne + B - 1) / B;                                                      // block grid of the upper triangle
+    const int nblk = g * (g + 1) / 2;                                                    // <= 45: one or two passes of 32 blocks
+    const int n_stage = nv * FZNZ_TROWS;
+    auto block_of = [&](int q, int& bi, int& bj) { for (bi = 0; bi < g; ++bi) { const int len = g - bi; if (q < len) { bj = bi + q; return; } q -= len; } bi = bj = 0; };
+    auto next_tile = [&](int r0) {                                                       // first tile at or after r0 with a view row (uniform)
+        for (; r0 < n; r0 += FZNZ_TROWS) {
+            const int w0 = r0 >> 5;
+            unsigned int any = 0;
+#pragma unroll
+            for (int w = 0; w < FZNZ_TROWS / 32; ++w) any |= (w0 + w < W) ? mask[w0 + w] : 0u;
+            if (any) break;
+        }
+        return r0;
+    };
+    for (int pass = 0; pass * 32 < nblk; ++pass) {
+        const int q = lane + 32 * pass;
+        const bool live = q < nblk;
+        int bi, bj; block_of(live ? q : 0, bi, bj);
+        const int i0 = bi * B, j0 = bj * B;
+        double acc[B][B];
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+#pragma unroll
+            for (int j = 0; j < B; ++j) acc[i][j] = 0.0;
+        }
+        __syncthreads();                                                                 // the tile buffer is free (previous pass / caller)
+        for (int e = tid; e < FZNZ_TROWS; e += THREADS) {                                // the ones column and the padding never change
+#pragma unroll 1
+            for (int a = nv; a < FZNZ_TLD; ++a) tile[e * FZNZ_TLD + a] = (a == nv) ? 1.0 : 0.0;
+        }
+        float pf[PF];
+        auto fetch = [&](int r0) {
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int e = tid + k * THREADS;
+                const int a = e / FZNZ_TROWS, row = r0 + (e % FZNZ_TROWS);
+                pf[k] = (e < n_stage && row < n) ? __ldg(data + var[a] * ldv + row) : 0.0f;
+            }
+        };
+        int r0 = next_tile(0);
+        if (r0 < n) fetch(r0);
+        while (r0 < n) {
+            __syncthreads();                                                             // previous tile fully consumed
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int e = tid + k * THREADS;
+                if (e < n_stage) tile[(e % FZNZ_TROWS) * FZNZ_TLD + e / FZNZ_TROWS] = (double)pf[k];
+            }
+            __syncthreads();
+            const int r1 = next_tile(r0 + FZNZ_TROWS);
+            if (r1 < n) fetch(r1);                                                       // in flight while this tile is consumed
+            for (int r = warp; r < FZNZ_TROWS; r += NW) {
+                const int row = r0 + r;
+                if (row >= n || !((mask[row >> 5] >> (row & 31)) & 1u)) continue;        // warp-uniform
+                if (live) {
+                    const double* v = tile + r * FZNZ_TLD;
+                    double vi[B], vj[B];
+#pragma unroll
+                    for (int i = 0; i < B; ++i) { vi[i] = v[i0 + i]; vj[i] = v[j0 + i]; }
+#pragma unroll
+                    for (int i = 0; i < B; ++i) {
+#pragma unroll
+                        for (int j = 0; j < B; ++j) acc[i][j] = fma(vi[i], vj[j], acc[i][j]);
+                    }
+                }
+            }
+            r0 = r1;
+        }
+        // cross-warp reduction in a fixed order (deterministic): partials through the tile buffer
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+#pragma unroll
+            for (int j = 0; j < B; ++j) tile[(warp * 32 + lane) * (B * B) + i * B + j] = acc[i][j];
+        }
+        __syncthreads();
+        for (int e = tid; e < 32 * B * B; e += THREADS) {
+            const int blk = e / (B * B), ij = e % (B * B);
+            const int qq = blk + 32 * pass;
+            if (qq >= nblk) continue;
+            int ci, cj; block_of(qq, ci, cj);
+            const int gi = ci * B + ij / B, gj = cj * B + ij % B;
+            if (gi < ne && gj < ne && gi <= gj) {
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) sum += tile[(w * 32 + blk) * (B * B) + ij];
+                G[gi * FZNZ_GMAX + gj] = sum;
+            }
+        }
+    }
+    __syncthreads();
+    const double inv_n = 1.0 / (double)rows;
+    const int n_pairs = nv * (nv - 1) / 2;
+    for (int e = tid; e < n_pairs; e += THREADS) {
+        int a, b; unrank2_small(e, nv, a, b);
+        const double sa = G[a * FZNZ_GMAX + nv], sb = G[b * FZNZ_GMAX + nv];
+        const double caa = G[a * FZNZ_GMAX + a] - sa * sa * inv_n, cbb = G[b * FZNZ_GMAX + b] - sb * sb * inv_n;
+        const double cab = G[a * FZNZ_GMAX + b] - sa * sb * inv_n;
+        double rr = cab / (sqrt(caa) * sqrt(cbb));
+        if (rr > 1.0) rr = 1.0; else if (rr < -1.0) rr = -1.0;
+        const float rf = isnan(rr) ? 0.0f : (float)rr;                                   // statfuns.jl:150: NaN -> 0; cor_mat eltype Float32
+        R[a * ld + b] = rf; R[b * ld + a] = rf;
+    }
+    __syncthreads();
+}
+
+// ---- block-cooperative cor_subset! (statfuns.jl:138-155) on the rows where var[xs] != 0 and var[ys] != 0 ------
+// Fills R[i*ld + j] for all slot pairs i != j < nv (slot -> variable id in var[]), NaN -> 0.  mask: W words of shared memory
+// followed (16-byte aligned) by FZNZ_GRAM_BYTES of scratch, mom: 2*nv doubles of shared memory.  Returns the number of rows of
+// the view (all threads).
 template <int THREADS>
 __device__ int fznz_subcor_block(const NzTable& t, const i64* var, int nv, int xs, int ys, float* R, int ld, unsigned int* mask, double* mom, int* s_cnt) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -98,6 +235,13 @@ __device__ int fznz_subcor_block(const NzTable& t, const i64* var, int nv, int x
         __syncthreads();
         return 0;
     }
+    if (nv <= FZNZ_NVMAX) {
+        extern __shared__ __align__(16) unsigned char smem[];
+        const unsigned int off = (((unsigned int)__cvta_generic_to_shared(mask + t.W) + 15u) & ~15u) - (unsigned int)__cvta_generic_to_shared(smem);
+        fznz_gram_block<THREADS>(t.data, t.ld, t.n, t.W, var, nv, rows, R, ld, mask, off);
+        return rows;
+    }
+    // larger capacity classes: one warp per variable for the moments, one warp per slot pair for the cross products
     // means and centred norms: one warp per variable, two passes (Statistics.cor: corm -> covzm)
     for (int a = warp; a < nv; a += THREADS / 32) {
         const float* x = t.data + var[a] * t.ld;

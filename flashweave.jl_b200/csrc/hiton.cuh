@@ -331,7 +331,7 @@ template <int THREADS, int TPT, bool NZ, bool GS, bool CACHE>
 #ifndef FW_HITON_MINB
 #define FW_HITON_MINB 5
 #endif
-__global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW_HITON_MINB : 8) : 1) hiton_fz_kernel(HitonArgs a) {
+__global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW_HITON_MINB : 8) : ((NZ && !GS) ? 2 : 1)) hiton_fz_kernel(HitonArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     const int cap = a.cap;

@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include "mi.cuh"
+#include "fznz_tc.cuh"
 #include "subsets.cuh"
 #include "hiton.cuh"
 
@@ -284,29 +285,66 @@ static cudaError_t pairwise_mi_run(PairwiseScratch& S, const MiTable& t, i64 hps
     return pairwise_finish(S, o_x, o_y, o_p, o_s, nf, m, p, alpha, fdr, st, out, n_launch, msg);
 }
 
-// pw_univar_neighbors for fz_nz (tests.jl:436-532): per-pair correlations on the co-non-zero rows
-static cudaError_t pairwise_fznz_run(PairwiseScratch& S, const NzTable& t, i64 n_obs_min, double alpha, bool fdr, bool reliable_only,
+// pw_univar_neighbors for fz_nz (tests.jl:436-532): per-pair correlations on the co-non-zero rows.
+// Default: tensor-core pre-filter (fznz_tc.cuh) + exact fp64 test of the candidate pairs; FWGPU_FZNZ_TC=0 (or use_tc = false)
+// runs the exact test on every pair instead - same neighbour lists, used by the tests to check the pre-filter.
+static bool fznz_use_tc() {
+    const char* e = getenv("FWGPU_FZNZ_TC");       // read on every call: the tests switch between the two paths
+    return e ? atoi(e) != 0 : true;
+}
+static cudaError_t pairwise_fznz_run(PairwiseScratch& S, fznztc::Planes& planes, const NzTable& t, i64 n_obs_min, double alpha, bool fdr, bool reliable_only,
                                      cudaStream_t st, PairwiseOut* out, int* n_launch, std::string* msg) {
     const int T = 256, WARPS = 8;
     const i64 p = t.p, n_pairs = p * (p - 1) / 2;
     out->n_tests = n_pairs;
     u64* counters; PWCK(S.get(0, sizeof(u64) * 4, (void**)&counters), "alloc");
-    i64 cap = std::max<i64>((i64)1 << 16, std::min<i64>(n_pairs, n_pairs / 8 + 1024));
     int *c_x, *c_y; double *c_p, *c_stat;
-    u64 h_cnt[2] = {0, 0};
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    u64 h_cnt[3] = {0, 0, 0};
+    if (fznz_use_tc() && t.n >= 64 && p >= 2) {
+        i64 ccap = std::max<i64>((i64)1 << 16, std::min<i64>(n_pairs, n_pairs / 16 + 1024));
+        int *k_x, *k_y;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            PWCK(S.get(16, sizeof(int) * ccap, (void**)&k_x), "alloc");
+            PWCK(S.get(17, sizeof(int) * ccap, (void**)&k_y), "alloc");
+            PWCK(cudaMemsetAsync(counters, 0, sizeof(u64) * 4, st), "memset");
+            { cudaError_t e_ = fznztc::run_prefilter(planes, t, n_obs_min, alpha, reliable_only, counters, ccap, k_x, k_y, attempt > 0, st, n_launch, msg); if (e_ != cudaSuccess) return e_; }
+            PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 3, cudaMemcpyDeviceToHost, st), "d2h");
+            PWCK(cudaStreamSynchronize(st), "sync (fznz_prefilter_kernel)");
+            if ((i64)h_cnt[0] <= ccap) break;
+            ccap = (i64)h_cnt[0];
+        }
+        const i64 n_cand = (i64)h_cnt[0];
+        const i64 cap = std::max<i64>(n_cand, 16);
         PWCK(S.get(7, sizeof(int) * cap, (void**)&c_x), "alloc");
         PWCK(S.get(8, sizeof(int) * cap, (void**)&c_y), "alloc");
         PWCK(S.get(9, sizeof(double) * cap, (void**)&c_p), "alloc");
         PWCK(S.get(10, sizeof(double) * cap, (void**)&c_stat), "alloc");
-        PWCK(cudaMemsetAsync(counters, 0, sizeof(u64) * 4, st), "memset");
-        pw_fznz_rows_kernel<WARPS><<<(unsigned)p, WARPS * 32, 0, st>>>(t, n_obs_min, alpha, reliable_only ? 1 : 0, counters, cap, c_x, c_y, c_p, c_stat);
-        (*n_launch)++;
-        PWCK(cudaGetLastError(), "pw_fznz_rows_kernel");
-        PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 2, cudaMemcpyDeviceToHost, st), "d2h");
-        PWCK(cudaStreamSynchronize(st), "sync");
-        if ((i64)h_cnt[0] <= cap) break;
-        cap = (i64)h_cnt[0];
+        if (n_cand > 0) {
+            const i64 blocks = std::min<i64>((n_cand + WARPS - 1) / WARPS, (i64)148 * 32);
+            fznztc::fznz_candidates_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, 0, st>>>(t, n_cand, k_x, k_y, n_obs_min, alpha, reliable_only ? 1 : 0,
+                                                                                       counters, cap, c_x, c_y, c_p, c_stat);
+            (*n_launch)++;
+            PWCK(cudaGetLastError(), "fznz_candidates_kernel");
+        }
+        PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 3, cudaMemcpyDeviceToHost, st), "d2h");
+        PWCK(cudaStreamSynchronize(st), "sync (fznz_candidates_kernel)");
+        h_cnt[0] = h_cnt[2];                                             // raw-significant pairs
+    } else {
+        i64 cap = std::max<i64>((i64)1 << 16, std::min<i64>(n_pairs, n_pairs / 8 + 1024));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            PWCK(S.get(7, sizeof(int) * cap, (void**)&c_x), "alloc");
+            PWCK(S.get(8, sizeof(int) * cap, (void**)&c_y), "alloc");
+            PWCK(S.get(9, sizeof(double) * cap, (void**)&c_p), "alloc");
+            PWCK(S.get(10, sizeof(double) * cap, (void**)&c_stat), "alloc");
+            PWCK(cudaMemsetAsync(counters, 0, sizeof(u64) * 4, st), "memset");
+            pw_fznz_rows_kernel<WARPS><<<(unsigned)p, WARPS * 32, 0, st>>>(t, n_obs_min, alpha, reliable_only ? 1 : 0, counters, cap, c_x, c_y, c_p, c_stat);
+            (*n_launch)++;
+            PWCK(cudaGetLastError(), "pw_fznz_rows_kernel");
+            PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 2, cudaMemcpyDeviceToHost, st), "d2h");
+            PWCK(cudaStreamSynchronize(st), "sync");
+            if ((i64)h_cnt[0] <= cap) break;
+            cap = (i64)h_cnt[0];
+        }
     }
     const i64 nf = (i64)h_cnt[0];
     out->n_raw_sig = nf;

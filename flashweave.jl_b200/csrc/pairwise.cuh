@@ -21,7 +21,7 @@ struct PairwiseOut {
 };
 
 struct PairwiseScratch {
-    void* bufs[16] = {nullptr}; size_t sizes[16] = {0};
+    void* bufs[20] = {nullptr}; size_t sizes[20] = {0};
     cudaError_t get(int i, size_t bytes, void** out) {
         if (bytes == 0) bytes = 16;
         if (sizes[i] < bytes) {
@@ -34,7 +34,7 @@ struct PairwiseScratch {
         *out = bufs[i];
         return cudaSuccess;
     }
-    ~PairwiseScratch() { for (int i = 0; i < 16; ++i) if (bufs[i]) cudaFree(bufs[i]); }
+    ~PairwiseScratch() { for (int i = 0; i < 20; ++i) if (bufs[i]) cudaFree(bufs[i]); }
 };
 
 // One CTA per row X: counts (pass 0) or writes in ascending-Y order (pass 1) the pairs with raw p < alpha.

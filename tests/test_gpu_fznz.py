@@ -132,6 +132,31 @@ def test_fznz_pairwise_subsets_hiton(fw, synth):
     assert n_same >= p - 1                      # a Float32 rounding flip may change one borderline decision
 
 
+def test_fznz_pairwise_prefilter_equals_exhaustive(fw, synth):
+    """The tensor-core pre-filter + exact candidate test must give the same neighbour lists, reliable-test count and
+    raw-significant count as the exact test on every pair (FWGPU_FZNZ_TC=0), on a heterogeneous table with meta variables."""
+    x, _ = synth.hetero(1210, 3000, B=24, seed=11)
+    x[17] = np.where(x[17] != 0, 2.5, 0.0)          # constant where present
+    x[40, 30:] = 0.0                                # present in < n_obs_min samples
+    res = {}
+    for mode in ("1", "0"):
+        os.environ["FWGPU_FZNZ_TC"] = mode
+        try:
+            eng = fw.Engine(0)
+            eng.set_data_colmajor(x, "fz_nz")
+            for alpha, nom in ((0.01, 20), (0.05, 100)):
+                got = eng.pw_univar_neighbors(alpha=alpha, n_obs_min=nom)
+                res[(mode, alpha)] = (got.offsets.copy(), got.nbr.copy(), got.stat.copy(), got.pval.copy(), dict(eng.pairwise_stats()))
+        finally:
+            os.environ.pop("FWGPU_FZNZ_TC", None)
+    for alpha in (0.01, 0.05):
+        a, b = res[("1", alpha)], res[("0", alpha)]
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+        assert (a[2] == b[2]).all() and (a[3] == b[3]).all()          # both paths take the statistic from the same exact kernel
+        assert a[4] == b[4], (a[4], b[4])
+        assert a[4]["n_raw_sig"] > 1000
+
+
 def test_fznz_golden_graphs(fw, hmp, golden_dir):
     graphs = json.load(open(os.path.join(golden_dir, "learning_expected.json")))
     x = np.ascontiguousarray(hmp["fz_nz"].T)
