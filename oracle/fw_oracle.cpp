@@ -995,6 +995,21 @@ i64 fwo_lgl(fwo_ctx* h, int max_k, double alpha, i64 hps, i64 n_obs_min, i64 max
     return (i64)edges.size();
 }
 
+// Exhaustive check of the divider-free round(x, digits=5) used by the CUDA path (csrc/fz.cuh round5f / round5d): for every
+// integer |k| <= limit, q0 = k * RN(1e-5), r = fma(-q0, 1e5, k), q = fma(r, RN(1e-5), q0) must equal the correctly rounded k / 1e5
+// (what Julia's round(x * 1e5) / 1e5 computes) in Float32 and in Float64.  Returns the number of mismatches.
+long long fwo_round5_shortcut_mismatches(long long limit) {
+    long long bad = 0;
+    const double invd = 1.0 / 100000.0; const float invf = 1.0f / 100000.0f;
+    for (long long k = -limit; k <= limit; ++k) {
+        const double y = (double)k, q0 = y * invd, r = std::fma(-q0, 100000.0, y), q = std::fma(r, invd, q0);
+        if ((k != 0 && q != y / 100000.0) || (k == 0 && q != 0.0)) ++bad;
+        const float yf = (float)k, q0f = yf * invf, rf = std::fmaf(-q0f, 100000.0f, yf), qf = std::fmaf(rf, invf, q0f);
+        if ((k != 0 && qf != yf / 100000.0f) || (k == 0 && qf != 0.0f)) ++bad;
+    }
+    return bad;
+}
+
 int fwo_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -186,3 +186,14 @@ def test_lgl_threads_deterministic(inputs):
     a = fwo.Oracle(inputs["fz"], "fz").lgl(max_k=3, mode="single", n_threads=1)
     b = fwo.Oracle(inputs["fz"], "fz").lgl(max_k=3, mode="single", n_threads=4)
     assert a["edges"] == b["edges"] and a["cond_tests"] == b["cond_tests"] == 633
+
+
+def test_round5_shortcut():
+    """csrc/fz.cuh evaluates round(x, digits=5) = rint(x * 1e5) / 1e5 without the divider (two fmas); the quotient must be the
+    correctly rounded one for every integer the CUDA path sends through it (|k| <= 4e5), in both precisions."""
+    import ctypes
+    from oracle import fwo
+    L = fwo.lib()
+    L.fwo_round5_shortcut_mismatches.restype = ctypes.c_longlong
+    L.fwo_round5_shortcut_mismatches.argtypes = [ctypes.c_longlong]
+    assert L.fwo_round5_shortcut_mismatches(400000) == 0
