@@ -38,6 +38,17 @@ if ROOT not in sys.path:
 
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,7 +165,7 @@ def main_reference(a, rank):
         "e2e": {"value": r["e2e_rate"], "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main_ours(a, rank, world, local_rank):
@@ -376,13 +387,19 @@ def main_ours(a, rank, world, local_rank):
                                           % (a.cpu_blocks, r["p_sample"], a.n, r["tests"]),
                                 "e2e_value": r["e2e_rate"], "secs": r["secs"],
                                 "note": "C++/OpenMP restatement of FlashWeave.jl (oracle/), not the Julia package; omits Julia's per-test String/Vector allocations"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
 def main():
     a = parse()
+    # stdout carries exactly ONE line (the JSON result): libraries that print to fd 1 (NCCL's version banner at communicator
+    # creation, torchrun notices) are sent to stderr for the whole run, the result line goes to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

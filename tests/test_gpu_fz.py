@@ -193,6 +193,29 @@ def test_hiton_pc_matches_oracle(fw, synth, hmp):
             assert res.tests_executed >= tot
 
 
+@pytest.mark.parametrize("B,n", [(26, 3000), (31, 3000), (40, 6000)])
+def test_hiton_pc_large_accepted_sets(fw, synth, B, n):
+    """Blocks whose members all stay significant: accepted sets of B - 1 members.  B = 26 / 31 fill the 32-slot class (tables,
+    p-value-free scan, one-pass colex enumeration, deferred p-values) up to its limit of 30; B = 40 starts there optimistically,
+    overflows at 31 accepted members and is re-run in the 64-slot class.  Everything must equal the oracle's HITON-PC."""
+    x = np.concatenate([synth.clique(2 * B, n, B=B, seed=41 + B), synth.chain(16, n, B=8, seed=43)])
+    eng, ora, _ = _engine_with_oracle_cor(fw, x)
+    p = x.shape[0]
+    uni = eng.pw_univar_neighbors(alpha=0.01, n_obs_min=20)
+    res = eng.si_HITON_PC(np.arange(p), max_k=3, alpha=0.01, n_obs_min=20)
+    biggest = 0
+    for T in list(range(0, 2 * B, 3)) + list(range(2 * B, p)):          # every third block member is enough (the oracle is serial)
+        a, b = uni.offsets[T], uni.offsets[T + 1]
+        wn, ws, wp, wt = ora.hiton_pc(T, uni.nbr[a:b], uni.stat[a:b], uni.pval[a:b], max_k=3, alpha=0.01, n_obs_min=20)
+        gn, gs, gp = res.pc(T)
+        assert list(gn) == list(wn), (T, list(gn), list(wn))
+        assert (gs == ws).all(), T
+        assert np.allclose(gp, wp, rtol=1e-12, atol=0), T
+        assert res.num_tests[T] == wt, (T, res.num_tests[T], wt)
+        biggest = max(biggest, len(wn))
+    assert biggest >= B - 2
+
+
 def test_lgl_golden_graph_maxk3(fw, hmp, golden_dir):
     """exp_fz_maxk3.edgelist: parallel="single" recovers the identical edge set."""
     graphs = json.load(open(os.path.join(golden_dir, "learning_expected.json")))

@@ -132,6 +132,24 @@ def test_fznz_pairwise_subsets_hiton(fw, synth):
     assert n_same >= p - 1                      # a Float32 rounding flip may change one borderline decision
 
 
+def test_fznz_subsets_gram_sizes(fw, synth):
+    """Jobs of 3 ... 34 variables: the register-blocked Gram takes one pass up to 27 variables, two passes for 28 ... 32, and
+    the pair-per-warp fallback beyond (64-slot class)."""
+    lat = synth.clique(48, 600, B=48, seed=61)
+    x = synth.with_zeros(lat, zero_frac=0.2, seed=62)
+    eng = fw.Engine(0)
+    eng.set_data_colmajor(x, "fz_nz")
+    ora = fwo.Oracle(x.T, "fz_nz")
+    jobs = [(0, 1, list(range(2, 2 + m))) for m in (1, 2, 5, 12, 24, 25, 26, 27, 28, 29, 30, 32, 40)]
+    gres = eng.test_subsets_batch([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs], max_k=2, alpha=0.01, n_obs_min=20)
+    stats = {"n": 0, "exact": 0}
+    for (X, Y, Z), g in zip(jobs, gres):
+        w = ora.test_subsets(X, Y, Z, max_k=2, alpha=0.01, n_obs_min=20)
+        _cmp(g[0], w[0], stats)
+        assert g[2] == w[2], (len(Z), g, w)            # num_tests
+    assert stats["exact"] >= stats["n"] - 2
+
+
 def test_fznz_pairwise_prefilter_equals_exhaustive(fw, synth):
     """The tensor-core pre-filter + exact candidate test must give the same neighbour lists, reliable-test count and
     raw-significant count as the exact test on every pair (FWGPU_FZNZ_TC=0), on a heterogeneous table with meta variables."""
