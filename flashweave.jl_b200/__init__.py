@@ -36,8 +36,14 @@ ABI_SYMBOLS = [
     "fw_set_data_f32", "fw_set_data_i32", "fw_adopt_data_f32_device", "fw_set_n_obs", "fw_levels", "fw_cor_matrix",
     "fw_set_cor_f32", "fw_adopt_cor_device", "fw_cor_device_ptr", "fw_adopt_cor_device_rows", "fw_cor_prepare", "fw_cor_rows", "fw_cor_symmetrize", "fw_upload_cor_f32", "fw_test_batch", "fw_test_subsets", "fw_test_subsets_batch",
     "fw_pairwise", "fw_pairwise_copy", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_capacity",
+    "fw_normalize_f32", "fw_get_data_f32", "fw_get_data_i32",
     "fw_build_info",
 ]
+
+# normalize_data's mode names and per-test defaults (src/preprocessing.jl:666-668, 569-573) -> enum fw_norm_mode
+NORM_MODES = {"tss": 0, "clr-adapt": 1, "clr-nonzero": 2, "pres-abs": 3, "clr-nonzero-binned": 4, "tss-nonzero-binned": 5}
+DEFAULT_NORM = {"mi": "pres-abs", "mi_nz": "clr-nonzero-binned", "fz": "clr-adapt", "fz_nz": "clr-nonzero"}
+NORM_KIND = {"tss": "fz", "clr-adapt": "fz", "clr-nonzero": "fz_nz", "pres-abs": "mi", "clr-nonzero-binned": "mi_nz", "tss-nonzero-binned": "mi_nz"}
 
 
 class FwError(RuntimeError):
@@ -105,6 +111,9 @@ def load_library():
         "fw_pairwise_stats": (i32, [vp, vp, vp, vp]),
         "fw_hiton_pc": (i32, [vp, i32, i64, vp, i32, dbl, i64, i64, i64] + [vp] * 11),
         "fw_hiton_pc_capacity": (i32, [vp, i64, vp, vp]),
+        "fw_normalize_f32": (i32, [vp, vp, i64, i64, i64, i32, i32, C.POINTER(i64), C.POINTER(i64), vp, vp]),
+        "fw_get_data_f32": (i32, [vp, vp, i64]),
+        "fw_get_data_i32": (i32, [vp, vp, i64]),
         "fw_build_info": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
@@ -235,18 +244,49 @@ class Engine:
             self._ck(self.L.fw_set_data_i32(self.h, _p(data_pn), n, p, n))
         self._keep = [data_pn]
         self.kind, self.n, self.p = kind, n, p
+        self._cor_valid = False
         return self
+
+    def normalize_data(self, data, test_name="", norm_mode="", n_bins=3, want_host=True):
+        """normalize_data(data; test_name | norm_mode) of the reference (src/preprocessing.jl:660-684) for a dense [n, p] table of
+        counts without meta variables.  The normalised table stays resident as the engine's table (ready for cor / pairwise /
+        HITON-PC with the matching test kind); returns dict(data=[n', p'] array or None, col_mask, obs_filter_mask, kind)."""
+        if bool(test_name) == bool(norm_mode):
+            raise ValueError("provide either test_name or norm_mode (but not both)")
+        mode = norm_mode or DEFAULT_NORM[test_name]
+        if mode not in NORM_MODES:
+            raise ValueError("%s is not a valid normalization mode" % mode)
+        d = np.ascontiguousarray(np.asarray(data).T, dtype=np.float32)          # [p, n] = column-major n x p Matrix{Float32}
+        p, n = d.shape
+        rmask = np.zeros(n, np.uint8); cmask = np.zeros(p, np.uint8)
+        n_out, p_out = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.fw_normalize_f32(self.h, _p(d), n, p, n, NORM_MODES[mode], n_bins, C.byref(n_out), C.byref(p_out), _p(rmask), _p(cmask)))
+        self.kind = test_name or NORM_KIND[mode]
+        self.n, self.p = n_out.value, p_out.value
+        self._cor_valid = False
+        out = None
+        if want_host and self.n > 0 and self.p > 0:
+            if NORM_MODES[mode] <= 2:
+                out = np.empty((self.p, self.n), np.float32)
+                self._ck(self.L.fw_get_data_f32(self.h, _p(out), self.n))
+            else:
+                out = np.empty((self.p, self.n), np.int32)
+                self._ck(self.L.fw_get_data_i32(self.h, _p(out), self.n))
+            out = out.T
+        return {"data": out, "col_mask": cmask.astype(bool), "obs_filter_mask": rmask.astype(bool), "kind": self.kind}
 
     def set_data_ptr(self, host_ptr, n, p, kind="fz"):
         """host pointer (e.g. a pinned torch tensor's data_ptr) to a column-major n x p float32 table"""
         assert KINDS[kind] >= 2
         self._ck(self.L.fw_set_data_f32(self.h, C.c_void_p(host_ptr), n, p, n))
         self.kind, self.n, self.p = kind, n, p
+        self._cor_valid = False
         return self
 
     def adopt_data_device(self, dev_ptr, n, p, kind="fz"):
         self._ck(self.L.fw_adopt_data_f32_device(self.h, C.c_void_p(dev_ptr), n, p, n))
         self.kind, self.n, self.p = kind, n, p
+        self._cor_valid = False
         return self
 
     def levels(self):
@@ -270,6 +310,7 @@ class Engine:
         out = np.empty((p, p), np.float32) if want_host else None
         self._ck(self.L.fw_upload_cor_f32(self.h, C.c_void_p(ptr), n, p, n, _p(out)))
         self.kind, self.n, self.p = "fz", n, p
+        self._cor_valid = True
         return out
 
     def set_n_obs(self, n):
@@ -281,6 +322,7 @@ class Engine:
         """cor_mat = Float32.(cor(data)) (learning.jl:42-44), computed and kept on the device."""
         out = np.empty((self.p, self.p), np.float32) if want_host else None
         self._ck(self.L.fw_cor_matrix(self.h, _p(out)))
+        self._cor_valid = True
         return out
 
     def set_cor(self, cor, n_obs=None, kind="fz"):
@@ -288,6 +330,7 @@ class Engine:
         assert c.ndim == 2 and c.shape[0] == c.shape[1]
         self._ck(self.L.fw_set_cor_f32(self.h, _p(c), c.shape[0]))
         self.p = c.shape[0]
+        self._cor_valid = True
         if self.kind is None:
             self.kind = kind
         if n_obs is not None:
@@ -298,6 +341,7 @@ class Engine:
     def adopt_cor_device(self, dev_ptr, p):
         self._ck(self.L.fw_adopt_cor_device(self.h, C.c_void_p(dev_ptr), p))
         self.p = p
+        self._cor_valid = True
 
     def cor_device_ptr(self):
         return self.L.fw_cor_device_ptr(self.h)
@@ -306,6 +350,7 @@ class Engine:
     def adopt_cor_device_rows(self, dev_ptr, p, rows_allocated):
         self._ck(self.L.fw_adopt_cor_device_rows(self.h, C.c_void_p(dev_ptr), p, rows_allocated))
         self.p = p
+        self._cor_valid = True
 
     def cor_prepare(self):
         nb = C.c_int32(0)
@@ -431,8 +476,8 @@ class Engine:
         if n_obs_min < 0:
             ml = int(self.levels()[0].max()) if kind in ("mi", "mi_nz") else None
             n_obs_min = auto_n_obs_min(kind, max_k, hps, max_level=ml)
-        if kind == "fz" and not self.L.fw_cor_device_ptr(self.h):
-            self.cor(want_host=False)
+        if kind == "fz" and not (getattr(self, "_cor_valid", False) and self.L.fw_cor_device_ptr(self.h)):
+            self.cor(want_host=False)                      # no cor_mat yet, or it belongs to a previous table
         uni = self.pw_univar_neighbors(alpha=alpha, hps=hps, n_obs_min=n_obs_min, FDR=FDR, kind=kind)
         tg = target_order(uni) if targets is None else _i64(targets)
         res = self.si_HITON_PC(tg, max_k=max_k, alpha=alpha, hps=hps, n_obs_min=n_obs_min, max_tests=max_tests, kind=kind, want_tpc=False)

@@ -20,6 +20,7 @@
 #include "cor_tc.cuh"
 #include "mi.cuh"
 #include "hiton_mi.cuh"
+#include "prep.cuh"
 
 static_assert(sizeof(fw_test_result) == 32, "TestResult layout (src/types.jl:140-145)");
 static_assert(sizeof(DevResult) == 32, "DevResult layout");
@@ -290,14 +291,9 @@ int32_t fw_adopt_data_f32_device(fw_ctx* ctx, const float* dev, int64_t n, int64
     ctx->n = n; ctx->p = p; ctx->ld = ld; ctx->data_kind = 0; ctx->n_obs = n; ctx->nz_ready = false;
     return FW_OK;
 }
-int32_t fw_set_data_i32(fw_ctx* ctx, const int32_t* host, int64_t n, int64_t p, int64_t ld) {
-    if (!ctx) return FW_ERR_INVALID;
-    NEED(host && n > 0 && p > 0 && ld >= n, FW_ERR_INVALID, "fw_set_data_i32: bad arguments");
-    CK(cudaSetDevice(ctx->device));
-    CK(ctx->d_data_i32.reserve((size_t)n * p));
-    CK(cudaMemcpy2DAsync(ctx->d_data_i32.ptr, n * sizeof(int), host, ld * sizeof(int), n * sizeof(int), p, cudaMemcpyHostToDevice, ctx->stream));
-    NEED(n < ((i64)1 << 31) - 64, FW_ERR_UNSUPPORTED, "fw_set_data_i32: more than 2^31 rows");
-    // get_levels / get_max_vals (src/misc.jl:64-97), then the bit-plane table
+// get_levels / get_max_vals (src/misc.jl:64-97) and the bit-plane table of the level codes resident in ctx->d_data_i32 ([p][n])
+static int install_discrete_table(fw_ctx* ctx, int64_t n, int64_t p, const char* who) {
+    NEED(n < ((i64)1 << 31) - 64, FW_ERR_UNSUPPORTED, "%s: more than 2^31 rows", who);
     CK(ctx->d_levels.reserve(p)); CK(ctx->d_maxvals.reserve(p)); CK(ctx->d_nnz.reserve(p)); CK(ctx->d_bad.reserve(4));
     CK(cudaMemsetAsync(ctx->d_bad.ptr, 0, sizeof(int), ctx->stream));
     {
@@ -313,9 +309,9 @@ int32_t fw_set_data_i32(fw_ctx* ctx, const int32_t* host, int64_t n, int64_t p, 
     CK(cudaMemcpyAsync(&bad, ctx->d_bad.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->data_kind = -1;
-    NEED(!(bad & 1), FW_ERR_INVALID, "fw_set_data_i32: negative level codes");
+    NEED(!(bad & 1), FW_ERR_INVALID, "%s: negative level codes", who);
     int mx = 0; for (i64 v = 0; v < p; ++v) mx = std::max(mx, ctx->h_maxvals[v]);
-    NEED(mx + 1 <= FW_MAX_L, FW_ERR_UNSUPPORTED, "fw_set_data_i32: %d levels; the bit-plane engine supports at most %d (maximum(max_vals)+1)", mx + 1, FW_MAX_L);
+    NEED(mx + 1 <= FW_MAX_L, FW_ERR_UNSUPPORTED, "%s: %d levels; the bit-plane engine supports at most %d (maximum(max_vals)+1)", who, mx + 1, FW_MAX_L);
     ctx->disc_L = std::max(mx + 1, 2); ctx->disc_W = (int)((n + 31) / 32);
     CK(ctx->d_planes.reserve((size_t)p * (ctx->disc_L - 1) * ctx->disc_W));
     {
@@ -327,6 +323,14 @@ int32_t fw_set_data_i32(fw_ctx* ctx, const int32_t* host, int64_t n, int64_t p, 
     ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 1; ctx->n_obs = n;
     return FW_OK;
 }
+int32_t fw_set_data_i32(fw_ctx* ctx, const int32_t* host, int64_t n, int64_t p, int64_t ld) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(host && n > 0 && p > 0 && ld >= n, FW_ERR_INVALID, "fw_set_data_i32: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_data_i32.reserve((size_t)n * p));
+    CK(cudaMemcpy2DAsync(ctx->d_data_i32.ptr, n * sizeof(int), host, ld * sizeof(int), n * sizeof(int), p, cudaMemcpyHostToDevice, ctx->stream));
+    return install_discrete_table(ctx, n, p, "fw_set_data_i32");
+}
 int32_t fw_set_n_obs(fw_ctx* ctx, int64_t n) { if (!ctx) return FW_ERR_INVALID; NEED(n >= 0, FW_ERR_INVALID, "n_obs < 0"); ctx->n_obs = n; return FW_OK; }
 
 int32_t fw_levels(fw_ctx* ctx, int32_t* levels, int32_t* max_vals) {
@@ -334,6 +338,172 @@ int32_t fw_levels(fw_ctx* ctx, int32_t* levels, int32_t* max_vals) {
     NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_levels: no discrete table resident (call fw_set_data_i32 first)");
     if (levels) memcpy(levels, ctx->h_levels.data(), sizeof(int) * ctx->p);
     if (max_vals) memcpy(max_vals, ctx->h_maxvals.data(), sizeof(int) * ctx->p);
+    return FW_OK;
+}
+
+// ---- normalisation (the step in front of the hot path; prep.cuh) -----------------------------------------------------
+int32_t fw_normalize_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, int64_t ld, int32_t norm, int32_t n_bins,
+                         int64_t* n_out, int64_t* p_out, uint8_t* row_mask, uint8_t* col_mask) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(host && n > 0 && p > 0 && ld >= n, FW_ERR_INVALID, "fw_normalize_f32: bad arguments (n=%lld p=%lld ld=%lld)", (long long)n, (long long)p, (long long)ld);
+    NEED(norm >= PREP_ROWS && norm <= PREP_BINNED_NZ_ROWS, FW_ERR_INVALID, "fw_normalize_f32: unknown normalisation mode %d", norm);
+    const bool binned = norm == PREP_BINNED_NZ_CLR || norm == PREP_BINNED_NZ_ROWS;
+    NEED(!binned || (n_bins >= 2 && n_bins <= FW_MAX_L), FW_ERR_UNSUPPORTED, "fw_normalize_f32: n_bins = %d not in 2..%d", n_bins, FW_MAX_L);
+    NEED(n < ((i64)1 << 31) - 64 && p < ((i64)1 << 31) - 64 && n <= (i64)65535 * 256, FW_ERR_UNSUPPORTED, "fw_normalize_f32: table too large");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int T = 256;
+    DevBuf<float> raw; DevBuf<unsigned char> dflag;
+    CK(raw.reserve((size_t)n * p)); CK(dflag.reserve(p));
+    CK(cudaMemcpy2DAsync(raw.ptr, n * sizeof(float), host, ld * sizeof(float), n * sizeof(float), p, cudaMemcpyHostToDevice, st));
+    // filter_by_variance (preprocessing.jl:367-409): variables first, then samples on the kept variables
+    prep_col_distinct_kernel<<<(unsigned)p, T, 0, st>>>(raw.ptr, n, n, dflag.ptr); ctx->launches++;
+    CK(cudaGetLastError());
+    std::vector<unsigned char> cflag(p);
+    CK(cudaMemcpyAsync(cflag.data(), dflag.ptr, p, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<int> cols; for (i64 v = 0; v < p; ++v) if (cflag[v] && n > 1) cols.push_back((int)v);
+    i64 p1 = (i64)cols.size();
+    std::vector<unsigned char> rflag(n, 0);
+    std::vector<int> rows;
+    DevBuf<int> dcols, drows, dnz0; DevBuf<float> dsum32; DevBuf<double> dsum64, dslog, dg, dpc;
+    std::vector<float> hsum32(n); std::vector<double> hsum64(n), hslog(n), hg(n, 1.0), hpc(n, 0.0); std::vector<int> hnz0(n);
+    if (p1 > 0) {
+        CK(dcols.reserve(p1)); CK(dnz0.reserve(n)); CK(dsum32.reserve(n)); CK(dsum64.reserve(n)); CK(dslog.reserve(n));
+        CK(cudaMemcpyAsync(dcols.ptr, cols.data(), sizeof(int) * p1, cudaMemcpyHostToDevice, st));
+        prep_row_stats_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(raw.ptr, n, n, dcols.ptr, p1, dsum32.ptr, dsum64.ptr, dnz0.ptr, dslog.ptr); ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(hsum32.data(), dsum32.ptr, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hsum64.data(), dsum64.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hslog.data(), dslog.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hnz0.data(), dnz0.ptr, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (i64 r = 0; r < n; ++r) if (hsum32[r] > 0.0f) { rflag[r] = 1; rows.push_back((int)r); }
+    }
+    // per-sample parameters on the host (O(n); fp64 exp/log as the reference evaluates them)
+    if (!rows.empty() && (norm == PREP_CLR_NZ || norm == PREP_BINNED_NZ_CLR)) {
+        for (int r : rows) hg[r] = std::exp(hslog[r] / (double)(p1 - hnz0[r]));                       // geomean of the non-zero entries
+    } else if (!rows.empty() && norm == PREP_CLR_ADAPT) {
+        // adaptive_pseudocount! (preprocessing.jl:157-175): deepest sample, smallest abundance, per-sample pseudo-counts
+        int md = rows[0]; for (int r : rows) if (hsum64[r] > hsum64[md]) md = r;                     // findmax: first maximum
+        CK(drows.reserve(rows.size()));
+        CK(cudaMemcpyAsync(drows.ptr, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice, st));
+        unsigned int hbits = 0x7f800000u;
+        CK(cudaMemcpyAsync(ctx->d_counter.ptr, &hbits, sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+        prep_min_nonzero_kernel<<<(unsigned)p1, T, 0, st>>>(raw.ptr, n, dcols.ptr, p1, drows.ptr, (i64)rows.size(), reinterpret_cast<unsigned int*>(ctx->d_counter.ptr)); ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&hbits, ctx->d_counter.ptr, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        float min_ab; memcpy(&min_ab, &hbits, sizeof(float));
+        const double base = min_ab >= 1.0f ? 1.0 : (double)min_ab / 10.0;
+        const double k = (double)hnz0[md], nprod1 = hslog[md], pv = (double)p1;
+        std::vector<int> kept;
+        for (int r : rows) {
+            const double nz0 = (double)hnz0[r];
+            const double pcv = std::exp((1.0 / (nz0 - pv)) * ((k - pv) * std::log(base) + nprod1 - hslog[r]));
+            if (pcv != 0.0) { hpc[r] = pcv; hg[r] = std::exp((hslog[r] + nz0 * std::log(pcv)) / pv); kept.push_back(r); }
+            else rflag[r] = 0;                                                                       // pseudo-count below machine precision: sample removed
+        }
+        rows.swap(kept);
+    }
+    const i64 n1 = (i64)rows.size();
+    std::vector<unsigned char> cmask(p, 0);
+    for (int v : cols) cmask[v] = 1;
+    i64 p2 = p1;
+    if (n1 == 0 || p1 == 0) {
+        ctx->data_kind = -1; ctx->n = 0; ctx->p = 0;
+        if (n_out) *n_out = 0; if (p_out) *p_out = 0;
+        if (row_mask) memcpy(row_mask, rflag.data(), n);
+        if (col_mask) memset(col_mask, 0, p);
+        return FW_OK;
+    }
+    CK(drows.reserve(n1));
+    CK(cudaMemcpyAsync(drows.ptr, rows.data(), sizeof(int) * n1, cudaMemcpyHostToDevice, st));
+    CK(dg.reserve(n)); CK(dpc.reserve(n));
+    CK(cudaMemcpyAsync(dg.ptr, hg.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dpc.ptr, hpc.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    const dim3 grid((unsigned)p1, (unsigned)((n1 + T - 1) / T));
+    if (norm == PREP_ROWS || norm == PREP_CLR_NZ || norm == PREP_CLR_ADAPT) {
+        CK(ctx->d_data_f32.reserve((size_t)n1 * p1));
+        prep_transform_kernel<<<grid, T, 0, st>>>(raw.ptr, n, dcols.ptr, drows.ptr, n1, norm, dsum32.ptr, dg.ptr, dpc.ptr, ctx->d_data_f32.ptr); ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+        ctx->n = n1; ctx->p = p1; ctx->ld = n1; ctx->data_kind = 0; ctx->n_obs = n1; ctx->nz_ready = false; ctx->tcp.valid = false;
+    } else {
+        DevBuf<int> tmp; DevBuf<unsigned int> dseen;
+        CK(tmp.reserve((size_t)n1 * p1)); CK(dseen.reserve(p1));
+        if (norm == PREP_BINARY) {
+            prep_binary_kernel<<<grid, T, 0, st>>>(raw.ptr, n, dcols.ptr, drows.ptr, n1, tmp.ptr); ctx->launches++;
+        } else {
+            NEED((i64)n1 * p1 < ((i64)1 << 31), FW_ERR_UNSUPPORTED, "fw_normalize_f32: more than 2^31 entries in a binned table");
+            DevBuf<double> vals, sorted; DevBuf<int> dnnz, doffs;
+            CK(vals.reserve((size_t)n1 * p1)); CK(sorted.reserve((size_t)n1 * p1)); CK(dnnz.reserve(p1)); CK(doffs.reserve(p1 + 1));
+            CK(cudaMemsetAsync(dnnz.ptr, 0, sizeof(int) * p1, st));
+            prep_rank_values_kernel<<<grid, T, 0, st>>>(raw.ptr, n, dcols.ptr, drows.ptr, n1, norm, dsum32.ptr, dg.ptr, vals.ptr, dnnz.ptr); ctx->launches++;
+            CK(cudaGetLastError());
+            std::vector<int> offs(p1 + 1); for (i64 j = 0; j <= p1; ++j) offs[j] = (int)(j * n1);
+            CK(cudaMemcpyAsync(doffs.ptr, offs.data(), sizeof(int) * (p1 + 1), cudaMemcpyHostToDevice, st));
+            size_t need = 0;
+            CK(cub::DeviceSegmentedSort::SortKeys(nullptr, need, vals.ptr, sorted.ptr, (int)(n1 * p1), (int)p1, doffs.ptr, doffs.ptr + 1, st));
+            DevBuf<unsigned char> tmpsort; CK(tmpsort.reserve(need));
+            CK(cub::DeviceSegmentedSort::SortKeys(tmpsort.ptr, need, vals.ptr, sorted.ptr, (int)(n1 * p1), (int)p1, doffs.ptr, doffs.ptr + 1, st)); ctx->launches += 3;
+            prep_bin_kernel<<<grid, T, 0, st>>>(vals.ptr, sorted.ptr, dnnz.ptr, n1, n_bins, tmp.ptr); ctx->launches++;
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(st));                       // the sort scratch is released at scope exit
+        }
+        CK(cudaGetLastError());
+        // level filter: exactly 2 levels (binary, preprocessing.jl:479-481) / exactly n_bins - 1 distinct non-zero levels (:511-513)
+        CK(cudaMemsetAsync(dseen.ptr, 0, sizeof(unsigned int) * p1, st));
+        prep_col_levels_kernel<<<(unsigned)p1, T, 0, st>>>(tmp.ptr, n1, dseen.ptr); ctx->launches++;
+        CK(cudaGetLastError());
+        std::vector<unsigned int> seen(p1);
+        CK(cudaMemcpyAsync(seen.data(), dseen.ptr, sizeof(unsigned int) * p1, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        std::vector<int> colmap;
+        for (i64 j = 0; j < p1; ++j) {
+            const int lv_all = __builtin_popcount(seen[j]), lv_nz = __builtin_popcount(seen[j] & ~1u);
+            const bool keep = norm == PREP_BINARY ? lv_all == 2 : lv_nz == n_bins - 1;
+            if (keep) colmap.push_back((int)j); else cmask[cols[j]] = 0;
+        }
+        p2 = (i64)colmap.size();
+        if (p2 == 0) {
+            ctx->data_kind = -1; ctx->n = 0; ctx->p = 0;
+            if (n_out) *n_out = n1; if (p_out) *p_out = 0;
+            if (row_mask) memcpy(row_mask, rflag.data(), n);
+            if (col_mask) memset(col_mask, 0, p);
+            return FW_OK;
+        }
+        DevBuf<int> dmap; CK(dmap.reserve(p2));
+        CK(cudaMemcpyAsync(dmap.ptr, colmap.data(), sizeof(int) * p2, cudaMemcpyHostToDevice, st));
+        CK(ctx->d_data_i32.reserve((size_t)n1 * p2));
+        prep_gather_cols_kernel<<<dim3((unsigned)p2, (unsigned)((n1 + T - 1) / T)), T, 0, st>>>(tmp.ptr, dmap.ptr, n1, ctx->d_data_i32.ptr); ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+        int st_ = install_discrete_table(ctx, n1, p2, "fw_normalize_f32");
+        if (st_ != FW_OK) return st_;
+    }
+    if (n_out) *n_out = n1; if (p_out) *p_out = p2;
+    if (row_mask) memcpy(row_mask, rflag.data(), n);
+    if (col_mask) memcpy(col_mask, cmask.data(), p);
+    return FW_OK;
+}
+
+int32_t fw_get_data_f32(fw_ctx* ctx, float* host_out, int64_t ld) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(ctx->data_kind == 0 && ctx->d_data_f32.ptr, FW_ERR_STATE, "fw_get_data_f32: no continuous table resident");
+    NEED(host_out && ld >= ctx->n, FW_ERR_INVALID, "fw_get_data_f32: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy2DAsync(host_out, ld * sizeof(float), ctx->d_data_f32.ptr, ctx->ld * sizeof(float), ctx->n * sizeof(float), ctx->p, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FW_OK;
+}
+int32_t fw_get_data_i32(fw_ctx* ctx, int32_t* host_out, int64_t ld) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(ctx->data_kind == 1 && ctx->d_data_i32.ptr, FW_ERR_STATE, "fw_get_data_i32: no discrete table resident");
+    NEED(host_out && ld >= ctx->n, FW_ERR_INVALID, "fw_get_data_i32: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy2DAsync(host_out, ld * sizeof(int), ctx->d_data_i32.ptr, ctx->n * sizeof(int), ctx->n * sizeof(int), ctx->p, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return FW_OK;
 }
 

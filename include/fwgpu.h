@@ -79,6 +79,28 @@ int32_t fw_adopt_data_f32_device(fw_ctx* ctx, const float* dev, int64_t n, int64
  * (size(data,1) in src/tests.jl:150,256) */
 int32_t fw_set_n_obs(fw_ctx* ctx, int64_t n);
 
+/* ---- normalisation: the step in front of the hot path --------------------------------------
+ * normalize_data / preprocess_data for dense tables without meta variables (src/preprocessing.jl:412-563, 660-684):
+ * filter_by_variance (:367-409; variables with a single value, then samples without reads), the normalisation proper, the
+ * level filters of the discrete modes, conversion to the target precision (Float32 / Int32).  `host` is the column-major n x p
+ * table as Float32 (check_convert_sparse, :579-594).  The result becomes the context's resident table exactly as if it had been
+ * passed to fw_set_data_f32 (FW_NORM_ROWS, _CLR_ADAPT, _CLR_NZ) or fw_set_data_i32 (the others); fw_get_data_* copies it out.
+ * row_mask[n] / col_mask[p] (may be NULL) receive the obs_filter_mask and the kept-variable mask; *n_out x *p_out is the new shape
+ * (0 variables or samples left: FW_OK, no table resident). */
+enum fw_norm_mode {
+    FW_NORM_ROWS = 0,             /* "tss"                 rownorm!                                   :348        */
+    FW_NORM_CLR_ADAPT = 1,        /* "clr-adapt"   (fz)    adaptive_clr!                              :133-215    */
+    FW_NORM_CLR_NZ = 2,           /* "clr-nonzero" (fz_nz) clr!(ignore_zeros = true)                  :192-207    */
+    FW_NORM_BINARY = 3,           /* "pres-abs"    (mi)    presabs_norm! + exactly-2-levels filter    :364, :475  */
+    FW_NORM_BINNED_NZ_CLR = 4,    /* "clr-nonzero-binned" (mi_nz)  clr_nz + discretize_nz (tied ranks) :217-292   */
+    FW_NORM_BINNED_NZ_ROWS = 5    /* "tss-nonzero-binned"          rownorm! + discretize_nz                       */
+};
+int32_t fw_normalize_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, int64_t ld, int32_t norm_mode, int32_t n_bins,
+                         int64_t* n_out, int64_t* p_out, uint8_t* row_mask, uint8_t* col_mask);
+/* copy the resident table to the host (column-major, leading dimension ld >= n) */
+int32_t fw_get_data_f32(fw_ctx* ctx, float* host_out, int64_t ld);
+int32_t fw_get_data_i32(fw_ctx* ctx, int32_t* host_out, int64_t ld);
+
 /* ---- precompute (src/learning.jl:33-47 prepare_lgl) ------------------------------------ */
 /* get_levels / get_max_vals, src/misc.jl:64-97 */
 int32_t fw_levels(fw_ctx* ctx, int32_t* levels, int32_t* max_vals);

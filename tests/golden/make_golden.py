@@ -9,8 +9,11 @@ Sources (all data, no code), relative to /root/reference/test/data:
   learning_expected/*.edgelist  -> 8 expected graphs (test/learning.jl:176-237)
 
 Run once in the build container:  python tests/golden/make_golden.py
+  HMP_SRA_gut/HMP_SRA_gut_small.tsv + preprocessing_expected/*.tsv
+      -> raw counts and the six expected normalisations (test/preprocessing.jl:48-84) for the normalisation step
+
 Outputs: tests/golden/hmp_inputs.npz, tests/golden/tests_expected.json,
-         tests/golden/learning_expected.json
+         tests/golden/learning_expected.json, tests/golden/prep_fixtures.npz
 """
 import json
 import os
@@ -35,6 +38,16 @@ def main():
     for k, v in inputs.items():
         assert v.shape == (346, 50), (k, v.shape)
     np.savez_compressed(os.path.join(OUT, "hmp_inputs.npz"), **inputs)
+
+    raw = [l.rstrip("\n").split("\t") for l in open(os.path.join(D, "HMP_SRA_gut", "HMP_SRA_gut_small.tsv"))]
+    counts = np.array([[float(v) for v in r[1:]] for r in raw[1:]])
+    assert counts.shape == (351, 50) and (counts == np.round(counts)).all()
+    prep = {"counts": counts.astype(np.int32)}
+    for mode, fn in [("clr-adapt", "clr_adapt"), ("clr-nonzero", "clr_nonzero"), ("clr-nonzero-binned", "clr_nonzero_binned"),
+                     ("pres-abs", "pres_abs"), ("tss", "tss"), ("tss-nonzero-binned", "tss_nonzero_binned")]:
+        e = np.loadtxt(os.path.join(pe, fn + ".tsv"), delimiter="\t")
+        prep[mode] = e.astype(np.int8) if ("binned" in mode or mode == "pres-abs") else e.astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "prep_fixtures.npz"), **prep)
 
     exp = {}
     with open(os.path.join(D, "tests_expected.tsv")) as f:
