@@ -51,3 +51,25 @@ if "C5m" in which:
 if "C5" in which:
     x, _ = synth.hetero(50010, 10000, B=24, seed=synth.BASE_SEED + 4)
     run("C5 hetero+meta 50010x10000 fz_nz max_k=3", x, "fz_nz", 3, reps=1)
+if "PREP" in which:
+    # normalisation throughput at the C4 shape: synthetic counts (Poisson around a log-normal depth), all six modes
+    rng = np.random.default_rng(7)
+    p_, n_ = 50000, 10000
+    counts = np.empty((p_, n_), np.float32)
+    for b in range(0, p_, 5000):
+        lam = rng.gamma(0.3, 30.0, size=(5000, 1)).astype(np.float32) * rng.lognormal(0.0, 0.5, size=(1, n_)).astype(np.float32)
+        counts[b:b + 5000] = rng.poisson(lam * (rng.random((5000, n_)) > 0.5)).astype(np.float32)
+    eng = fw.Engine(0)
+    rmask = np.zeros(n_, np.uint8); cmask = np.zeros(p_, np.uint8)
+    import ctypes as C
+    for mode in ("tss", "clr-nonzero", "clr-adapt", "pres-abs", "clr-nonzero-binned"):
+        best = None
+        for rep in range(2):
+            n_out, p_out = C.c_int64(0), C.c_int64(0)
+            t0 = time.perf_counter()
+            eng._ck(eng.L.fw_normalize_f32(eng.h, counts.ctypes.data_as(C.c_void_p), n_, p_, n_, fw.NORM_MODES[mode], 3, C.byref(n_out), C.byref(p_out),
+                                           rmask.ctypes.data_as(C.c_void_p), cmask.ctypes.data_as(C.c_void_p)))
+            eng.synchronize(); dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        print(json.dumps({"config": "normalisation %s, %d x %d counts from pageable host memory" % (mode, p_, n_), "ms": best * 1e3,
+                          "n_out": n_out.value, "p_out": p_out.value, "input_GBps": p_ * n_ * 4 / best / 1e9}), flush=True)
