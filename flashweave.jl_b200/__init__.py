@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "fw_set_data_f32", "fw_set_data_i32", "fw_adopt_data_f32_device", "fw_set_n_obs", "fw_levels", "fw_cor_matrix",
     "fw_set_cor_f32", "fw_adopt_cor_device", "fw_cor_device_ptr", "fw_adopt_cor_device_rows", "fw_cor_prepare", "fw_cor_rows", "fw_cor_symmetrize", "fw_upload_cor_f32", "fw_test_batch", "fw_test_subsets", "fw_test_subsets_batch",
     "fw_pairwise", "fw_pairwise_copy", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_capacity",
-    "fw_normalize_f32", "fw_get_data_f32", "fw_get_data_i32",
+    "fw_normalize_f32", "fw_get_data_f32", "fw_get_data_i32", "fw_set_data_csc_f32", "fw_set_data_csc_i32",
     "fw_build_info",
 ]
 
@@ -112,6 +112,8 @@ def load_library():
         "fw_hiton_pc": (i32, [vp, i32, i64, vp, i32, dbl, i64, i64, i64] + [vp] * 11),
         "fw_hiton_pc_capacity": (i32, [vp, i64, vp, vp]),
         "fw_normalize_f32": (i32, [vp, vp, i64, i64, i64, i32, i32, C.POINTER(i64), C.POINTER(i64), vp, vp]),
+        "fw_set_data_csc_f32": (i32, [vp, vp, vp, vp, i64, i64]),
+        "fw_set_data_csc_i32": (i32, [vp, vp, vp, vp, i64, i64]),
         "fw_get_data_f32": (i32, [vp, vp, i64]),
         "fw_get_data_i32": (i32, [vp, vp, i64]),
         "fw_build_info": (C.c_char_p, []),
@@ -274,6 +276,27 @@ class Engine:
                 self._ck(self.L.fw_get_data_i32(self.h, _p(out), self.n))
             out = out.T
         return {"data": out, "col_mask": cmask.astype(bool), "obs_filter_mask": rmask.astype(bool), "kind": self.kind}
+
+    def set_data_csc(self, colptr, rowval, nzval, n, p, kind):
+        """SparseMatrixCSC{T,Int64} triple (0-based here; the Julia glue sets index base 1) of an n x p table."""
+        cp, rv = _i64(colptr), _i64(rowval)
+        if KINDS[kind] >= 2:
+            nz = np.ascontiguousarray(nzval, dtype=np.float32)
+            self._ck(self.L.fw_set_data_csc_f32(self.h, _p(cp), _p(rv), _p(nz), n, p))
+        else:
+            nz = np.ascontiguousarray(nzval, dtype=np.int32)
+            self._ck(self.L.fw_set_data_csc_i32(self.h, _p(cp), _p(rv), _p(nz), n, p))
+        self.kind, self.n, self.p = kind, n, p
+        self._cor_valid = False
+        return self
+
+    def get_data(self):
+        """the resident table as an [n, p] array"""
+        if KINDS[self.kind] >= 2:
+            out = np.empty((self.p, self.n), np.float32); self._ck(self.L.fw_get_data_f32(self.h, _p(out), self.n))
+        else:
+            out = np.empty((self.p, self.n), np.int32); self._ck(self.L.fw_get_data_i32(self.h, _p(out), self.n))
+        return out.T
 
     def set_data_ptr(self, host_ptr, n, p, kind="fz"):
         """host pointer (e.g. a pinned torch tensor's data_ptr) to a column-major n x p float32 table"""

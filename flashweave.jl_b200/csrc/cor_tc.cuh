@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(THREADS) standardize_split_kernel(const float*
 //   * the cross terms hi*lo + lo*hi (2^-8 smaller) go to their own accumulator, read once at the end.
 // Residual bias at n = 10^4, |r| -> 1: ~2e-6 (was 5.6e-5).
 constexpr int CHUNK = 16;                                  // k-blocks per drained partial sum (1024 samples)
+constexpr int COR_GROUP = 8;                               // tile rows per rasterisation group of the cluster kernel
 constexpr int NTHREADS = 192;                              // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
 constexpr int TMEM_ALLOC = 512;                            // main[0] @0, main[1] @128, cross @256
 
@@ -327,7 +328,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 cor_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-               float* __restrict__ C, i64 p, int num_kb, int nb, int bi0, int mirror, int bjlo, int bjhi) {
+               float* __restrict__ C, i64 p, int num_kb, int nb, int bi0, int bi1, int mirror, int bjlo, int bjhi) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -339,16 +340,31 @@ cor_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     uint32_t crank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
 
-    // cluster q -> (tile row bi, column pair): row bi (from bi0) covers tile columns [max(bi, bjlo), bjhi) in pairs
-    // (row-range mode: bjlo = 0, bjhi = nb; column-band mode of the upload-overlapped path: bi0 = 0, rows up to bjhi)
+    // Tile order (L2 rasterisation).  The standardised table (2 GB at C4) is far larger than L2, and every tile streams its 128
+    // A rows and 128 B rows over the whole K range; CTAs that run at the same time advance through K roughly in lock step, so an
+    // operand row block is fetched from DRAM once per GROUP of co-resident tiles that share it.  Tile rows are therefore taken in
+    // groups of COR_GROUP; inside a group the column pairs are the outer loop and the rows the inner one: the ~74 clusters of a
+    // wave cover COR_GROUP rows x ~9 column pairs (COR_GROUP + 18 row blocks of operands instead of 1 + 148 in row-major order).
+    // cluster q -> (bi, column pair); a pair covers columns (bj, bj + 1) of the rectangle rows [r0, r0 + rows) x columns
+    // [max(r0, bjlo), bjhi); CTAs whose tile lies below the diagonal or beyond bjhi still feed their half of A to the peer,
+    // compute a redundant tile and write nothing (row-range mode: bjlo = 0, bjhi = nb; column-band mode of the
+    // upload-overlapped path: bi0 = 0, bi1 = bjhi).
     int bi = bi0, bj;
-    bool live = true;                                   // the odd CTA of a row's last pair may have no tile of its own
+    bool live = true;
     {
         long long q = blockIdx.x >> 1;
-        for (;; ++bi) { const int lo = bi > bjlo ? bi : bjlo; const long long pr = (bjhi - lo + 1) >> 1; if (q < pr) break; q -= pr; }
-        const int lo = bi > bjlo ? bi : bjlo;
-        bj = lo + 2 * (int)q + (int)crank;
-        if (bj >= bjhi) { bj = bjhi - 1; live = false; }    // still feeds its half of A to the peer; computes a redundant tile, writes nothing
+        int r0 = bi0, rows = 1, lo = 0;
+        for (;; r0 += COR_GROUP) {
+            rows = bi1 - r0 < COR_GROUP ? bi1 - r0 : COR_GROUP;
+            lo = r0 > bjlo ? r0 : bjlo;
+            const long long cnt = (long long)((bjhi - lo + 1) >> 1) * rows;
+            if (q < cnt || r0 + COR_GROUP >= bi1) break;
+            q -= cnt;
+        }
+        bi = r0 + (int)(q % rows);
+        bj = lo + 2 * (int)(q / rows) + (int)crank;
+        if (bj >= bjhi) { bj = bjhi - 1; live = false; }
+        if (bj < bi) live = false;
     }
     const int n_chunks = (num_kb + CHUNK - 1) / CHUNK;
 
@@ -493,15 +509,24 @@ static bool use_cluster_kernel() {
     static const int v = [] { const char* e = getenv("FWGPU_COR_CLUSTER"); return e ? atoi(e) : 1; }();
     return v != 0;
 }
+// clusters of cor_tc2_kernel for tile rows [bi0, bi1) x columns [bjlo, bjhi): see the tile-order comment in the kernel
+static long long grouped_clusters(int bi0, int bi1, int bjlo, int bjhi) {
+    long long c = 0;
+    for (int r0 = bi0; r0 < bi1; r0 += COR_GROUP) {
+        const int rows = bi1 - r0 < COR_GROUP ? bi1 - r0 : COR_GROUP;
+        const int lo = r0 > bjlo ? r0 : bjlo;
+        c += (long long)((bjhi - lo + 1) >> 1) * rows;
+    }
+    return c;
+}
 static cudaError_t run_rows(const Prepared& P, float* d_cor, i64 p, int bi0, int bi1, bool mirror, cudaStream_t st, int* n_launch, std::string* msg) {
     if (bi1 > P.nb) bi1 = P.nb;
     if (bi0 >= bi1) return cudaSuccess;
     if (use_cluster_kernel()) {
-        long long clusters = 0;
-        for (int bi = bi0; bi < bi1; ++bi) clusters += (P.nb - bi + 1) >> 1;
+        const long long clusters = grouped_clusters(bi0, bi1, 0, P.nb);
         cudaError_t e = cudaFuncSetAttribute(cor_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute(cor_tc2_kernel)"; return e; }
-        cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(P.kp / BK), P.nb, bi0, mirror ? 1 : 0, 0, P.nb);
+        cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(P.kp / BK), P.nb, bi0, bi1, mirror ? 1 : 0, 0, P.nb);
         (*n_launch)++;
         e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "cor_tc2_kernel"; return e; }
         return cudaSuccess;
@@ -558,9 +583,8 @@ static cudaError_t run_overlapped(Scratch& S, const float* host, float* d_data, 
         const i64 s1 = (c == chunks - 1) ? p_pad : (i64)t1 * BM;          // the last chunk also zero-fills the padding rows
         standardize_split_kernel<256><<<(unsigned)(s1 - c0), 256, 0, st>>>(d_data, n, n, p, kp, zhi, zlo, c0);
         (*n_launch)++;
-        long long clusters = 0;
-        for (int bi = 0; bi < t1; ++bi) { const int lo = bi > t0 ? bi : t0; clusters += (t1 - lo + 1) >> 1; }
-        cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(kp / BK), nb, 0, 1, t0, t1);
+        const long long clusters = grouped_clusters(0, t1, t0, t1);
+        cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(kp / BK), nb, 0, t1, 1, t0, t1);
         (*n_launch)++;
         e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "cor_tc2_kernel (band)"; return e; }
         t0 = t1;

@@ -201,6 +201,35 @@ static cudaError_t grid_for(K kernel, int threads, size_t smem, int sm_count, i6
 }
 
 
+// SparseMatrixCSC{Float32,Int64} / SparseMatrixCSC{Int32,Int64} input (the reference's default make_sparse = true tables):
+// uploaded as the CSC triple (nnz-proportional PCIe traffic) and densified on the device into the resident table
+template <class T>
+static int set_data_csc(fw_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const T* nzval, int64_t n, int64_t p, DevBuf<T>& dst, const char* who) {
+    NEED(colptr && n > 0 && p > 0, FW_ERR_INVALID, "%s: bad arguments", who);
+    const i64 base = ctx->index_base;
+    const i64 nnz = colptr[p] - colptr[0];
+    NEED(colptr[0] == base && nnz >= 0 && (nnz == 0 || (rowval && nzval)), FW_ERR_INVALID, "%s: bad CSC structure (colptr[0] must equal the index base %lld)", who, (long long)base);
+    for (i64 v = 0; v < p; ++v) NEED(colptr[v + 1] >= colptr[v], FW_ERR_INVALID, "%s: colptr not monotone", who);
+    CK(cudaSetDevice(ctx->device));
+    DevBuf<i64> dcp, drv; DevBuf<T> dnz;
+    CK(dcp.reserve(p + 1)); CK(drv.reserve(nnz)); CK(dnz.reserve(nnz)); CK(dst.reserve((size_t)n * p)); CK(ctx->d_bad.reserve(4));
+    CK(cudaMemcpyAsync(dcp.ptr, colptr, sizeof(i64) * (p + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz) {
+        CK(cudaMemcpyAsync(drv.ptr, rowval, sizeof(i64) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dnz.ptr, nzval, sizeof(T) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaMemsetAsync(dst.ptr, 0, sizeof(T) * (size_t)n * p, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_bad.ptr, 0, sizeof(int), ctx->stream));
+    csc_scatter_kernel<T><<<(unsigned)p, 256, 0, ctx->stream>>>(dcp.ptr, drv.ptr, dnz.ptr, n, p, base, dst.ptr, ctx->d_bad.ptr);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, ctx->d_bad.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    NEED(!bad, FW_ERR_INVALID, "%s: row index out of range", who);
+    return FW_OK;
+}
+
 extern "C" {
 
 const char* fw_build_info(void) {
@@ -330,6 +359,19 @@ int32_t fw_set_data_i32(fw_ctx* ctx, const int32_t* host, int64_t n, int64_t p, 
     CK(ctx->d_data_i32.reserve((size_t)n * p));
     CK(cudaMemcpy2DAsync(ctx->d_data_i32.ptr, n * sizeof(int), host, ld * sizeof(int), n * sizeof(int), p, cudaMemcpyHostToDevice, ctx->stream));
     return install_discrete_table(ctx, n, p, "fw_set_data_i32");
+}
+int32_t fw_set_data_csc_f32(fw_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const float* nzval, int64_t n, int64_t p) {
+    if (!ctx) return FW_ERR_INVALID;
+    int st_ = set_data_csc<float>(ctx, colptr, rowval, nzval, n, p, ctx->d_data_f32, "fw_set_data_csc_f32");
+    if (st_ != FW_OK) return st_;
+    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n; ctx->nz_ready = false; ctx->tcp.valid = false;
+    return FW_OK;
+}
+int32_t fw_set_data_csc_i32(fw_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const int32_t* nzval, int64_t n, int64_t p) {
+    if (!ctx) return FW_ERR_INVALID;
+    int st_ = set_data_csc<int>(ctx, colptr, rowval, nzval, n, p, ctx->d_data_i32, "fw_set_data_csc_i32");
+    if (st_ != FW_OK) return st_;
+    return install_discrete_table(ctx, n, p, "fw_set_data_csc_i32");
 }
 int32_t fw_set_n_obs(fw_ctx* ctx, int64_t n) { if (!ctx) return FW_ERR_INVALID; NEED(n >= 0, FW_ERR_INVALID, "n_obs < 0"); ctx->n_obs = n; return FW_OK; }
 

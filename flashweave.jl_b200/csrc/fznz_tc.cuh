@@ -32,6 +32,7 @@ constexpr int B_TILE = BN * BK * 2;                    // 8 KB
 constexpr int STAGE_BYTES = 3 * A_TILE + 3 * B_TILE;   // 72 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 constexpr int NTHREADS = 192;
+constexpr int TC_GROUP = 8;                            // X blocks per rasterisation group
 constexpr float VAR_EPS = 0.02f;                        // planes have unit variance over a variable's non-zero rows
 
 // one CTA per variable: mean / sd over the non-zero rows (fixed-order reductions: deterministic), then the three bf16 planes
@@ -106,9 +107,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) fznz_prefilter_kernel(const __gri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + STAGES * STAGE_BYTES + 16 * STAGES + 16);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // tile (I, J): X block I (128 variables) against Y block J (64 variables), J >= 2 I (some Y above some X)
+    // tile (I, J): X block I (128 variables) against Y block J (64 variables), J >= 2 I (some Y above some X).  Tile order as in
+    // cor_tc2_kernel: X blocks in groups of TC_GROUP, inside a group the Y blocks are the outer loop, so the tiles that run at
+    // the same time share TC_GROUP X row blocks and ~18 Y row blocks of the operand planes (3 GB at C5, far larger than L2)
+    // instead of streaming a different Y block each; tiles of the group's rectangle below the diagonal exit at once.
     int I = 0, J = 0;
-    { long long q = blockIdx.x; for (I = 0; I < a.nb_a; ++I) { const long long len = a.nb_b - 2 * I; if (q < len) { J = 2 * I + (int)q; break; } q -= len; } }
+    {
+        long long q = blockIdx.x;
+        int r0 = 0, rows = 1;
+        for (;; r0 += TC_GROUP) {
+            rows = a.nb_a - r0 < TC_GROUP ? a.nb_a - r0 : TC_GROUP;
+            const long long cnt = (long long)(a.nb_b - 2 * r0) * rows;
+            if (q < cnt || r0 + TC_GROUP >= a.nb_a) break;
+            q -= cnt;
+        }
+        I = r0 + (int)(q % rows);
+        J = 2 * r0 + (int)(q / rows);
+        if (J < 2 * I || J >= a.nb_b) return;
+    }
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -320,7 +336,7 @@ static cudaError_t run_prefilter(Planes& P, const NzTable& t, i64 n_obs_min, dou
     a.z_alpha = (float)(z_of_alpha(alpha) * (1.0 - 1e-6));
     a.counters = counters; a.cand_cap = cand_cap; a.cand_x = cand_x; a.cand_y = cand_y;
     long long tiles = 0;
-    for (int I = 0; I < a.nb_a; ++I) tiles += a.nb_b - 2 * I;
+    for (int r0 = 0; r0 < a.nb_a; r0 += TC_GROUP) tiles += (long long)(a.nb_b - 2 * r0) * std::min(TC_GROUP, a.nb_a - r0);
     fznz_prefilter_kernel<<<(unsigned)tiles, NTHREADS, SMEM_BYTES, st>>>(tm_m, tm_x, tm_x2, a);
     (*n_launch)++;
     e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "fznz_prefilter_kernel"; return e; }

@@ -148,3 +148,17 @@ __global__ void __launch_bounds__(256) prep_gather_cols_kernel(const int* __rest
     const i64 i = (i64)blockIdx.y * blockDim.x + threadIdx.x;
     if (i < n1) dst[j * n1 + i] = src[(i64)colmap[j] * n1 + i];
 }
+
+// ---- sparse input: SparseMatrixCSC{T,Int64} (colptr, rowval, nzval; 0- or 1-based) -> the dense column-major table ------------
+// (the reference densifies column views the same way for the dense test kernels; stored zeros stay zeros)
+template <class T>
+__global__ void __launch_bounds__(256) csc_scatter_kernel(const i64* __restrict__ colptr, const i64* __restrict__ rowval, const T* __restrict__ nzval,
+                                                          i64 n, i64 p, i64 base, T* __restrict__ dense, int* __restrict__ bad) {
+    const i64 v = blockIdx.x;
+    const i64 b = colptr[v] - base, e = colptr[v + 1] - base;
+    for (i64 k = b + threadIdx.x; k < e; k += blockDim.x) {
+        const i64 r = rowval[k] - base;
+        if (r < 0 || r >= n) { atomicOr(bad, 1); continue; }
+        dense[v * n + r] = nzval[k];
+    }
+}

@@ -72,6 +72,11 @@ int32_t fw_last_timing(fw_ctx* ctx, double* out_ms, int32_t n);
 int32_t fw_set_data_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, int64_t ld);
 /* discrete table (mi / mi_nz): Matrix{Int32} level codes >= 0 */
 int32_t fw_set_data_i32(fw_ctx* ctx, const int32_t* host, int64_t n, int64_t p, int64_t ld);
+/* sparse tables: SparseMatrixCSC{Float32,Int64} / SparseMatrixCSC{Int32,Int64} as (colptr[p+1], rowval[nnz], nzval[nnz]) with the
+ * context's index base (fw_set_index_base(ctx, 1) for Julia's arrays).  Only the triple crosses PCIe; the table is densified
+ * on the device and then behaves exactly like the dense one (the dense test semantics are the canonical ones). */
+int32_t fw_set_data_csc_f32(fw_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const float* nzval, int64_t n, int64_t p);
+int32_t fw_set_data_csc_i32(fw_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const int32_t* nzval, int64_t n, int64_t p);
 /* same, device-resident inputs owned by the caller (e.g. a tensor that was NCCL-broadcast);
  * the pointer must stay valid until the next fw_set_data / fw_adopt_data / fw_destroy */
 int32_t fw_adopt_data_f32_device(fw_ctx* ctx, const float* dev, int64_t n, int64_t p, int64_t ld);

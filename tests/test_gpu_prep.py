@@ -112,3 +112,27 @@ def test_counts_to_network(fw, fx, golden_dir):
         else:
             have = {(a, b) for a, b, _ in r["edges"]}
         assert have == want, (tn, len(have), len(want))
+
+
+def test_sparse_csc_input(fw, fx):
+    """SparseMatrixCSC triples (the reference's default make_sparse = true tables) give the same resident table, and therefore
+    the same tests, as the dense upload; index base 1 as the Julia glue passes them; bad structure fails loudly."""
+    import scipy.sparse as sp
+    for kind, dense in (("fz_nz", prep.normalize(fx["counts"], test_name="fz_nz")[0]), ("mi_nz", prep.normalize(fx["counts"], test_name="mi_nz")[0])):
+        n, p = dense.shape
+        m = sp.csc_matrix(dense)
+        a = fw.Engine(0).set_data(dense, kind)
+        b = fw.Engine(0).set_data_csc(m.indptr, m.indices, m.data, n, p, kind)
+        assert (b.get_data() == dense).all()
+        ra = a.pw_univar_neighbors(alpha=0.01, n_obs_min=20)
+        rb = b.pw_univar_neighbors(alpha=0.01, n_obs_min=20)
+        assert (ra.offsets == rb.offsets).all() and (ra.nbr == rb.nbr).all() and (ra.stat == rb.stat).all()
+        c = fw.Engine(0)
+        c.L.fw_set_index_base(c.h, 1)
+        c.set_data_csc(m.indptr + 1, m.indices + 1, m.data, n, p, kind)
+        assert (c.get_data() == dense).all()
+        c.L.fw_set_index_base(c.h, 0)
+        with pytest.raises(fw.FwError):
+            fw.Engine(0).set_data_csc(m.indptr, m.indices + n, m.data, n, p, kind)       # rows out of range
+        with pytest.raises(fw.FwError):
+            fw.Engine(0).set_data_csc(m.indptr + 1, m.indices, m.data, n, p, kind)       # colptr[0] != index base
