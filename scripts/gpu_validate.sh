@@ -12,5 +12,6 @@ fi
 if [ -n "$NCU" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_C4.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:hiton_fz -s 2 -c 1 -o gpurun_out/prof_hiton_C4 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_hiton_C4.log 2>&1
+  timeout 900 ncu --set full --clock-control none -k regex:cor_tc2 -s 24 -c 1 -o gpurun_out/prof_cor_C4 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_cor_C4.log 2>&1
   ls -la gpurun_out
 fi
