@@ -37,6 +37,7 @@ ABI_SYMBOLS = [
     "fw_set_cor_f32", "fw_adopt_cor_device", "fw_cor_device_ptr", "fw_adopt_cor_device_rows", "fw_cor_prepare", "fw_cor_rows", "fw_cor_symmetrize", "fw_upload_cor_f32", "fw_test_batch", "fw_test_subsets", "fw_test_subsets_batch",
     "fw_pairwise", "fw_pairwise_copy", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_capacity",
     "fw_normalize_f32", "fw_get_data_f32", "fw_get_data_i32", "fw_set_data_csc_f32", "fw_set_data_csc_i32",
+    "fw_host_register", "fw_host_unregister",
     "fw_build_info",
 ]
 
@@ -114,6 +115,8 @@ def load_library():
         "fw_normalize_f32": (i32, [vp, vp, i64, i64, i64, i32, i32, C.POINTER(i64), C.POINTER(i64), vp, vp]),
         "fw_set_data_csc_f32": (i32, [vp, vp, vp, vp, i64, i64]),
         "fw_set_data_csc_i32": (i32, [vp, vp, vp, vp, i64, i64]),
+        "fw_host_register": (i32, [vp, vp, i64]),
+        "fw_host_unregister": (i32, [vp, vp]),
         "fw_get_data_f32": (i32, [vp, vp, i64]),
         "fw_get_data_i32": (i32, [vp, vp, i64]),
         "fw_build_info": (C.c_char_p, []),
@@ -188,7 +191,15 @@ class Engine:
         self.n = self.p = 0
         self._keep = []
 
+    def _unpin_hbuf(self):
+        b = getattr(self, "_hbuf", None)
+        if b is not None and getattr(self, "h", None):
+            for k in b.get("pinned", []):
+                self.L.fw_host_unregister(self.h, _p(b[k]))
+            b["pinned"] = []
+
     def close(self):
+        self._unpin_hbuf()
         if getattr(self, "h", None):
             self.L.fw_destroy(self.h)
             self.h = None
@@ -482,7 +493,13 @@ class Engine:
                  "tpcc": np.zeros(max(nt, 1), np.int64), "tpcn": np.zeros(cp, np.int64), "tpcs": np.zeros(cp), "tpcp": np.zeros(cp),
                  "ntests": np.zeros(max(nt, 1), np.int64)}
             if reuse_buffers:
+                self._unpin_hbuf()
                 self._hbuf = b
+                # reused result buffers are page-locked once: the copy-out then runs at full PCIe speed
+                b["pinned"] = []
+                for k in ("off", "pcc", "pcn", "pcs", "pcp", "tpcc", "tpcn", "tpcs", "tpcp", "ntests"):
+                    if self.L.fw_host_register(self.h, _p(b[k]), b[k].nbytes) == 0:
+                        b["pinned"].append(k)
         ex = C.c_int64(0)
         tp = want_tpc
         self._ck(self.L.fw_hiton_pc(self.h, KINDS[kind or self.kind], nt, _p(t), max_k, alpha, hps, n_obs_min, max_tests,

@@ -276,6 +276,22 @@ int32_t fw_destroy(fw_ctx* ctx) {
     return FW_OK;
 }
 
+// page-lock / unlock a caller-owned host buffer (result arrays that are reused across calls then move at full PCIe speed)
+int32_t fw_host_register(fw_ctx* ctx, void* ptr, int64_t bytes) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(ptr && bytes > 0, FW_ERR_INVALID, "fw_host_register: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return FW_OK;
+}
+int32_t fw_host_unregister(fw_ctx* ctx, void* ptr) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(ptr, FW_ERR_INVALID, "fw_host_unregister: NULL");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostUnregister(ptr));
+    return FW_OK;
+}
+
 const char* fw_last_error(fw_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int32_t fw_set_index_base(fw_ctx* ctx, int32_t base) {
@@ -781,7 +797,8 @@ int32_t fw_test_subsets_batch(fw_ctx* ctx, int32_t kind, int64_t n_jobs, const i
         ma.cap = need;
         ma.out = dres.ptr; ma.out_Zs = dZs.ptr; ma.out_k = dk.ptr; ma.num_tests = dnt.ptr; ma.frac = dfr.ptr; ma.executed_total = ctx->d_exec.ptr;
         const int TH = 256; const int L = ma.t.L;
-        size_t smem = ((sizeof(i64) * (need + 1) + sizeof(i64) * need + sizeof(int) * need + 15) & ~(size_t)15) + (size_t)(TH / 32) * L * L * L * L * L * sizeof(int) + 16;
+        size_t smem = ((sizeof(i64) * (need + 1) + sizeof(i64) * need + sizeof(int) * need + 15) & ~(size_t)15) + (size_t)(TH / 32) * L * L * L * L * L * sizeof(int)
+                      + (size_t)(TH / 32) * MI_BIN_WARP_BYTES + 16;      // + the count buffers of the batched binary scan
         NEED(smem <= 200 * 1024, FW_ERR_UNSUPPORTED, "fw_test_subsets: |Z_total| = %d exceeds the supported maximum", need - 2);
         CK(cudaMemsetAsync(ctx->d_counter.ptr, 0, sizeof(int), ctx->stream));
         int grid = 1;
@@ -1062,7 +1079,7 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         std::stable_sort(sel.begin(), sel.end(), [&](int x, int y) { return (hoff[x + 1] - hoff[x]) > (hoff[y + 1] - hoff[y]); });
         i64 need = 2; for (i64 t = 0; t < n_targets; ++t) need = std::max<i64>(need, hoff[t + 1] - hoff[t] + 2);
         const int TH = 256; const int L = ma.t.L;
-        const size_t tabs = (size_t)(TH / 32) * L * L * L * L * L * sizeof(int);
+        const size_t tabs = (size_t)(TH / 32) * L * L * L * L * L * sizeof(int) + (size_t)(TH / 32) * MI_BIN_WARP_BYTES;   // + count buffers of the batched binary scan
         // optimistic capacity (accepted sets are far smaller than candidate lists); re-run overflowing targets with the full bound
         int caps[2] = {(int)std::min<i64>(need, 64), (int)need};
         CK(cudaEventRecord(ctx->ev[4], ctx->stream));

@@ -16,6 +16,184 @@ struct MiSlotTest {
     }
 };
 
+// ---- binary fast path of the subset scan: counting per warp, statistics per lane -------------------------------------------------
+// mi_test_warp spends most of its instructions after the counting: the MI sum (fp64 log), the degrees of freedom and the
+// chi^2 tail are scalar work that a warp executes for ONE test.  Here a warp takes a batch of B consecutive subsets: it counts the
+// 2 x 2 x 2^k table of each of them cooperatively (lanes stride over the words; mask tree + inclusion-exclusion popcounts as in
+// mi_test_warp_bin) into shared memory, then lane j evaluates the statistics of subset j - the scalar part is amortised over the
+// batch.  Batches grow 1 -> 8 -> 32 subsets per warp, so the reference's early exit (which almost always happens in the first
+// few subsets) still costs one small chunk.  Per-lane results feed the same first-failure / arg-max reductions as eval_subsets
+// with one thread per test.  Valid for kind "mi", 2-level tables (L = 2) and 2-level X and Y; same integers and formulas as
+// mi_test_warp_bin (statfuns.jl:163-305, tests.jl:184-229), summed in stratum order.
+template <int K>
+__device__ __forceinline__ void mi_count_bin_to_smem(const unsigned int* __restrict__ planes, int W, unsigned int tail_mask, i64 X, i64 Y, i64 z0, i64 z1, i64 z2, int* out /* 4 * 2^K cells */) {
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    constexpr int S = 1 << K;
+    int cn[S], cx[S], cy[S], cxy[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { cn[s] = 0; cx[s] = 0; cy[s] = 0; cxy[s] = 0; }
+    const unsigned int* px = planes + (size_t)X * W;
+    const unsigned int* py = planes + (size_t)Y * W;
+    const unsigned int* pz0 = planes + (size_t)z0 * W;
+    const unsigned int* pz1 = planes + (size_t)z1 * W;
+    const unsigned int* pz2 = planes + (size_t)z2 * W;
+    for (int w = lane; w < W; w += 32) {
+        const unsigned int valid = (w == W - 1) ? tail_mask : 0xffffffffu;
+        const unsigned int x = __ldg(px + w), y = __ldg(py + w);
+        unsigned int m[S];
+        m[0] = valid;
+        if (K > 0) { const unsigned int z = __ldg(pz0 + w); m[1] = m[0] & z; m[0] &= ~z; }
+        if (K > 1) { const unsigned int z = __ldg(pz1 + w);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) { m[s + 2] = m[s] & z; m[s] &= ~z; } }
+        if (K > 2) { const unsigned int z = __ldg(pz2 + w);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { m[s + 4] = m[s] & z; m[s] &= ~z; } }
+        const unsigned int xy = x & y;
+#pragma unroll
+        for (int s = 0; s < S; ++s) { cn[s] += __popc(m[s]); cx[s] += __popc(m[s] & x); cy[s] += __popc(m[s] & y); cxy[s] += __popc(m[s] & xy); }
+    }
+    int mine = 0;                                   // lane c owns cell (a = c & 1, b = (c >> 1) & 1, stratum = c >> 2)
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int n = __reduce_add_sync(full, cn[s]), nx = __reduce_add_sync(full, cx[s]);
+        const int ny = __reduce_add_sync(full, cy[s]), nxy = __reduce_add_sync(full, cxy[s]);
+        if ((lane >> 2) == s) {
+            const int a = lane & 1, b = (lane >> 1) & 1;
+            mine = a ? (b ? nxy : nx - nxy) : (b ? ny - nxy : n - nx - ny + nxy);
+        }
+    }
+    if (lane < 4 * S) out[lane] = mine;
+}
+
+// statistics of one 2 x 2 x S table (S = 2^K strata, K >= 1), one thread: tests.jl:200-221, statfuns.jl:163-254, 281-305.
+// The fp64 terms are accumulated in the order of the reference's loops `for i, j, k` (statfuns.jl:181: x level, y level, strata
+// innermost; strata in raw-key order here - the reference walks them in first-seen order, which can differ in the last ulp, see
+// DESIGN.md 4.5): the diagonal sum takes the (0,0) cells of all strata, then the (1,1) cells; the off-diagonal sum (0,1), then (1,0).
+// cs: this lane's 4 S counts, uv: 2 S doubles of scratch for the deferred terms (both in shared memory, bank-conflict-free strides)
+__device__ MiResult mi_stats_bin_thread(const int* cs /* [S][b][a] */, double* uv, int S, i64 hps) {
+    MiResult r;
+    i64 n_obs = 0; int levels_z = 0;
+    for (int s = 0; s < S; ++s) { const int tot = cs[4 * s] + cs[4 * s + 1] + cs[4 * s + 2] + cs[4 * s + 3]; n_obs += tot; levels_z += tot > 0; }
+    if (!(((double)n_obs / (double)(4 * levels_z)) > (double)hps)) { r.stat = 0.0; r.pval = 1.0; r.df = 0; r.suff = false; return r; }
+    double pos = 0.0, neg = 0.0; i64 n_pos = 0, n_neg = 0; int df = 0;
+    for (int s = 0; s < S; ++s) {
+        const int c00 = cs[4 * s], c10 = cs[4 * s + 1], c01 = cs[4 * s + 2], c11 = cs[4 * s + 3];   // index = 2 b + a (a: X level, b: Y level)
+        const int ma0 = c00 + c01, ma1 = c10 + c11;          // margins over Y for X = 0, 1 (marg_i)
+        const int mb0 = c00 + c10, mb1 = c01 + c11;          // margins over X for Y = 0, 1 (marg_j)
+        const int mk = ma0 + ma1;
+        if (c00 != 0) { pos += log((double)((i64)mk * c00) / (double)((i64)ma0 * mb0)) * (double)c00; n_pos += c00; }
+        if (c01 != 0) { neg += log((double)((i64)mk * c01) / (double)((i64)ma0 * mb1)) * (double)c01; n_neg += c01; }
+        const double u = c11 != 0 ? log((double)((i64)mk * c11) / (double)((i64)ma1 * mb1)) * (double)c11 : 0.0;
+        const double v = c10 != 0 ? log((double)((i64)mk * c10) / (double)((i64)ma1 * mb0)) * (double)c10 : 0.0;
+        n_pos += c11; n_neg += c10;
+        df += (ma0 > 0 && ma1 > 0 && mb0 > 0 && mb1 > 0) ? 1 : 0;
+        uv[2 * s] = u; uv[2 * s + 1] = v;                      // (1,1) and (1,0) terms of stratum s
+    }
+    for (int s = 0; s < S; ++s) { pos += uv[2 * s]; neg += uv[2 * s + 1]; }       // adding an exact 0.0 term changes nothing
+    const i64 n_mi = n_pos + n_neg;
+    double mi = (pos + neg) / (double)n_mi;
+    if (neg * ((double)n_neg / (double)n_mi) > pos * ((double)n_pos / (double)n_mi)) mi *= -1.0;
+    r.stat = mi; r.df = df; r.pval = mi_pval_dev(fabs(mi), df, n_obs); r.suff = true;
+    return r;
+}
+
+// cnt: MI_BIN_WARP_BYTES of shared memory per warp: 32 subsets x 33 ints of counts (row stride 33: the cell-per-lane stores and
+// the subset-per-lane loads are both conflict-free) + 32 x 17 doubles of scratch.  All threads of the CTA call this with identical arguments.
+constexpr int MI_BIN_CNT_LD = 33, MI_BIN_UV_LD = 17;
+constexpr int MI_BIN_WARP_BYTES = 32 * MI_BIN_CNT_LD * 4 + 32 * MI_BIN_UV_LD * 8;
+template <int THREADS>
+__device__ void eval_subsets_mi_bin(const unsigned int* __restrict__ planes, int W, unsigned int tail_mask, const i64* var, int xs, int ys, const int* acc, int m, int max_k, double alpha, i64 max_tests,
+                                    i64 hps, i64* tri_off, int* cnt, EvalShared* sh, EvalOut* out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = THREADS / 32;
+    const unsigned full = 0xffffffffu;
+    const SubsetCounts sc = subset_counts(m, max_k);
+    if (sc.c3 > 0) for (int i = tid; i <= m; i += THREADS) tri_off[i] = sc.c3 - choose3(m - i);
+    if (tid == 0) sh->fail_idx = (u64)FW_INF_IDX;
+    __syncthreads();
+    const i64 limit = (max_tests > 0 && max_tests < sc.total) ? max_tests : sc.total;
+    const i64 X = var[xs], Y = var[ys];
+    int* wcnt = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(cnt) + (size_t)warp * MI_BIN_WARP_BYTES);
+    double* wuv = reinterpret_cast<double*>(wcnt + 32 * MI_BIN_CNT_LD);
+    i64 my_fail = FW_INF_IDX; double f_stat = 0.0, f_p = 0.0; i64 f_df = 0; int f_suff = 0;
+    i64 best_idx = -1; double b_stat = 0.0, b_p = -1.0; i64 b_df = 0;
+    i64 executed = 0;
+    bool any_fail = false;
+    int B = 1;                                                   // subsets per warp in this chunk
+    for (i64 base = 0; base < limit;) {
+        const i64 my_idx = base + (i64)warp * B + lane;           // the subset this lane will evaluate
+        const bool mine = lane < B && my_idx < limit;
+        int k = 0, pa = 0, pb = 0, pc = 0;
+        if (mine) unrank_subset(my_idx, m, sc, tri_off, k, pa, pb, pc);
+        // counting: the warp walks through its batch
+        for (int j = 0; j < B; ++j) {
+            const i64 idx = base + (i64)warp * B + j;
+            if (idx >= limit) break;                             // warp-uniform
+            const int kj = __shfl_sync(full, k, j);
+            const i64 z0 = var[acc[__shfl_sync(full, pa, j)]];
+            const i64 z1 = var[acc[__shfl_sync(full, pb, j)]];   // positions beyond k are 0: harmless valid members
+            const i64 z2 = var[acc[__shfl_sync(full, pc, j)]];
+            if (kj == 3) mi_count_bin_to_smem<3>(planes, W, tail_mask, X, Y, z0, z1, z2, wcnt + j * MI_BIN_CNT_LD);
+            else if (kj == 2) mi_count_bin_to_smem<2>(planes, W, tail_mask, X, Y, z0, z1, z2, wcnt + j * MI_BIN_CNT_LD);
+            else mi_count_bin_to_smem<1>(planes, W, tail_mask, X, Y, z0, z1, z2, wcnt + j * MI_BIN_CNT_LD);
+        }
+        __syncwarp();
+        if (mine) {
+            const MiResult r = mi_stats_bin_thread(wcnt + lane * MI_BIN_CNT_LD, wuv + lane * MI_BIN_UV_LD, 1 << k, hps);
+            const bool sig = (r.pval < alpha) && r.suff;
+            const bool stop = !sig || (max_tests > 0 && my_idx + 1 >= max_tests);
+            if (stop) { my_fail = my_idx; f_stat = r.stat; f_p = r.pval; f_df = r.df; f_suff = r.suff ? 1 : 0; }
+            else if (r.pval >= b_p) { best_idx = my_idx; b_stat = r.stat; b_p = r.pval; b_df = r.df; }
+        }
+        __syncwarp();
+        const i64 end = base + (i64)NW * B;
+        executed = end < limit ? end : limit;
+        any_fail = __syncthreads_or(my_fail != FW_INF_IDX);
+        if (any_fail) break;
+        base = end; B = B == 1 ? 8 : 32;
+    }
+    if (any_fail) {
+        if (my_fail != FW_INF_IDX) atomicMin(&sh->fail_idx, (u64)my_fail);
+        __syncthreads();
+        if ((u64)my_fail == sh->fail_idx) {
+            int k, a, b, c;
+            unrank_subset(my_fail, m, sc, tri_off, k, a, b, c);
+            out->stat = f_stat; out->pval = f_p; out->df = f_df; out->suff = f_suff;
+            out->sig = ((f_p < alpha) && f_suff) ? 1 : 0;
+            out->k = k; out->pos[0] = a; out->pos[1] = b; out->pos[2] = c;
+            out->num_tests = my_fail + 1; out->total = sc.total; out->executed = executed; executed_by_k(sc, executed, out->ex_k);
+        }
+        __syncthreads();
+        return;
+    }
+    // all significant: arg-max p-value, ties -> larger index (tests.jl:338-341)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double op = __shfl_down_sync(full, b_p, off);
+        double os = __shfl_down_sync(full, b_stat, off);
+        i64 oi = __shfl_down_sync(full, best_idx, off);
+        i64 od = __shfl_down_sync(full, b_df, off);
+        if (op > b_p || (op == b_p && oi > best_idx)) { b_p = op; b_stat = os; best_idx = oi; b_df = od; }
+    }
+    if (lane == 0) { sh->w_p[warp] = b_p; sh->w_stat[warp] = b_stat; sh->w_idx[warp] = best_idx; sh->w_df[warp] = b_df; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NW; ++w) {
+            double op = sh->w_p[w]; i64 oi = sh->w_idx[w];
+            if (op > b_p || (op == b_p && oi > best_idx)) { b_p = op; b_stat = sh->w_stat[w]; best_idx = oi; b_df = sh->w_df[w]; }
+        }
+        int k = 0, a = 0, b = 0, c = 0;
+        if (best_idx >= 0) unrank_subset(best_idx, m, sc, tri_off, k, a, b, c);
+        out->stat = b_stat; out->pval = b_p; out->df = b_df; out->suff = 1;
+        out->sig = (b_p < alpha) ? 1 : 0;
+        out->k = k; out->pos[0] = a; out->pos[1] = b; out->pos[2] = c;
+        out->num_tests = limit; out->total = sc.total; out->executed = executed; executed_by_k(sc, executed, out->ex_k);
+    }
+    __syncthreads();
+}
+
 struct HitonMiArgs {
     MiTable t; i64 hps;
     const i64* uni_off; const i64* uni_nbr; const double* uni_stat; const double* uni_p;
@@ -44,6 +222,8 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
     int* pc_slot = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;
     int* tabs = reinterpret_cast<int*>(smem + o);
     int* tab = tabs + warp * tab_ints;
+    int* cnt = tabs + (THREADS / 32) * tab_ints;                                     // batched binary scan: [warps][32][32] ints
+    const bool bin_table = (L == 2 && !a.t.nz);
     __shared__ EvalShared sh;
     __shared__ EvalOut ev;
     __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_accept;
@@ -99,7 +279,10 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
                 for (int s = tid; s < M; s += THREADS) acc[s] = s + 1;
                 __syncthreads();
                 MiSlotTest tf; tf.t = a.t; tf.var = var; tf.x = 0; tf.y = ys; tf.hps = a.hps; tf.tab = tab;
-                eval_subsets<THREADS, TPT, 32>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                if (bin_table && a.t.levels[T] == 2 && a.t.levels[cand] == 2)
+                    eval_subsets_mi_bin<THREADS>(a.t.planes, a.t.W, a.t.tail_mask, var, 0, ys, acc, M, a.max_k, a.alpha, a.max_tests, a.hps, tri_off, cnt, &sh, &ev);
+                else
+                    eval_subsets<THREADS, TPT, 32>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
                 if (tid == 0) {
                     s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
                     if (ev.sig) { tpc_stat[M] = ev.stat; tpc_p[M] = ev.pval; s_accept = 1; }
@@ -127,7 +310,10 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
                 if (tid == 0) { pcs_stat[s_npc] = tpc_stat[c - 1]; pcs_p[s_npc] = tpc_p[c - 1]; s_accept = 1; }
             } else {
                 MiSlotTest tf; tf.t = a.t; tf.var = var; tf.x = 0; tf.y = c; tf.hps = a.hps; tf.tab = tab;
-                eval_subsets<THREADS, TPT, 32>(tf, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+                if (bin_table && a.t.levels[T] == 2 && a.t.levels[var[c]] == 2)
+                    eval_subsets_mi_bin<THREADS>(a.t.planes, a.t.W, a.t.tail_mask, var, 0, c, acc, macc, a.max_k, a.alpha, a.max_tests, a.hps, tri_off, cnt, &sh, &ev);
+                else
+                    eval_subsets<THREADS, TPT, 32>(tf, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
                 if (tid == 0) {
                     s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
                     if (ev.sig) { pcs_stat[s_npc] = ev.stat; pcs_p[s_npc] = ev.pval; s_accept = 1; }
@@ -176,6 +362,8 @@ __global__ void __launch_bounds__(THREADS) subsets_mi_kernel(SubsetsMiArgs a) {
     int* acc = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;
     o = (o + 15) & ~(size_t)15;
     int* tab = reinterpret_cast<int*>(smem + o) + warp * tab_ints;
+    int* cnt = reinterpret_cast<int*>(smem + o) + (THREADS / 32) * tab_ints;
+    const bool bin_table = (L == 2 && !a.t.nz);
     __shared__ EvalShared sh;
     __shared__ EvalOut ev;
     __shared__ int s_ji;
@@ -192,7 +380,10 @@ __global__ void __launch_bounds__(THREADS) subsets_mi_kernel(SubsetsMiArgs a) {
         for (int s = tid; s < m; s += THREADS) acc[s] = s + 2;
         __syncthreads();
         MiSlotTest tf; tf.t = a.t; tf.var = var; tf.x = 0; tf.y = 1; tf.hps = a.hps; tf.tab = tab;
-        eval_subsets<THREADS, TPT, 32>(tf, acc, m, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
+        if (bin_table && a.t.levels[a.X[job]] == 2 && a.t.levels[a.Y[job]] == 2)
+            eval_subsets_mi_bin<THREADS>(a.t.planes, a.t.W, a.t.tail_mask, var, 0, 1, acc, m, a.max_k, a.alpha, a.max_tests, a.hps, tri_off, cnt, &sh, &ev);
+        else
+            eval_subsets<THREADS, TPT, 32>(tf, acc, m, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
         if (tid == 0) {
             a.out[job] = make_result(ev.stat, ev.pval, ev.df, ev.suff != 0);
             for (int i = 0; i < 3; ++i) a.out_Zs[job * 3 + i] = (i < ev.k) ? a.z_idx[z0 + ev.pos[i]] : -1;

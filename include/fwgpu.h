@@ -61,6 +61,10 @@ int32_t fw_set_index_base(fw_ctx* ctx, int32_t base);          /* 0 (default) or
 /* cudaStream_t all kernels of this context are launched on (for CUDA-event timing). */
 void* fw_stream(fw_ctx* ctx);
 int32_t fw_synchronize(fw_ctx* ctx);
+/* cudaHostRegister / cudaHostUnregister of a caller-owned buffer (e.g. the result arrays of fw_hiton_pc when they are reused
+ * across calls, or a SharedArray table): page-locked buffers move at full PCIe speed and asynchronously */
+int32_t fw_host_register(fw_ctx* ctx, void* ptr, int64_t bytes);
+int32_t fw_host_unregister(fw_ctx* ctx, void* ptr);
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 int64_t fw_launch_count(fw_ctx* ctx);
 /* device time in ms (CUDA events on the context's stream) of the last run of each phase:

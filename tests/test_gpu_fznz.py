@@ -175,6 +175,26 @@ def test_fznz_pairwise_prefilter_equals_exhaustive(fw, synth):
         assert a[4]["n_raw_sig"] > 1000
 
 
+def test_fznz_pairwise_prefilter_candidate_overflow(fw, synth):
+    """One big block: nearly every pair is significant, so the candidate list outgrows its first allocation (n_pairs / 16) and
+    the pre-filter is re-run with the exact size; the result must still equal the exhaustive path."""
+    lat = synth.clique(1600, 800, B=1600, seed=71)
+    x = synth.with_zeros(lat, zero_frac=0.3, seed=72)
+    res = {}
+    for mode in ("1", "0"):
+        os.environ["FWGPU_FZNZ_TC"] = mode
+        try:
+            eng = fw.Engine(0)
+            eng.set_data_colmajor(x, "fz_nz")
+            got = eng.pw_univar_neighbors(alpha=0.01, n_obs_min=20)
+            res[mode] = (got.offsets.copy(), got.nbr.copy(), got.stat.copy(), got.pval.copy(), dict(eng.pairwise_stats()))
+        finally:
+            os.environ.pop("FWGPU_FZNZ_TC", None)
+    a, b = res["1"], res["0"]
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[2] == b[2]).all() and (a[3] == b[3]).all() and a[4] == b[4]
+    assert a[4]["n_raw_sig"] > 1600 * 1599 // 2 // 2          # far more candidates than n_pairs / 16 + 1024
+
+
 def test_fznz_golden_graphs(fw, hmp, golden_dir):
     graphs = json.load(open(os.path.join(golden_dir, "learning_expected.json")))
     x = np.ascontiguousarray(hmp["fz_nz"].T)
