@@ -470,6 +470,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
             AccView av; av.n_head = M - c; av.head_base = c + 1; av.tail = pc_slot;
             bool accept = false;                       // thread 0 only
             if (macc == 0) {
+                __syncthreads();                       // every thread has read s_npc before thread 0 may advance it (no scan, hence no barrier, on this path)
                 if (tid == 0) { pcs_stat[npc0] = tpc_stat[c - 1]; pcs_p[npc0] = tpc_p[c - 1]; accept = true; }   // support_dict = TPC_dict
             } else {
                 FzSlotTest tf; tf.r.R = R; tf.r.ld = ld; tf.x = 0; tf.y = c; tf.fc = a.fc;
