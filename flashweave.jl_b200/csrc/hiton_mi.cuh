@@ -395,6 +395,27 @@ __global__ void __launch_bounds__(THREADS) subsets_mi_kernel(SubsetsMiArgs a) {
     }
 }
 
+// univariate test of two 2-level variables from the four counts, one thread (tests.jl:28-77, statfuns.jl:207-254; same
+// formulas as mi_test_warp_bin<0>, terms accumulated in the order of the reference's loops `for i, for j`)
+__device__ MiResult mi_pair_bin_thread(int n, int nx, int ny, int nxy, i64 hps, i64 n_obs_min) {
+    MiResult r;
+    if ((i64)n < n_obs_min || n == 0) { r.stat = 0.0; r.pval = 1.0; r.df = 0; r.suff = false; return r; }     // weak pre-check, tests.jl:9-20
+    const i64 n_obs = n;
+    if (!(!(n_obs < n_obs_min) && (((double)n_obs / 4.0) > (double)hps))) { r.stat = 0.0; r.pval = 1.0; r.df = 0; r.suff = false; return r; }   // tests.jl:58
+    const int c11 = nxy, c10 = nx - nxy, c01 = ny - nxy, c00 = n - nx - ny + nxy;       // c[a = X level][b = Y level]
+    const int ma0 = n - nx, ma1 = nx, mb0 = n - ny, mb1 = ny;
+    double pos = 0.0, neg = 0.0; i64 n_pos = 0, n_neg = 0;
+    if (c00 != 0) { pos += log((double)(n_obs * c00) / (double)((i64)ma0 * mb0)) * (double)c00; n_pos += c00; }
+    if (c01 != 0) { neg += log((double)(n_obs * c01) / (double)((i64)ma0 * mb1)) * (double)c01; n_neg += c01; }
+    if (c10 != 0) { neg += log((double)(n_obs * c10) / (double)((i64)ma1 * mb0)) * (double)c10; n_neg += c10; }
+    if (c11 != 0) { pos += log((double)(n_obs * c11) / (double)((i64)ma1 * mb1)) * (double)c11; n_pos += c11; }
+    const int df = (ma0 > 0 && ma1 > 0 && mb0 > 0 && mb1 > 0) ? 1 : 0;
+    double mi = (pos + neg) / (double)n_obs;
+    if (neg * ((double)n_neg / (double)n_obs) > pos * ((double)n_pos / (double)n_obs)) mi *= -1.0;
+    r.stat = mi; r.df = df; r.pval = mi_pval_dev(fabs(mi), df, n_obs); r.suff = true;
+    return r;
+}
+
 // ---- pairwise stage for the discrete kinds: one warp per pair, unordered emission of raw-significant pairs ----
 // (pw_univar_kernel!, tests.jl:410-433: X-trimmed view when needs_nz_view(X); add_pwresults_to_matrix!, :391-407)
 template <int WARPS>
@@ -406,6 +427,49 @@ __global__ void __launch_bounds__(WARPS * 32) pw_mi_rows_kernel(MiTable t, i64 h
     int* tab = smem_tab + warp * (t.L * t.L);
     const i64 X = blockIdx.x;
     i64 n_rel = 0;
+    if (t.L == 2 && !t.nz && t.levels[X] == 2) {
+        // binary table: one LANE per pair.  N(X=1,Y=1) = popc(X & Y) over the words is the only count that is not a per-variable
+        // constant (N(X=1) = nnz[X], N(Y=1) = nnz[Y], N = n), so a lane walks its own Y plane (its cache line serves the next 31
+        // words) against the broadcast X plane and then evaluates MI / df / p by itself - no reductions, no idle lanes.
+        // Pairs whose Y is not a 2-level variable take the warp-cooperative generic test below.
+        const unsigned int* px = t.planes + (size_t)X * t.W;
+        const int nx = t.nnz[X];
+        u64 n_rel_lane = 0;
+        for (i64 y0 = X + 1 + (i64)warp * 32; y0 < t.p; y0 += (i64)WARPS * 32) {
+            const i64 Y = y0 + lane;
+            const bool in_range = Y < t.p;
+            const bool bin_y = in_range && t.levels[Y] == 2;
+            if (bin_y) {
+                const unsigned int* py = t.planes + (size_t)Y * t.W;
+                int nxy = 0;
+                for (int w = 0; w < t.W; ++w) nxy += __popc(__ldg(px + w) & __ldg(py + w));
+                const MiResult r = mi_pair_bin_thread(t.n, nx, t.nnz[Y], nxy, hps, n_obs_min);
+                const bool rel = r.suff || !reliable_only;
+                n_rel_lane += rel;
+                if (rel && r.pval < alpha) {
+                    u64 pos = atomicAdd(&counters[0], 1ull);
+                    if ((i64)pos < cap) { c_x[pos] = (int)X; c_y[pos] = (int)Y; c_p[pos] = r.pval; c_stat[pos] = r.stat; }
+                }
+            }
+            unsigned int rest = __ballot_sync(0xffffffffu, in_range && !bin_y);
+            while (rest) {
+                const int j = __ffs(rest) - 1; rest &= rest - 1;
+                MiResult r = mi_test_warp(t, X, y0 + j, nullptr, 0, hps, n_obs_min, tab);
+                const bool rel = r.suff || !reliable_only;
+                if (lane == 0) {
+                    n_rel_lane += rel;
+                    if (rel && r.pval < alpha) {
+                        u64 pos = atomicAdd(&counters[0], 1ull);
+                        if ((i64)pos < cap) { c_x[pos] = (int)X; c_y[pos] = (int)(y0 + j); c_p[pos] = r.pval; c_stat[pos] = r.stat; }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) n_rel_lane += __shfl_xor_sync(0xffffffffu, n_rel_lane, o);
+        if (lane == 0 && n_rel_lane) atomicAdd(&counters[1], n_rel_lane);
+        return;
+    }
     for (i64 Y = X + 1 + warp; Y < t.p; Y += WARPS) {
         MiResult r = mi_test_warp(t, X, Y, nullptr, 0, hps, n_obs_min, tab);
         // unreliable tests become NaN and are excluded from BH's m (tests.jl:397-402, 521-526)
