@@ -257,14 +257,38 @@ __device__ void eval_subsets_fz_cached(const CorSlots r, const FzTab tab, int xs
     }
     if (!any_fail && total > n0) {
         // ---- everything else in one pass ----
-        for (int q = tid; q < c3; q += THREADS) {
+        // two independent tests per thread and iteration, evaluated by the straight-line fz_k3_straight (fz.cuh): without the
+        // slow-path branches of the division / square-root intrinsics the compiler overlaps the two dependent chains
+        auto decode = [&](int q, int& a, int& b, int& c) {
             const unsigned int e = clx[q];
-            const int a = e & 31, b = (e >> 5) & 31, c = e >> 10;
+            a = e & 31; b = (e >> 5) & 31; c = e >> 10;
             const int na = m - a - 1, pa = b - a - 1;
             // reference (lexicographic) index: triples that start before a, pairs of the suffix that start before b, then c
-            const int idx = c3 - ((na + 1) * na * (na - 1)) / 6 + pa * na - ((pa * (pa + 1)) >> 1) + (c - b - 1);
-            if (idx < n0) continue;
-            consider(idx, triple(a, b, c));
+            return c3 - ((na + 1) * na * (na - 1)) / 6 + pa * na - ((pa * (pa + 1)) >> 1) + (c - b - 1);
+        };
+        auto k3 = [&](int a, int b, int c, bool& special) {
+            const int ab = a * FZ_TLD + b, ac = a * FZ_TLD + c, bc = b * FZ_TLD + c, ba = b * FZ_TLD + a, ca = c * FZ_TLD + a;
+            return fz_k3_straight(S1[bc], S1[ac], S1[ab], S1[ca], S1[ba], S2[ac], S2[ab], S2[ca], S2[ba], S3[ab], S3[ba], A2[ab], special);
+        };
+#ifndef FW_HITON_INFLIGHT
+#define FW_HITON_INFLIGHT 2
+#endif
+        constexpr int NF = FW_HITON_INFLIGHT;
+        for (int q = tid; q < c3; q += NF * THREADS) {
+            int ia[NF], ib[NF], ic[NF], idx[NF]; bool has[NF], sp[NF]; double sv[NF];
+#pragma unroll
+            for (int u = 0; u < NF; ++u) {
+                has[u] = q + u * THREADS < c3;
+                idx[u] = decode(has[u] ? q + u * THREADS : q, ia[u], ib[u], ic[u]);
+                sp[u] = false;
+            }
+#pragma unroll
+            for (int u = 0; u < NF; ++u) sv[u] = k3(ia[u], ib[u], ic[u], sp[u]);
+#pragma unroll
+            for (int u = 0; u < NF; ++u) {
+                if (sp[u]) sv[u] = pcor_generic(r, xs, ys, acc[ia[u]], acc[ib[u]], acc[ic[u]], 3);
+                if (has[u] && idx[u] >= n0) consider(idx[u], sv[u]);
+            }
         }
         for (int q = tid; q < c2; q += THREADS) {
             const int a = plx[q] & 31, b = plx[q] >> 5;
