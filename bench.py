@@ -354,7 +354,7 @@ def main_ours(a, rank, world, local_rank):
                 "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["which"],
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "40 B of correlations per k=3 test: this kernel is instruction-issue bound, not HBM bound (see DESIGN.md 4.1)",
-                "ncu": {"issue_slots_busy": 0.545, "fp64_pipe": 0.21, "alu_pipe": 0.27, "warp_instr_per_test": 11.8,
+                "ncu": {"issue_slots_busy": 0.525, "fp64_pipe": 0.25, "alu_pipe": 0.30, "warp_instr_per_test": 10.4,
                         "source": "profiles/r01s2_hiton_fz_C4_raw.csv (one ncu --set full capture of this launch, not live)"}}
     cor_ms = float(np.mean(cor_wall_ms[-a.steps:])) if dist is not None else float(min(gemm_ms))
     roofline_cor = {"kernel": "cor_mat GEMM (N=1: fw_cor_matrix on the resident table, timed alone; N>1: row-sharded + NCCL all-gather + symmetrise, wall time of the whole step)", "bound": "tensor",
