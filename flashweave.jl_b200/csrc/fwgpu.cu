@@ -327,6 +327,7 @@ int32_t fw_set_data_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, in
     CK(ctx->d_data_f32.reserve((size_t)n * p));
     CK(cudaMemcpy2DAsync(ctx->d_data_f32.ptr, n * sizeof(float), host, ld * sizeof(float), n * sizeof(float), p, cudaMemcpyHostToDevice, ctx->stream));
     ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n; ctx->nz_ready = false;
+    ctx->cor_p = 0; ctx->tcp.valid = false;          // a resident cor_mat belongs to the previous table
     return FW_OK;
 }
 int32_t fw_adopt_data_f32_device(fw_ctx* ctx, const float* dev, int64_t n, int64_t p, int64_t ld) {
@@ -334,6 +335,7 @@ int32_t fw_adopt_data_f32_device(fw_ctx* ctx, const float* dev, int64_t n, int64
     NEED(dev && n > 0 && p > 0 && ld >= n, FW_ERR_INVALID, "fw_adopt_data_f32_device: bad arguments");
     ctx->d_data_f32.adopt(const_cast<float*>(dev), (size_t)ld * p);
     ctx->n = n; ctx->p = p; ctx->ld = ld; ctx->data_kind = 0; ctx->n_obs = n; ctx->nz_ready = false;
+    ctx->cor_p = 0; ctx->tcp.valid = false;
     return FW_OK;
 }
 // get_levels / get_max_vals (src/misc.jl:64-97) and the bit-plane table of the level codes resident in ctx->d_data_i32 ([p][n])
@@ -380,7 +382,7 @@ int32_t fw_set_data_csc_f32(fw_ctx* ctx, const int64_t* colptr, const int64_t* r
     if (!ctx) return FW_ERR_INVALID;
     int st_ = set_data_csc<float>(ctx, colptr, rowval, nzval, n, p, ctx->d_data_f32, "fw_set_data_csc_f32");
     if (st_ != FW_OK) return st_;
-    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n; ctx->nz_ready = false; ctx->tcp.valid = false;
+    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n; ctx->nz_ready = false; ctx->tcp.valid = false; ctx->cor_p = 0;
     return FW_OK;
 }
 int32_t fw_set_data_csc_i32(fw_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const int32_t* nzval, int64_t n, int64_t p) {
@@ -486,7 +488,7 @@ int32_t fw_normalize_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, i
         prep_transform_kernel<<<grid, T, 0, st>>>(raw.ptr, n, dcols.ptr, drows.ptr, n1, norm, dsum32.ptr, dg.ptr, dpc.ptr, ctx->d_data_f32.ptr); ctx->launches++;
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));
-        ctx->n = n1; ctx->p = p1; ctx->ld = n1; ctx->data_kind = 0; ctx->n_obs = n1; ctx->nz_ready = false; ctx->tcp.valid = false;
+        ctx->n = n1; ctx->p = p1; ctx->ld = n1; ctx->data_kind = 0; ctx->n_obs = n1; ctx->nz_ready = false; ctx->tcp.valid = false; ctx->cor_p = 0;
     } else {
         DevBuf<int> tmp; DevBuf<unsigned int> dseen;
         CK(tmp.reserve((size_t)n1 * p1)); CK(dseen.reserve(p1));
