@@ -68,3 +68,16 @@ def test_host_graph_assembly(fw):
     assert fw.assemble_graph(res, uni, "fz") == [(0, 1, 0.5)]
     assert list(fw.target_order(fw.NbrCSR(np.array([0, 2, 2, 3]), None, None, None))) == [1, 2, 0]
     assert list(fw.shard_targets(np.arange(10), 1, 4)) == [1, 5, 9]
+
+
+def test_edgelist_format(fw, tmp_path):
+    """write_edgelist follows src/io.jl:338-359: `# header`, `# meta mask`, then `name<TAB>name<TAB>weight` with Julia's
+    shortest round-trip float text (Python's repr gives the same digits)."""
+    path = tmp_path / "net.edgelist"
+    fw.write_edgelist(str(path), [(3, 6, 0.1891748160123825), (3, 13, -0.31248563528060913)], p=14)
+    lines = open(path).read().split("\n")
+    assert lines[0] == "# header\t" + ",".join("X%d" % i for i in range(1, 15))
+    assert lines[1] == "# meta mask\t" + ",".join(["false"] * 14)
+    assert lines[2] == "X4\tX7\t0.1891748160123825" and lines[3] == "X4\tX14\t-0.31248563528060913" and lines[4] == ""
+    fw.write_edgelist(str(path), [(0, 1, 1.0)], header=["a", "b", "m"], meta_mask=[False, False, True])
+    assert open(path).read() == "# header\ta,b,m\n# meta mask\tfalse,false,true\na\tb\t1.0\n"
