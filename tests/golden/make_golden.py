@@ -13,7 +13,8 @@ Run once in the build container:  python tests/golden/make_golden.py
       -> raw counts and the six expected normalisations (test/preprocessing.jl:48-84) for the normalisation step
 
 Outputs: tests/golden/hmp_inputs.npz, tests/golden/tests_expected.json,
-         tests/golden/learning_expected.json, tests/golden/prep_fixtures.npz
+         tests/golden/learning_expected.json, tests/golden/prep_fixtures.npz,
+         tests/golden/meta_onehot.json
 """
 import json
 import os
@@ -48,6 +49,20 @@ def main():
         e = np.loadtxt(os.path.join(pe, fn + ".tsv"), delimiter="\t")
         prep[mode] = e.astype(np.int8) if ("binned" in mode or mode == "pres-abs") else e.astype(np.float32)
     np.savez_compressed(os.path.join(OUT, "prep_fixtures.npz"), **prep)
+
+    # meta variables: raw factor table and the reference's expected one-hot encoding (test/preprocessing.jl:144-170)
+    def conv(v):
+        for t in (int, float):
+            try:
+                return t(v)
+            except ValueError:
+                pass
+        return v
+    raw = [l.rstrip("\n").split("\t") for l in open(os.path.join(D, "HMP_SRA_gut", "HMP_SRA_gut_tiny_meta_oneHotTest.tsv"))]
+    exp_oh = [l.rstrip("\n").split("\t") for l in open(os.path.join(pe, "meta_tiny_oneHotTest.tsv"))]
+    with open(os.path.join(OUT, "meta_onehot.json"), "w") as f:
+        json.dump({"header": raw[0], "columns": [[conv(r[j]) for r in raw[1:]] for j in range(len(raw[0]))],
+                   "expected_header": exp_oh[0], "expected": [[float(v) for v in r] for r in exp_oh[1:]]}, f)
 
     exp = {}
     with open(os.path.join(D, "tests_expected.tsv")) as f:
