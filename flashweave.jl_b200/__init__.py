@@ -260,7 +260,7 @@ class Engine:
         self._cor_valid = False
         return self
 
-    def normalize_data(self, data, test_name="", norm_mode="", n_bins=3, want_host=True):
+    def normalize_data(self, data, test_name="", norm_mode="", n_bins=3, want_host=True, meta_data=None, meta_header=None, make_onehot=True):
         """normalize_data(data; test_name | norm_mode) of the reference (src/preprocessing.jl:660-684) for a dense [n, p] table of
         counts without meta variables.  The normalised table stays resident as the engine's table (ready for cor / pairwise /
         HITON-PC with the matching test kind); returns dict(data=[n', p'] array or None, col_mask, obs_filter_mask, kind)."""
@@ -286,7 +286,17 @@ class Engine:
                 out = np.empty((self.p, self.n), np.int32)
                 self._ck(self.L.fw_get_data_i32(self.h, _p(out), self.n))
             out = out.T
-        return {"data": out, "col_mask": cmask.astype(bool), "obs_filter_mask": rmask.astype(bool), "kind": self.kind}
+        res = {"data": out, "col_mask": cmask.astype(bool), "obs_filter_mask": rmask.astype(bool), "kind": self.kind,
+               "meta_mask": np.zeros(self.p, bool), "meta_names": []}
+        if meta_data is not None and self.n > 0 and self.p > 0:
+            # meta variables (preprocessing.jl:418-446, 523-556) are host-side factor handling: the normalised OTU table comes back
+            # once, the prepared meta columns are appended, and the combined table becomes the resident one
+            from . import meta as _meta
+            table = out if out is not None else self.get_data()
+            comb, mmask, mnames = _meta.combine_with_meta(table, res["obs_filter_mask"], meta_data, meta_header, mode, make_onehot)
+            self.set_data(comb, self.kind)
+            res.update(data=comb if want_host else None, meta_mask=mmask, meta_names=mnames)
+        return res
 
     def set_data_csc(self, colptr, rowval, nzval, n, p, kind):
         """SparseMatrixCSC{T,Int64} triple (0-based here; the Julia glue sets index base 1) of an n x p table."""

@@ -118,3 +118,19 @@ def prepare_meta(columns, names, norm, obs_filter_mask=None, make_onehot=True, n
     if names:
         names = [nm for nm, k in zip(names, keep) if k]
     return mat, names
+
+
+INTERNAL_NORM = {"tss": "rows", "clr-adapt": "clr_adapt", "clr-nonzero": "clr_nz", "pres-abs": "binary",
+                 "clr-nonzero-binned": "binned_nz_clr", "tss-nonzero-binned": "binned_nz_rows"}          # preprocessing.jl:666-668
+
+
+def combine_with_meta(norm_table, obs_filter_mask, meta_columns, meta_header, norm_mode, make_onehot=True):
+    """hcat(data, meta_data) of preprocess_data (preprocessing.jl:549-556): the normalised OTU table [n', p'] followed by the
+    prepared meta variables, in the table's element type (Float32 / Int32).  Returns (combined [n', p' + q'], meta_mask, meta_names)."""
+    mat, names = prepare_meta(meta_columns, meta_header, INTERNAL_NORM[norm_mode], obs_filter_mask=obs_filter_mask, make_onehot=make_onehot)
+    norm_table = np.asarray(norm_table)
+    if mat.shape[0] != norm_table.shape[0]:
+        raise ValueError("meta data has %d samples after filtering, the table %d" % (mat.shape[0], norm_table.shape[0]))
+    combined = np.concatenate([norm_table, mat.astype(norm_table.dtype)], axis=1)
+    meta_mask = np.concatenate([np.zeros(norm_table.shape[1], bool), np.ones(mat.shape[1], bool)])
+    return combined, meta_mask, names

@@ -61,7 +61,9 @@ def main():
     raw = [l.rstrip("\n").split("\t") for l in open(os.path.join(D, "HMP_SRA_gut", "HMP_SRA_gut_tiny_meta_oneHotTest.tsv"))]
     exp_oh = [l.rstrip("\n").split("\t") for l in open(os.path.join(pe, "meta_tiny_oneHotTest.tsv"))]
     with open(os.path.join(OUT, "meta_onehot.json"), "w") as f:
-        json.dump({"header": raw[0], "columns": [[conv(r[j]) for r in raw[1:]] for j in range(len(raw[0]))],
+        tiny = [l.rstrip("\n").split("\t") for l in open(os.path.join(D, "HMP_SRA_gut", "HMP_SRA_gut_tiny.tsv"))]
+        json.dump({"counts": [[int(v) for v in r] for r in tiny[1:]],
+                   "header": raw[0], "columns": [[conv(r[j]) for r in raw[1:]] for j in range(len(raw[0]))],
                    "expected_header": exp_oh[0], "expected": [[float(v) for v in r] for r in exp_oh[1:]]}, f)
 
     exp = {}

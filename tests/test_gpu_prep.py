@@ -136,3 +136,33 @@ def test_sparse_csc_input(fw, fx):
             fw.Engine(0).set_data_csc(m.indptr, m.indices + n, m.data, n, p, kind)       # rows out of range
         with pytest.raises(fw.FwError):
             fw.Engine(0).set_data_csc(m.indptr + 1, m.indices, m.data, n, p, kind)       # colptr[0] != index base
+
+
+def test_meta_variables(fw, golden_dir):
+    """test/preprocessing.jl:144-185 through Engine.normalize_data: OTU counts normalised on the device, meta variables one-hot
+    encoded / discretised / shifted on the host and appended; the combined table is the resident one."""
+    fxm = json.load(open(os.path.join(golden_dir, "meta_onehot.json")))
+    counts = np.array(fxm["counts"], dtype=np.float64)
+    exp = np.array(fxm["expected"])
+    meta = fwload.load_sub("meta")
+    for tn in ("fz", "mi", "fz_nz", "mi_nz"):
+        eng = fw.Engine(0)
+        got = eng.normalize_data(counts, test_name=tn, meta_data=fxm["columns"], meta_header=fxm["header"])
+        data, mm, rm = got["data"], got["meta_mask"], got["obs_filter_mask"]
+        assert got["meta_names"] == fxm["expected_header"] and mm.sum() == len(fxm["expected_header"])
+        A = data[:, mm][:, :-1].astype(np.float64)
+        if tn == "fz_nz":
+            A -= 1                                      # the +1 shift of one-hot variables in the zero-ignoring mode
+        assert (A == exp[rm][:, :-1]).all(), tn
+        if tn.startswith("mi"):
+            assert len(np.unique(data[:, -1])) == 2
+        # the same combination from the oracle's normalisation
+        w = prep.normalize(counts, test_name=tn)
+        inv = {v: k for k, v in prep.MODE_MAP.items()}
+        wc, wm, wn = meta.combine_with_meta(w[0], w[2], fxm["columns"], fxm["header"], inv[prep.DEFAULT_NORM[tn]])
+        assert data.shape == wc.shape and (mm == wm).all()
+        assert np.allclose(data, wc, rtol=2e-6, atol=1e-6)
+        # resident table = returned table; the hot path runs on it
+        assert eng.p == data.shape[1] and eng.n == data.shape[0]
+        assert (eng.get_data() == data).all()
+        eng.LGL(max_k=0)
