@@ -164,6 +164,23 @@ static int ensure_nz_table(fw_ctx* ctx, NzTable* t) {
     return FW_OK;
 }
 
+// longest jobs first: stable order of `sel` by descending candidate count (hoff[t + 1] - hoff[t]); a counting sort, because
+// this runs on the host in front of every HITON launch (50 000 targets at C4) while the GPU waits
+static void sort_by_candidates_desc(std::vector<int>& sel, const std::vector<i64>& hoff) {
+    i64 mx = 0;
+    for (int t : sel) mx = std::max<i64>(mx, hoff[t + 1] - hoff[t]);
+    if (mx > (i64)4 * (i64)sel.size() + 1024) {                                  // sparse key range: comparison sort
+        std::stable_sort(sel.begin(), sel.end(), [&](int x, int y) { return (hoff[x + 1] - hoff[x]) > (hoff[y + 1] - hoff[y]); });
+        return;
+    }
+    std::vector<i64> start((size_t)mx + 2, 0);
+    for (int t : sel) start[(size_t)(mx - (hoff[t + 1] - hoff[t])) + 1]++;       // bucket b = mx - count: descending count
+    for (size_t b = 1; b < start.size(); ++b) start[b] += start[b - 1];
+    std::vector<int> out(sel.size());
+    for (int t : sel) out[(size_t)start[(size_t)(mx - (hoff[t + 1] - hoff[t]))]++] = t;
+    sel.swap(out);
+}
+
 // ---- capacity classes shared by the subset-search and HITON launches -------------------------
 static const int kCaps[4] = {32, 64, 128, 224};
 static size_t hiton_smem_bytes(int cap, bool r_in_smem, int nz_words = -1, bool cache = false) {
@@ -1078,7 +1095,7 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         ma.num_tests = dnt.ptr; ma.executed_total = ctx->d_exec.ptr; ma.status = dstatus.ptr;
         std::vector<int> sel(n_targets);
         std::iota(sel.begin(), sel.end(), 0);
-        std::stable_sort(sel.begin(), sel.end(), [&](int x, int y) { return (hoff[x + 1] - hoff[x]) > (hoff[y + 1] - hoff[y]); });
+        sort_by_candidates_desc(sel, hoff);
         i64 need = 2; for (i64 t = 0; t < n_targets; ++t) need = std::max<i64>(need, hoff[t + 1] - hoff[t] + 2);
         const int TH = 256; const int L = ma.t.L;
         const size_t tabs = (size_t)(TH / 32) * L * L * L * L * L * sizeof(int) + (size_t)(TH / 32) * MI_BIN_WARP_BYTES;   // + count buffers of the batched binary scan
@@ -1136,7 +1153,7 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         if (pending[c].empty()) continue;
         std::vector<int>& sel = pending[c];
         // longest jobs first (candidate count is the work proxy)
-        std::stable_sort(sel.begin(), sel.end(), [&](int x, int y) { return (hoff[x + 1] - hoff[x]) > (hoff[y + 1] - hoff[y]); });
+        sort_by_candidates_desc(sel, hoff);
         int n_sel = (int)sel.size();
         CK(cudaMemcpyAsync(dsel.ptr, sel.data(), sizeof(int) * n_sel, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ctx->d_counter.ptr, 0, sizeof(int), ctx->stream));
