@@ -81,3 +81,25 @@ def test_edgelist_format(fw, tmp_path):
     assert lines[2] == "X4\tX7\t0.1891748160123825" and lines[3] == "X4\tX14\t-0.31248563528060913" and lines[4] == ""
     fw.write_edgelist(str(path), [(0, 1, 1.0)], header=["a", "b", "m"], meta_mask=[False, False, True])
     assert open(path).read() == "# header\ta,b,m\n# meta mask\tfalse,false,true\na\tb\t1.0\n"
+
+
+def test_c_host_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    """include/fwgpu.h is plain C99; examples/fw_demo.c (the ccall sequence of INTEGRATION.md written in C) compiles with
+    -pedantic, links against libfwgpu.so, and either runs (GPU present) or stops at fw_create with the no-fallback message."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "fw_demo")
+    libdir = os.path.join(root, "flashweave.jl_b200")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "examples", "fw_demo.c"), "-L" + libdir, "-lfwgpu", "-Wl,-rpath," + libdir, "-lm", "-o", exe],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    if r.returncode == 0:
+        assert "conditional tests" in r.stdout
+    else:
+        assert r.returncode == 1 and "no CPU fallback" in r.stdout, r.stdout
