@@ -102,6 +102,14 @@ static int fail(fw_ctx* c, int code, const char* fmt, ...) {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 #define NEED(cond, code, ...) do { if (!(cond)) return fail(ctx, code, __VA_ARGS__); } while (0)
 
+// a new resident table invalidates everything derived from the previous one: cor_mat, the standardised split table, the
+// non-zero planes and the univariate neighbour lists (fw_hiton_pc / fw_pairwise_copy then fail with FW_ERR_STATE instead of
+// silently running against the lists of another table)
+static void table_changed(fw_ctx* c) {
+    c->nz_ready = false; c->tcp.valid = false; c->cor_p = 0;
+    c->uni_entries = -1; c->h_uni_off.clear();
+}
+
 static FzConsts make_fz_consts(i64 n_rows, i64 n_obs_min) {
     FzConsts fc;
     i64 sf = n_rows - 0 - 3;                 // len_z is hard-coded 0 (src/tests.jl:156,256)
@@ -343,16 +351,17 @@ int32_t fw_set_data_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, in
     CK(cudaSetDevice(ctx->device));
     CK(ctx->d_data_f32.reserve((size_t)n * p));
     CK(cudaMemcpy2DAsync(ctx->d_data_f32.ptr, n * sizeof(float), host, ld * sizeof(float), n * sizeof(float), p, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n; ctx->nz_ready = false;
-    ctx->cor_p = 0; ctx->tcp.valid = false;          // a resident cor_mat belongs to the previous table
+    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n;
+    table_changed(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));          // host pointers are borrowed for the duration of the call only (page-locked sources copy asynchronously)
     return FW_OK;
 }
 int32_t fw_adopt_data_f32_device(fw_ctx* ctx, const float* dev, int64_t n, int64_t p, int64_t ld) {
     if (!ctx) return FW_ERR_INVALID;
     NEED(dev && n > 0 && p > 0 && ld >= n, FW_ERR_INVALID, "fw_adopt_data_f32_device: bad arguments");
     ctx->d_data_f32.adopt(const_cast<float*>(dev), (size_t)ld * p);
-    ctx->n = n; ctx->p = p; ctx->ld = ld; ctx->data_kind = 0; ctx->n_obs = n; ctx->nz_ready = false;
-    ctx->cor_p = 0; ctx->tcp.valid = false;
+    ctx->n = n; ctx->p = p; ctx->ld = ld; ctx->data_kind = 0; ctx->n_obs = n;
+    table_changed(ctx);
     return FW_OK;
 }
 // get_levels / get_max_vals (src/misc.jl:64-97) and the bit-plane table of the level codes resident in ctx->d_data_i32 ([p][n])
@@ -385,6 +394,7 @@ static int install_discrete_table(fw_ctx* ctx, int64_t n, int64_t p, const char*
         CK(cudaGetLastError());
     }
     ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 1; ctx->n_obs = n;
+    table_changed(ctx);
     return FW_OK;
 }
 int32_t fw_set_data_i32(fw_ctx* ctx, const int32_t* host, int64_t n, int64_t p, int64_t ld) {
@@ -399,7 +409,8 @@ int32_t fw_set_data_csc_f32(fw_ctx* ctx, const int64_t* colptr, const int64_t* r
     if (!ctx) return FW_ERR_INVALID;
     int st_ = set_data_csc<float>(ctx, colptr, rowval, nzval, n, p, ctx->d_data_f32, "fw_set_data_csc_f32");
     if (st_ != FW_OK) return st_;
-    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n; ctx->nz_ready = false; ctx->tcp.valid = false; ctx->cor_p = 0;
+    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n;
+    table_changed(ctx);
     return FW_OK;
 }
 int32_t fw_set_data_csc_i32(fw_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const int32_t* nzval, int64_t n, int64_t p) {
@@ -488,7 +499,7 @@ int32_t fw_normalize_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, i
     for (int v : cols) cmask[v] = 1;
     i64 p2 = p1;
     if (n1 == 0 || p1 == 0) {
-        ctx->data_kind = -1; ctx->n = 0; ctx->p = 0;
+        ctx->data_kind = -1; ctx->n = 0; ctx->p = 0; table_changed(ctx);
         if (n_out) *n_out = 0; if (p_out) *p_out = 0;
         if (row_mask) memcpy(row_mask, rflag.data(), n);
         if (col_mask) memset(col_mask, 0, p);
@@ -505,7 +516,8 @@ int32_t fw_normalize_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, i
         prep_transform_kernel<<<grid, T, 0, st>>>(raw.ptr, n, dcols.ptr, drows.ptr, n1, norm, dsum32.ptr, dg.ptr, dpc.ptr, ctx->d_data_f32.ptr); ctx->launches++;
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));
-        ctx->n = n1; ctx->p = p1; ctx->ld = n1; ctx->data_kind = 0; ctx->n_obs = n1; ctx->nz_ready = false; ctx->tcp.valid = false; ctx->cor_p = 0;
+        ctx->n = n1; ctx->p = p1; ctx->ld = n1; ctx->data_kind = 0; ctx->n_obs = n1;
+        table_changed(ctx);
     } else {
         DevBuf<int> tmp; DevBuf<unsigned int> dseen;
         CK(tmp.reserve((size_t)n1 * p1)); CK(dseen.reserve(p1));
@@ -544,7 +556,7 @@ int32_t fw_normalize_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, i
         }
         p2 = (i64)colmap.size();
         if (p2 == 0) {
-            ctx->data_kind = -1; ctx->n = 0; ctx->p = 0;
+            ctx->data_kind = -1; ctx->n = 0; ctx->p = 0; table_changed(ctx);
             if (n_out) *n_out = n1; if (p_out) *p_out = 0;
             if (row_mask) memcpy(row_mask, rflag.data(), n);
             if (col_mask) memset(col_mask, 0, p);
@@ -592,6 +604,7 @@ int32_t fw_set_cor_f32(fw_ctx* ctx, const float* host_cor, int64_t p) {
     CK(ctx->d_cor.reserve((size_t)p * p));
     CK(cudaMemcpyAsync(ctx->d_cor.ptr, host_cor, sizeof(float) * (size_t)p * p, cudaMemcpyHostToDevice, ctx->stream));
     ctx->cor_p = p; if (ctx->p == 0) ctx->p = p;
+    CK(cudaStreamSynchronize(ctx->stream));          // the host buffer is borrowed for the duration of the call only
     return FW_OK;
 }
 int32_t fw_adopt_cor_device(fw_ctx* ctx, const float* dev_cor, int64_t p) {
@@ -623,7 +636,9 @@ int32_t fw_upload_cor_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, 
     ctx->launches += nl;
     if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_upload_cor_f32: %s: %s", msg.c_str(), cudaGetErrorString(e));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_valid[0] = true;
-    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n; ctx->nz_ready = false; ctx->cor_p = p; ctx->tcp.valid = false;
+    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n;
+    table_changed(ctx); ctx->cor_p = p;
+    CK(cudaStreamSynchronize(ctx->copy_stream));     // every chunk has left the (borrowed) host buffer; the GEMM tail may still be running
     if (host_out) {
         CK(cudaMemcpyAsync(host_out, ctx->d_cor.ptr, sizeof(float) * (size_t)p * p, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -921,6 +936,7 @@ int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_
                             ctx->sm_count, ctx->stream, &po, &nl, &msg);
     }
     ctx->launches += nl;
+    if (e != cudaSuccess && msg.find("unsupported size") != std::string::npos) return fail(ctx, FW_ERR_UNSUPPORTED, "fw_pairwise: %s", msg.c_str());
     if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_pairwise: %s: %s", msg.c_str(), cudaGetErrorString(e));
     CK(cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->ev_valid[1] = true;
     // adopt the CSR

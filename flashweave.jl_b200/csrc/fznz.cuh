@@ -9,8 +9,15 @@
 // on the rows where X != 0 and Y != 0, and n for fz_pval is the number of those rows.  Here the row view is a
 // bit mask (AND of two precomputed non-zero planes), the sub-matrix is recomputed per job into the same
 // shared-memory block R that the plain Fisher-z kernels gather from cor_mat, and the tests themselves are the
-// unchanged pcor_rec code of fz.cuh.  Moments are accumulated in fp64 in two passes (mean, then centred
-// products) like Statistics.cor, and the result is rounded to Float32 (cor_mat's eltype, learning.jl:127-129).
+// unchanged pcor_rec code of fz.cuh.
+//
+// Canonical summation (shared with oracle/fw_oracle.cpp::cor_view, operation for operation, so the Float32 correlations are
+// bit-equal on both sides): every variable is shifted by its value in the FIRST row of the view; the raw moments
+// G_ab = sum x'_a x'_b and S_a = sum x'_a are accumulated with fma in increasing row order in 8 interleaved partial sums
+// (class = row index mod 8), the partials are added in order 0..7 starting from 0.0; c_ab = G_ab - (S_a*S_b)/n and
+// r_ab = c_ab / (sqrt(c_aa)*sqrt(c_bb)) with individually rounded operations, clamped to [-1, 1] and rounded to Float32
+// (cor_mat's eltype, learning.jl:127-129).  All three code paths below (register-blocked Gram, pair items of the large
+// capacity classes, the univariate warp) produce exactly these partial sums.
 #pragma once
 #include "common.cuh"
 #include "fz.cuh"
@@ -44,6 +51,18 @@ __device__ __forceinline__ FzConsts nz_consts(i64 rows, i64 n_obs_min) {
 
 // ---- univariate test, one warp (tests.jl:108-160 on the X-trimmed view of tests.jl:412-416) ----------------
 struct NzUni { double stat; double pval; bool suff; };
+// canonical correlation from the combined moments (see the header): NaN passes through
+__device__ __forceinline__ double fznz_r_from_moments(double gaa, double gbb, double gab, double sa, double sb, double n) {
+    const double caa = __dsub_rn(gaa, __ddiv_rn(__dmul_rn(sa, sa), n));
+    const double cbb = __dsub_rn(gbb, __ddiv_rn(__dmul_rn(sb, sb), n));
+    const double cab = __dsub_rn(gab, __ddiv_rn(__dmul_rn(sa, sb), n));
+    double rr = __ddiv_rn(cab, __dmul_rn(__dsqrt_rn(caa), __dsqrt_rn(cbb)));
+    if (rr > 1.0) rr = 1.0; else if (rr < -1.0) rr = -1.0;             // clampcor; NaN passes through
+    return rr;
+}
+// One pass over the rows where X != 0 and Y != 0.  Lane (c = lane & 7, j = lane >> 3) accumulates class c (row mod 8) of one
+// moment: j = 0: Sx (and Sy in a second register), 1: Sxx, 2: Syy, 3: Sxy.  Per 32-row word every lane loads its own row
+// (coalesced) and the four rows of a class reach their lane by shuffles, in increasing row order.
 __device__ NzUni fznz_uni_warp(const NzTable& t, i64 X, i64 Y, i64 n_obs_min) {
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
@@ -52,23 +71,43 @@ __device__ NzUni fznz_uni_warp(const NzTable& t, i64 X, i64 Y, i64 n_obs_min) {
     if (rows_x < n_obs_min) { r.stat = 0.0; r.pval = 1.0; r.suff = (0 >= n_obs_min); return r; }     // tests.jl:111-115,159
     const float* x = t.data + X * t.ld; const float* y = t.data + Y * t.ld;
     const unsigned int* mx = t.nzmask + X * t.W; const unsigned int* my = t.nzmask + Y * t.W;
-    int cnt = 0;
-    for (int w = lane; w < t.W; w += 32) cnt += __popc(mx[w] & my[w]);
+    int cnt = 0, first = 0x7fffffff;
+    for (int w = lane; w < t.W; w += 32) {
+        const unsigned int m = mx[w] & my[w];
+        cnt += __popc(m);
+        if (m && first == 0x7fffffff) first = w * 32 + __ffs(m) - 1;
+    }
     const i64 n_obs = __reduce_add_sync(full, cnt);
+    first = __reduce_min_sync(full, first);
     double p_stat = 0.0;
     if (n_obs > 0 && n_obs >= n_obs_min) {
-        double sx = 0.0, sy = 0.0;
-        for (int i = lane; i < t.n; i += 32) { float a = x[i], b = y[i]; if (a != 0.0f && b != 0.0f) { sx += (double)a; sy += (double)b; } }
-        for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(full, sx, o); sy += __shfl_xor_sync(full, sy, o); }
-        const double mxv = sx / (double)n_obs, myv = sy / (double)n_obs;
-        double sxx = 0.0, syy = 0.0, sxy = 0.0;
-        for (int i = lane; i < t.n; i += 32) {
-            float a = x[i], b = y[i];
-            if (a != 0.0f && b != 0.0f) { double da = (double)a - mxv, db = (double)b - myv; sxx += da * da; syy += db * db; sxy += da * db; }
+        const double cx = (double)x[first], cy = (double)y[first];
+        const int c = lane & 7, j = lane >> 3;
+        double acc = 0.0, acc2 = 0.0;
+        for (int w = 0; w < t.W; ++w) {
+            const unsigned int m = mx[w] & my[w];                        // warp-uniform
+            if (!m) continue;
+            const int row = w * 32 + lane;
+            const float a = row < t.n ? x[row] : 0.0f, b = row < t.n ? y[row] : 0.0f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int src = c + 8 * q;
+                const float aq = __shfl_sync(full, a, src), bq = __shfl_sync(full, b, src);
+                if ((m >> src) & 1u) {
+                    const double da = __dsub_rn((double)aq, cx), db = __dsub_rn((double)bq, cy);
+                    const double u = (j == 2) ? db : da;
+                    const double v = (j == 0) ? 1.0 : ((j == 1) ? da : db);
+                    acc = fma(u, v, acc);
+                    acc2 = fma(db, 1.0, acc2);
+                }
+            }
         }
-        for (int o = 16; o > 0; o >>= 1) { sxx += __shfl_xor_sync(full, sxx, o); syy += __shfl_xor_sync(full, syy, o); sxy += __shfl_xor_sync(full, sxy, o); }
-        double rr = sxy / (sqrt(sxx) * sqrt(syy));
-        if (rr > 1.0) rr = 1.0; else if (rr < -1.0) rr = -1.0;         // clampcor; NaN passes through (tests.jl:143, :381)
+        double tot = 0.0, tot2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { tot += __shfl_sync(full, acc, (lane & 24) + k); tot2 += __shfl_sync(full, acc2, (lane & 24) + k); }
+        const double sx = __shfl_sync(full, tot, 0), sy = __shfl_sync(full, tot2, 0);
+        const double sxx = __shfl_sync(full, tot, 8), syy = __shfl_sync(full, tot, 16), sxy = __shfl_sync(full, tot, 24);
+        const double rr = fznz_r_from_moments(sxx, syy, sxy, sx, sy, (double)n_obs);      // NaN passes through (tests.jl:143, :381)
         p_stat = (double)(float)rr;                                      // eltype of the data (Float32)
     }
     r.stat = p_stat;
@@ -96,7 +135,8 @@ constexpr int FZNZ_GRAM_BYTES = (FZNZ_TROWS * FZNZ_TLD + 8) * 8 + FZNZ_GMAX * FZ
 
 template <int THREADS>
 __device__ void fznz_gram_block(const float* __restrict__ data, i64 ldv, int n, int W, const i64* var, int nv, int rows,
-                                float* R, int ld, const unsigned int* mask, unsigned int buf_off) {
+                                float* R, int ld, const unsigned int* mask, unsigned int buf_off, const double* piv) {
+    static_assert(THREADS == 256, "canonical summation: 8 warps = 8 row classes (row index mod 8), see the header");
     extern __shared__ __align__(16) unsigned char smem[];      // buf_off: offset of the scratch from the dynamic shared-memory base (keeps LDS/STS)
     unsigned char* buf = smem + buf_off;
     constexpr int B = 4;
@@ -153,7 +193,7 @@ __device__ void fznz_gram_block(const float* __restrict__ data, i64 ldv, int n, 
 #pragma unroll
             for (int k = 0; k < PF; ++k) {
                 const int e = tid + k * THREADS;
-                if (e < n_stage) tile[(e % FZNZ_TROWS) * FZNZ_TLD + e / FZNZ_TROWS] = (double)pf[k];
+                if (e < n_stage) tile[(e % FZNZ_TROWS) * FZNZ_TLD + e / FZNZ_TROWS] = __dsub_rn((double)pf[k], piv[e / FZNZ_TROWS]);
             }
             __syncthreads();
             const int r1 = next_tile(r0 + FZNZ_TROWS);
@@ -198,15 +238,11 @@ __device__ void fznz_gram_block(const float* __restrict__ data, i64 ldv, int n, 
         }
     }
     __syncthreads();
-    const double inv_n = 1.0 / (double)rows;
     const int n_pairs = nv * (nv - 1) / 2;
     for (int e = tid; e < n_pairs; e += THREADS) {
         int a, b; unrank2_small(e, nv, a, b);
-        const double sa = G[a * FZNZ_GMAX + nv], sb = G[b * FZNZ_GMAX + nv];
-        const double caa = G[a * FZNZ_GMAX + a] - sa * sa * inv_n, cbb = G[b * FZNZ_GMAX + b] - sb * sb * inv_n;
-        const double cab = G[a * FZNZ_GMAX + b] - sa * sb * inv_n;
-        double rr = cab / (sqrt(caa) * sqrt(cbb));
-        if (rr > 1.0) rr = 1.0; else if (rr < -1.0) rr = -1.0;
+        const double rr = fznz_r_from_moments(G[a * FZNZ_GMAX + a], G[b * FZNZ_GMAX + b], G[a * FZNZ_GMAX + b],
+                                              G[a * FZNZ_GMAX + nv], G[b * FZNZ_GMAX + nv], (double)rows);
         const float rf = isnan(rr) ? 0.0f : (float)rr;                                   // statfuns.jl:150: NaN -> 0; cor_mat eltype Float32
         R[a * ld + b] = rf; R[b * ld + a] = rf;
     }
@@ -222,52 +258,67 @@ __device__ int fznz_subcor_block(const NzTable& t, const i64* var, int nv, int x
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
     const unsigned int* mx = t.nzmask + var[xs] * t.W; const unsigned int* my = t.nzmask + var[ys] * t.W;
-    if (tid == 0) *s_cnt = 0;
+    if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0x7fffffff; }              // rows of the view, first row of the view
     __syncthreads();
-    int c = 0;
-    for (int w = tid; w < t.W; w += THREADS) { unsigned int m = mx[w] & my[w]; mask[w] = m; c += __popc(m); }
+    int c = 0, first = 0x7fffffff;
+    for (int w = tid; w < t.W; w += THREADS) {
+        unsigned int m = mx[w] & my[w]; mask[w] = m; c += __popc(m);
+        if (m && first == 0x7fffffff) first = w * 32 + __ffs(m) - 1;
+    }
     c = __reduce_add_sync(full, c);
-    if (lane == 0 && c) atomicAdd(s_cnt, c);
+    first = __reduce_min_sync(full, first);
+    if (lane == 0 && c) { atomicAdd(&s_cnt[0], c); atomicMin(&s_cnt[1], first); }
     __syncthreads();
-    const int rows = *s_cnt;
+    const int rows = s_cnt[0];
     if (rows == 0) {                                    // empty view: every correlation is NaN -> 0 (statfuns.jl:150)
         for (int e = tid; e < nv * nv; e += THREADS) R[(e / nv) * ld + (e % nv)] = 0.0f;
         __syncthreads();
         return 0;
     }
+    const int row0 = s_cnt[1];
     if (nv <= FZNZ_NVMAX) {
+        // pivots (the variables' values in the first row of the view) in mom[0..nv)
+        for (int a = tid; a < nv; a += THREADS) mom[a] = (double)__ldg(t.data + var[a] * t.ld + row0);
         extern __shared__ __align__(16) unsigned char smem[];
         const unsigned int off = (((unsigned int)__cvta_generic_to_shared(mask + t.W) + 15u) & ~15u) - (unsigned int)__cvta_generic_to_shared(smem);
-        fznz_gram_block<THREADS>(t.data, t.ld, t.n, t.W, var, nv, rows, R, ld, mask, off);
+        fznz_gram_block<THREADS>(t.data, t.ld, t.n, t.W, var, nv, rows, R, ld, mask, off, mom);   // (its first barrier publishes the pivots)
         return rows;
     }
-    // larger capacity classes: one warp per variable for the moments, one warp per slot pair for the cross products
-    // means and centred norms: one warp per variable, two passes (Statistics.cor: corm -> covzm)
-    for (int a = warp; a < nv; a += THREADS / 32) {
-        const float* x = t.data + var[a] * t.ld;
-        double s = 0.0;
-        for (int i = lane; i < t.n; i += 32) if ((mask[i >> 5] >> (i & 31)) & 1u) s += (double)x[i];
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(full, s, o);
-        const double mu = s / (double)rows;
-        double ss = 0.0;
-        for (int i = lane; i < t.n; i += 32) if ((mask[i >> 5] >> (i & 31)) & 1u) { double d = (double)x[i] - mu; ss += d * d; }
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(full, ss, o);
-        if (lane == 0) { mom[2 * a] = mu; mom[2 * a + 1] = sqrt(ss); }
+    // larger capacity classes: the same canonical partial sums, one (item, class) per lane - 4 items per warp, lane (j = lane >> 3,
+    // c = lane & 7) walks the rows of class c (row mod 8) of item j in increasing order.  First the per-variable moments
+    // (S_a, G_aa) into mom[2a], mom[2a+1], then one item per slot pair (a < b).
+    const int cls = lane & 7, sub = lane >> 3;
+    auto item_sum = [&](const float* xa, double pa, const float* xb, double pb) {        // xb == nullptr: the ones column
+        double acc = 0.0;
+        for (int row = cls; row < t.n; row += 8) {
+            if (!((mask[row >> 5] >> (row & 31)) & 1u)) continue;
+            const double da = __dsub_rn((double)xa[row], pa);
+            const double db = xb ? __dsub_rn((double)xb[row], pb) : 1.0;
+            acc = fma(da, db, acc);
+        }
+        double tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot += __shfl_sync(full, acc, (lane & 24) + k);
+        return tot;
+    };
+    for (int it = warp * 4 + sub; it < ((2 * nv + 3) & ~3); it += (THREADS / 32) * 4) {   // item 2a: S_a, item 2a+1: G_aa (padded to whole warps)
+        const bool live = it < 2 * nv;
+        const int a = live ? it >> 1 : 0;
+        const float* xa = t.data + var[a] * t.ld;
+        const double pa = (double)xa[row0];
+        const double v = item_sum(xa, pa, (it & 1) ? xa : nullptr, pa);
+        if (live && cls == 0) mom[it] = v;
     }
     __syncthreads();
-    // centred cross products: one warp per slot pair (a < b)
     const int n_pairs = nv * (nv - 1) / 2;
-    for (int e = warp; e < n_pairs; e += THREADS / 32) {
-        int a, b; unrank2(e, nv, a, b);
+    for (int e = warp * 4 + sub; e < ((n_pairs + 3) & ~3); e += (THREADS / 32) * 4) {
+        const bool live = e < n_pairs;
+        int a = 0, b = 1; if (live) unrank2(e, nv, a, b);
         const float* xa = t.data + var[a] * t.ld; const float* xb = t.data + var[b] * t.ld;
-        const double ma = mom[2 * a], mb = mom[2 * b];
-        double s = 0.0;
-        for (int i = lane; i < t.n; i += 32) if ((mask[i >> 5] >> (i & 31)) & 1u) s += ((double)xa[i] - ma) * ((double)xb[i] - mb);
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(full, s, o);
-        if (lane == 0) {
-            double rr = s / (mom[2 * a + 1] * mom[2 * b + 1]);
-            if (rr > 1.0) rr = 1.0; else if (rr < -1.0) rr = -1.0;
-            float rf = isnan(rr) ? 0.0f : (float)rr;                    // statfuns.jl:150: NaN -> 0; cor_mat eltype Float32
+        const double gab = item_sum(xa, (double)xa[row0], xb, (double)xb[row0]);
+        if (live && cls == 0) {
+            const double rr = fznz_r_from_moments(mom[2 * a + 1], mom[2 * b + 1], gab, mom[2 * a], mom[2 * b], (double)rows);
+            const float rf = isnan(rr) ? 0.0f : (float)rr;                    // statfuns.jl:150: NaN -> 0; cor_mat eltype Float32
             R[a * ld + b] = rf; R[b * ld + a] = rf;
         }
     }
@@ -304,7 +355,7 @@ __global__ void __launch_bounds__(THREADS) fznz_test_batch_kernel(NzTable t, i64
     __shared__ float R[25];
     __shared__ double mom[10];
     __shared__ i64 var[5];
-    __shared__ int s_cnt;
+    __shared__ int s_cnt[2];
     for (i64 tix = blockIdx.x; tix < n_tests; tix += gridDim.x) {
         __syncthreads();
         const int kk = k[tix];
@@ -317,7 +368,7 @@ __global__ void __launch_bounds__(THREADS) fznz_test_batch_kernel(NzTable t, i64
         }
         if (threadIdx.x == 0) { var[0] = X[tix]; var[1] = Y[tix]; for (int j = 0; j < 3; ++j) var[2 + j] = j < kk ? Zs[tix * 3 + j] : X[tix]; }
         __syncthreads();
-        const int rows = fznz_subcor_block<THREADS>(t, var, kk + 2, 0, 1, R, 5, mask, mom, &s_cnt);
+        const int rows = fznz_subcor_block<THREADS>(t, var, kk + 2, 0, 1, R, 5, mask, mom, s_cnt);
         if (threadIdx.x == 0) {
             // tests.jl:250-265 on the (X, Y)-trimmed view: n = rows of the view
             FzConsts fc = nz_consts(rows, n_obs_min);

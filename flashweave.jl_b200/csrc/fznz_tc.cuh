@@ -6,9 +6,14 @@
 //     n   = sum m_x m_y      Sx  = sum x m_y      Sxx = sum x^2 m_y      Sxy = sum x y
 //                            Sy  = sum m_x y      Syy = sum m_x y^2
 // i.e. six p x p x n contractions of the three bf16 operand planes {M, X, X2} - tensor-core work.  bf16 operands give r to
-// ~1e-4, which is not the parity target, so this kernel only CLASSIFIES: a pair whose approximate |r| is within a safety band
-// of the significance threshold (or above it), or whose view variance is suspiciously small (r may be NaN), goes to the exact
-// fp64 warp-per-pair kernel (fznz_uni_warp); all others are provably-not-significant and are only counted.  Counts (n, exact:
+// ~1e-4, which is not the parity target, so this kernel only CLASSIFIES.  From the worst-case rounding errors of the operands
+// (bf16: |dx'| <= 2^-9 |x'|, the x'^2 plane 3 * 2^-9, a product x'y' 2 * 2^-9; Cauchy-Schwarz turns sums of |x'| into
+// sqrt(n Sxx)) and of the truncating fp32 accumulation it derives an interval for each view variance and for the covariance,
+//     vx in [vx~ - ex, .],  ex = (E2 + T) qx + 2 |mx| (E1 + T) sqrt(qx),   qx = Sxx / n
+//     |cov| <= |cov~| + ec, ec = (E3 + T) sqrt(qx qy) + (E1 + T) (|mx| sqrt(qy) + |my| sqrt(qx)),
+// and a pair is dismissed only if the resulting UPPER bound of |r| is below the significance threshold; a pair whose variance
+// interval reaches zero (r may be NaN or arbitrarily ill-conditioned: few shared rows far from the column mean, constant
+// columns) always goes to the exact fp64 warp-per-pair test (fznz_uni_warp), as does every pair above the threshold.  Counts (n, exact:
 // sums of 0/1 products in fp32) decide the "too few rows" cases exactly as the reference does.  The resulting neighbour lists are
 // identical to the exhaustive exact kernel (tests/test_gpu_fznz.py compares both), at ~3 % of its fp64 work.
 //
@@ -33,7 +38,6 @@ constexpr int STAGE_BYTES = 3 * A_TILE + 3 * B_TILE;   // 72 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 constexpr int NTHREADS = 192;
 constexpr int TC_GROUP = 8;                            // X blocks per rasterisation group
-constexpr float VAR_EPS = 0.02f;                        // planes have unit variance over a variable's non-zero rows
 
 // one CTA per variable: mean / sd over the non-zero rows (fixed-order reductions: deterministic), then the three bf16 planes
 template <int THREADS>
@@ -92,6 +96,7 @@ struct PrefilterArgs {
     const int* nnz;                             // per-variable non-zero count (rows of the X-trimmed view, tests.jl:412-416)
     i64 n_obs_min; int reliable_only;
     float z_alpha;                              // two-sided normal quantile of alpha: p < alpha  <=>  sqrt(n-3) * atanh|r| > z_alpha
+    float trunc_rel;                            // T: bound of the accumulated truncation of the fp32 TMEM accumulators, relative to sum |terms|
     u64* counters;                              // [0] candidates appended, [1] pairs counted reliable here (non-candidates)
     i64 cand_cap; int* cand_x; int* cand_y;
 };
@@ -220,11 +225,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fznz_prefilter_kernel(const __gri
                         const float mx = __uint_as_float(v[1][j]) * inv, my = __uint_as_float(v[2][j]) * inv;
                         const float vx = __uint_as_float(v[3][j]) * inv - mx * mx, vy = __uint_as_float(v[4][j]) * inv - my * my;
                         const float cov = __uint_as_float(v[5][j]) * inv - mx * my;
-                        const bool var_ok = vx > VAR_EPS && vy > VAR_EPS;
-                        const float r = fabsf(cov) * rsqrtf(fmaxf(vx * vy, 1e-30f));
+                        // error intervals (see the header); 1.02: the bounds use the computed moments in place of the true ones
+                        const float E1 = 1.02f / 512.0f + a.trunc_rel, E2 = 1.02f / 128.0f + a.trunc_rel, E3 = 1.02f / 256.0f + a.trunc_rel;
+                        const float qx = __uint_as_float(v[3][j]) * inv, qy = __uint_as_float(v[4][j]) * inv;
+                        const float sqx = sqrtf(qx), sqy = sqrtf(qy);
+                        const float lo_vx = vx - (E2 * qx + 2.0f * fabsf(mx) * E1 * sqx);
+                        const float lo_vy = vy - (E2 * qy + 2.0f * fabsf(my) * E1 * sqy);
+                        const float hi_cov = fabsf(cov) + E3 * sqx * sqy + E1 * (fabsf(mx) * sqy + fabsf(my) * sqx);
+                        const bool var_ok = lo_vx > 0.0f && lo_vy > 0.0f;
+                        const float r_hi = hi_cov * rsqrtf(fmaxf(lo_vx * lo_vy, 1e-30f)) * 1.0001f;   // fp32 evaluation of these formulas
                         const float thr = n > 3.5f ? tanhf(a.z_alpha * rsqrtf(n - 3.0f)) : 2.0f;   // n - 3 <= 0: the p-value is 1
-                        const float band = fmaxf(4e-3f, 0.1f * thr);
-                        cand = !var_ok || !(r < thr - band);                                      // NaN-safe: anything odd is a candidate
+                        cand = !var_ok || !(r_hi < thr * 0.999f);                                  // NaN-safe: anything odd is a candidate
                         if (!cand) n_rel += 1u;
                     }
                 }
@@ -334,6 +345,7 @@ static cudaError_t run_prefilter(Planes& P, const NzTable& t, i64 n_obs_min, dou
     a.p = p; a.num_kb = (int)(kp / BK); a.nb_a = (int)(p_pad / BM); a.nb_b = (int)(p_pad / BN);
     a.nnz = t.nnz; a.n_obs_min = n_obs_min; a.reliable_only = reliable_only ? 1 : 0;
     a.z_alpha = (float)(z_of_alpha(alpha) * (1.0 - 1e-6));
+    a.trunc_rel = (float)(2.0 * (double)(kp / 16) / 8388608.0);       // one truncation (< 2^-23 relative) per K = 16 accumulation, x2 margin
     a.counters = counters; a.cand_cap = cand_cap; a.cand_x = cand_x; a.cand_y = cand_y;
     long long tiles = 0;
     for (int r0 = 0; r0 < a.nb_a; r0 += TC_GROUP) tiles += (long long)(a.nb_b - 2 * r0) * std::min(TC_GROUP, a.nb_a - r0);

@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
     const FzTab tb = fz_tab_layout((int)o);      // only carved (and only valid) when CACHE
     __shared__ EvalShared sh;
     __shared__ EvalOut ev;
-    __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_cnt, s_spec;
+    __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_cnt[2], s_spec;
     __shared__ FzScanShared fsh;
     __shared__ i64 s_ntests;
     __shared__ u64 s_exec, s_exk[3];
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
                 bool run = true;
                 if constexpr (NZ) {
                     // cor_subset! on the rows where T != 0 and candidate != 0 (tests.jl:293-308; hiton.jl:41-50,85)
-                    const int rows = fznz_subcor_block<THREADS>(a.nzt, slotvar, M + 2, 0, ys, R, ld, vmask, mom, &s_cnt);
+                    const int rows = fznz_subcor_block<THREADS>(a.nzt, slotvar, M + 2, 0, ys, R, ld, vmask, mom, s_cnt);
                     run = !(a.n_obs_min > (i64)rows);                     // else (0, 1, 0, false), zero tests: rejected
                     tf.fc = nz_consts(rows, a.n_obs_min);
                 }
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
                 if constexpr (NZ) {
                     for (int s = tid; s <= M; s += THREADS) slotvar[s] = (s == 0) ? T : member[s - 1];
                     __syncthreads();
-                    const int rows = fznz_subcor_block<THREADS>(a.nzt, slotvar, M + 1, 0, c, R, ld, vmask, mom, &s_cnt);
+                    const int rows = fznz_subcor_block<THREADS>(a.nzt, slotvar, M + 1, 0, c, R, ld, vmask, mom, s_cnt);
                     run = !(a.n_obs_min > (i64)rows);
                     tf.fc = nz_consts(rows, a.n_obs_min);
                 }
@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(THREADS) subsets_fz_kernel(SubsetsArgs a) {
     unsigned int* vmask = reinterpret_cast<unsigned int*>(smem + o);
     __shared__ EvalShared sh;
     __shared__ EvalOut ev;
-    __shared__ int s_ji, s_cnt;
+    __shared__ int s_ji, s_cnt[2];
     float* R;
     if constexpr (GS) R = a.gscratch + (size_t)blockIdx.x * cap * cap; else R = Rs;
     const int ld = cap;
@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(THREADS) subsets_fz_kernel(SubsetsArgs a) {
         } else {
             for (int s = tid; s < nv; s += THREADS) slotvar[s] = s == 0 ? a.X[job] : (s == 1 ? a.Y[job] : a.z_idx[z0 + s - 2]);
             __syncthreads();
-            const int rows = fznz_subcor_block<THREADS>(a.nzt, slotvar, nv, 0, 1, R, ld, vmask, mom, &s_cnt);
+            const int rows = fznz_subcor_block<THREADS>(a.nzt, slotvar, nv, 0, 1, R, ld, vmask, mom, s_cnt);
             if (a.n_obs_min > (i64)rows) {                                  // tests.jl:293-296
                 if (tid == 0) {
                     a.out[job] = make_result(0.0, 1.0, 0, false);

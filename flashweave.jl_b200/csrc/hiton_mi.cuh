@@ -528,6 +528,7 @@ static cudaError_t pairwise_mi_run(PairwiseScratch& S, const MiTable& t, i64 hps
     pw_pair_keys<<<pw_blocks(nf, T), T, 0, st>>>(c_x, c_y, p, keys, vals, nf); (*n_launch)++;
     int end_bit = 1; while (((u64)1 << end_bit) < (u64)p * (u64)p && end_bit < 64) ++end_bit;
     void* tmp = nullptr; size_t need = 0;
+    if (nf >= ((i64)1 << 31) - 1) { if (msg) *msg = "more than 2^31 raw-significant pairs are not supported (unsupported size)"; return cudaErrorInvalidValue; }
     cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys2, vals, vals2, (int)nf, 0, end_bit, st);
     PWCK(S.get(5, need, &tmp), "alloc");
     PWCK(cub::DeviceRadixSort::SortPairs(tmp, need, keys, keys2, vals, vals2, (int)nf, 0, end_bit, st), "sort"); (*n_launch) += 8;
@@ -619,6 +620,7 @@ static cudaError_t pairwise_fznz_run(PairwiseScratch& S, fznztc::Planes& planes,
     pw_pair_keys<<<pw_blocks(nf, T), T, 0, st>>>(c_x, c_y, p, keys, vals, nf); (*n_launch)++;
     int end_bit = 1; while (((u64)1 << end_bit) < (u64)p * (u64)p && end_bit < 64) ++end_bit;
     void* tmp = nullptr; size_t need = 0;
+    if (nf >= ((i64)1 << 31) - 1) { if (msg) *msg = "more than 2^31 raw-significant pairs are not supported (unsupported size)"; return cudaErrorInvalidValue; }
     cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys2, vals, vals2, (int)nf, 0, end_bit, st);
     PWCK(S.get(5, need, &tmp), "alloc");
     PWCK(cub::DeviceRadixSort::SortPairs(tmp, need, keys, keys2, vals, vals2, (int)nf, 0, end_bit, st), "sort"); (*n_launch) += 8;

@@ -166,6 +166,8 @@ static inline unsigned pw_blocks(i64 n, int t) { return (unsigned)((n + t - 1) /
 static cudaError_t pairwise_finish(PairwiseScratch& S, int* c_x, int* c_y, double* c_p, double* c_stat, i64 nf, i64 m, i64 p, double alpha, bool fdr,
                                    cudaStream_t st, PairwiseOut* out, int* n_launch, std::string* msg) {
     const int T = 256;
+    // cub's sorts / scans take 32-bit item counts here: a denser univariate network than 2^31 - 1 raw-significant pairs is refused, not truncated
+    if (nf >= ((i64)1 << 31) - 1) { if (msg) *msg = "more than 2^31 raw-significant pairs are not supported (unsupported size)"; return cudaErrorInvalidValue; }
     void* tmp = nullptr; size_t tmp_bytes = 0, need = 0;
     double *adj, *rev; unsigned char* keep; u64 *keys, *keys2; unsigned int *vals, *vals2; i64 *keep64, *keep_pos;
     i64* d_off = out->d_off;
@@ -207,6 +209,7 @@ static cudaError_t pairwise_finish(PairwiseScratch& S, int* c_x, int* c_y, doubl
     PWCK(cudaMemcpyAsync(&last_keep, keep + nf - 1, 1, cudaMemcpyDeviceToHost, st), "d2h");
     PWCK(cudaStreamSynchronize(st), "sync");
     const i64 n_keep = last_pos + last_keep, ne = 2 * n_keep;
+    if (ne >= ((i64)1 << 31) - 1) { if (msg) *msg = "more than 2^31 neighbour-list entries are not supported (unsupported size)"; return cudaErrorInvalidValue; }
     out->n_entries = ne;
     if (ne == 0) { PWCK(cudaMemsetAsync(d_off, 0, sizeof(i64) * (p + 1), st), "memset"); return cudaSuccess; }
     pw_emit_directed<<<pw_blocks(nf, T), T, 0, st>>>(c_x, c_y, keep, keep_pos, nf, p, keys, vals); (*n_launch)++;

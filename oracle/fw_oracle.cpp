@@ -266,6 +266,49 @@ static void cor_columns(const Data& D, const Rows& R, const i64* vars, i64 nv, d
 }
 
 // ---------------------------------------------------------------------------------
+// View correlations of the zero-ignoring Fisher-z kind: cor_subset! (statfuns.jl:138-155, called from
+// tests.jl:293-308 on the hiton.jl:41-50,85 views) and the univariate `cor(sub_x, sub_y)` of tests.jl:127-147.
+// The reference evaluates Statistics.cor on a Float32 view (Float32 arithmetic, BLAS/pairwise summation order:
+// not reproducible outside Julia); here the same Pearson correlation is evaluated in Float64 and rounded to
+// Float32, in ONE summation order that the engine (csrc/fznz.cuh) follows operation for operation, so that the
+// Float32 correlations - and with them pcor_rec's 5-digit roundings - are bit-equal on both sides:
+//   * every variable is shifted by its value in the first row of the view (exact zero variance for a variable
+//     that is constant on the view; no cancellation when |mean| >> sd);
+//   * raw moments G_ab = sum x'_a x'_b and S_a = sum x'_a are accumulated with fma in increasing row order in
+//     8 interleaved partial sums (class = row index in the full table mod 8), the partials added in order 0..7;
+//   * c_ab = G_ab - (S_a*S_b)/n, r_ab = c_ab / (sqrt(c_aa)*sqrt(c_bb)), clamped to [-1, 1], NaN kept.
+// ---------------------------------------------------------------------------------
+static void cor_view(const Data& D, const Rows& R, const i64* vars, i64 nv, double* out /* nv x nv col-major */, bool cont32) {
+    const i64 m = R.size();
+    const i64 ne = nv + 1;                                   // entry nv is the constant 1 (sums)
+    std::vector<double> P((size_t)(8 * ne * ne), 0.0), piv((size_t)nv, 0.0), v((size_t)ne, 1.0);
+    if (m > 0) for (i64 a = 0; a < nv; ++a) piv[a] = D.cont[R[0] + vars[a] * D.n];
+    for (i64 i = 0; i < m; ++i) {
+        const i64 row = R[i];
+        double* Pw = &P[(size_t)((row & 7) * ne * ne)];
+        for (i64 a = 0; a < nv; ++a) v[a] = D.cont[row + vars[a] * D.n] - piv[a];
+        for (i64 a = 0; a < nv; ++a) for (i64 b = a; b < ne; ++b) Pw[a * ne + b] = std::fma(v[a], v[b], Pw[a * ne + b]);
+    }
+    std::vector<double> G((size_t)(ne * ne), 0.0);
+    for (i64 e = 0; e < ne * ne; ++e) { double s = 0.0; for (int w = 0; w < 8; ++w) s += P[(size_t)(w * ne * ne + e)]; G[e] = s; }
+    const double n = (double)m;
+    for (i64 a = 0; a < nv; ++a) {
+        out[a + a * nv] = 1.0;
+        const double sa = G[a * ne + nv];
+        const double caa = G[a * ne + a] - (sa * sa) / n;
+        for (i64 b = a + 1; b < nv; ++b) {
+            const double sb = G[b * ne + nv];
+            const double cbb = G[b * ne + b] - (sb * sb) / n;
+            const double cab = G[a * ne + b] - (sa * sb) / n;
+            double r = cab / (std::sqrt(caa) * std::sqrt(cbb));
+            if (r > 1.0) r = 1.0; else if (r < -1.0) r = -1.0;   // clampcor (NaN passes through)
+            if (cont32) r = (double)(float)r;
+            out[a + b * nv] = r; out[b + a * nv] = r;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // Discrete machinery.
 // ---------------------------------------------------------------------------------
 struct DiscScratch {
@@ -446,7 +489,8 @@ static fwo_result test_fz_uni(const Ctx& c, i64 X, i64 Y, const Rows& R, i64 n_o
             n_obs = sub.size();
             if (n_obs >= n_obs_min) {
                 i64 vars[2] = {X, Y}; double out[4];
-                cor_columns(c.D, sub, vars, 2, out, c.cont32);
+                if (is_nz(c.kind)) cor_view(c.D, sub, vars, 2, out, c.cont32);
+                else cor_columns(c.D, sub, vars, 2, out, c.cont32);
                 p_stat = out[2];
             } else p_stat = 0.0;
         }
@@ -494,7 +538,7 @@ static SubsetsOut test_subsets(Ctx& c, DiscScratch* s, i64 X, i64 Y, const std::
         for (i64 z : Z_total) vars.push_back(z);
         i64 nv = (i64)vars.size();
         std::vector<double> sub((size_t)(nv * nv));
-        cor_columns(c.D, R, vars.data(), nv, sub.data(), c.cont32);   // statfuns.jl:138-155 cor_subset!
+        cor_view(c.D, R, vars.data(), nv, sub.data(), c.cont32);      // statfuns.jl:138-155 cor_subset!
         for (i64 a = 0; a < nv - 1; ++a) for (i64 b = a + 1; b < nv; ++b) {
             double v = sub[(size_t)(a + b * nv)]; if (std::isnan(v)) v = 0.0;
             c.cor_mut[(size_t)(vars[a] + vars[b] * c.D.p)] = v; c.cor_mut[(size_t)(vars[b] + vars[a] * c.D.p)] = v;
@@ -888,7 +932,7 @@ void fwo_test_cond(fwo_ctx* h, i64 X, i64 Y, const i64* Zs, int k, i64 hps, i64 
             std::vector<i64> vars; vars.push_back(X); vars.push_back(Y); for (int i = 0; i < k; ++i) vars.push_back(Zs[i]);
             i64 nv = (i64)vars.size(); std::vector<double> sub((size_t)(nv * nv));
             h->ensure_scratch();
-            cor_columns(c.D, R, vars.data(), nv, sub.data(), c.cont32);
+            cor_view(c.D, R, vars.data(), nv, sub.data(), c.cont32);
             for (i64 a = 0; a < nv - 1; ++a) for (i64 b = a + 1; b < nv; ++b) {
                 double v = sub[(size_t)(a + b * nv)]; if (std::isnan(v)) v = 0.0;
                 c.cor_mut[(size_t)(vars[a] + vars[b] * c.D.p)] = v; c.cor_mut[(size_t)(vars[b] + vars[a] * c.D.p)] = v;
@@ -959,6 +1003,34 @@ i64 fwo_hiton_pc(fwo_ctx* h, i64 T, const i64* uni_nbr, const double* uni_stat, 
     for (size_t i = 0; i < o.PC.size(); ++i) { pc_nbr[i] = o.PC[i].v; pc_stat[i] = o.PC[i].stat; pc_p[i] = o.PC[i].pval; }
     *num_tests = o.num_tests;
     return (i64)o.PC.size();
+}
+
+// The same for many targets at once (one OpenMP thread per target = the reference's one worker per target job,
+// interleaved.jl:90): univariate lists as CSR over the listed targets (uni_off[n_targets + 1]); outputs use the same offsets
+// (a target's PC is never longer than its candidate list).  Used by the sampled GPU-vs-oracle parity checks.
+void fwo_hiton_pc_batch(fwo_ctx* h, i64 n_targets, const i64* targets, const i64* uni_off, const i64* uni_nbr, const double* uni_stat,
+                        const double* uni_p, int max_k, double alpha, i64 hps, i64 n_obs_min, i64 max_tests, int n_threads,
+                        i64* pc_count, i64* pc_nbr, double* pc_stat, double* pc_p, i64* num_tests) {
+    Ctx& c = h->c;
+    Params P; P.kind = c.kind; P.max_k = max_k; P.alpha = alpha; P.hps = hps; P.n_obs_min = n_obs_min; P.max_tests = max_tests;
+    P.fdr = true; P.correct_reliable_only = true; P.fast_elim = true;
+    const i64 p = c.D.p;
+#pragma omp parallel num_threads(n_threads > 0 ? n_threads : 1)
+    {
+        DiscScratch s; if (is_discrete(c.kind)) s.init(c.max_level, max_k, c.D.n);
+        Ctx local = c;
+        std::vector<double> scratch;
+        if (c.kind == FZ_NZ) { scratch.assign((size_t)(p * p), 0.0); local.cor_mut = scratch.data(); local.C.m = scratch.data(); }
+        std::set<i64> empty;
+#pragma omp for schedule(dynamic, 1)
+        for (i64 t = 0; t < n_targets; ++t) {
+            std::vector<Nbr> uni;
+            for (i64 i = uni_off[t]; i < uni_off[t + 1]; ++i) { Nbr nb = {uni_nbr[i], uni_stat[i], uni_p[i]}; uni.push_back(nb); }
+            HitonOut o = si_hiton_pc(local, &s, targets[t], uni, P, empty);
+            pc_count[t] = (i64)o.PC.size(); num_tests[t] = o.num_tests;
+            for (size_t i = 0; i < o.PC.size(); ++i) { pc_nbr[uni_off[t] + (i64)i] = o.PC[i].v; pc_stat[uni_off[t] + (i64)i] = o.PC[i].stat; pc_p[uni_off[t] + (i64)i] = o.PC[i].pval; }
+        }
+    }
 }
 
 // Full LGL (learning.jl:203-279).  n_obs_min < 0: automatic.  mode 0 "single", 1 "single_il" emulation.

@@ -68,6 +68,8 @@ def lib():
         L.fwo_auto_n_obs_min.argtypes = [p, C.c_int, i64]
         L.fwo_hiton_pc.restype = i64
         L.fwo_hiton_pc.argtypes = [p, i64, p, p, p, i64, C.c_int, dbl, i64, i64, i64, p, i64, p, p, p, p]
+        L.fwo_hiton_pc_batch.restype = None
+        L.fwo_hiton_pc_batch.argtypes = [p, i64, p, p, p, p, p, C.c_int, dbl, i64, i64, i64, C.c_int, p, p, p, p, p]
         L.fwo_lgl.restype = i64
         L.fwo_lgl.argtypes = [p, C.c_int, dbl, i64, i64, i64, C.c_int, C.c_int, C.c_int, p, i64,
                               p, p, p, i64, p, p, p, p, p, p, i64, p]
@@ -193,6 +195,21 @@ class Oracle:
         k = self.L.fwo_hiton_pc(self.h, T, _ptr(un), _ptr(us), _ptr(up), len(un), max_k, alpha, hps, n_obs_min, max_tests,
                                 _ptr(wl), len(wl), _ptr(pn), _ptr(ps), _ptr(pp), C.byref(nt))
         return pn[:k].copy(), ps[:k].copy(), pp[:k].copy(), int(nt.value)
+
+    def hiton_pc_batch(self, targets, uni_off, uni_nbr, uni_stat, uni_p, max_k=3, alpha=0.01, hps=5, n_obs_min=0, max_tests=0, n_threads=0):
+        """si_HITON_PC ("single" semantics) for many targets; CSR in, CSR out over the same offsets:
+        returns (pc_count, pc_nbr, pc_stat, pc_p, num_tests)."""
+        tg, off, un = _i64(targets), _i64(uni_off), _i64(uni_nbr)
+        us = np.ascontiguousarray(uni_stat, dtype=np.float64)
+        up = np.ascontiguousarray(uni_p, dtype=np.float64)
+        nt, cap = len(tg), max(int(off[-1]), 1)
+        pcc = np.zeros(max(nt, 1), np.int64); ntests = np.zeros(max(nt, 1), np.int64)
+        pn = np.zeros(cap, np.int64); ps = np.zeros(cap); pp = np.zeros(cap)
+        if n_threads <= 0:
+            n_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.L.fwo_hiton_pc_batch(self.h, nt, _ptr(tg), _ptr(off), _ptr(un), _ptr(us), _ptr(up), max_k, alpha, hps, n_obs_min, max_tests,
+                                  n_threads, _ptr(pcc), _ptr(pn), _ptr(ps), _ptr(pp), _ptr(ntests))
+        return pcc[:nt], pn, ps, pp, ntests[:nt]
 
     def lgl(self, max_k=3, alpha=0.01, hps=5, n_obs_min=-1, max_tests=10_000_000, fdr=True, mode="single", n_threads=1,
             targets=None, want_pc=False):

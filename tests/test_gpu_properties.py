@@ -112,6 +112,23 @@ def test_abi_errors_are_loud(fw):
         eng.test_subsets(0, 1, [2, 3, 4, 5, 6], max_k=4)
     with pytest.raises(fw.FwError, match="neighbour lists"):
         eng.si_HITON_PC([0, 1])
+    # a new table (same p) invalidates the neighbour lists and the cor_mat of the previous one: loud, not stale
+    eng.pw_univar_neighbors(alpha=0.5, n_obs_min=0)
+    eng.si_HITON_PC([0, 1], max_k=1)
+    eng.set_data_colmajor(x[::-1].copy(), "fz")
+    with pytest.raises(fw.FwError, match="no cor_mat"):
+        eng.test_batch([0], [1], [(2,)])
+    eng.cor(want_host=False)
+    with pytest.raises(fw.FwError, match="neighbour lists"):
+        eng.si_HITON_PC([0, 1], max_k=1)
+    with pytest.raises(fw.FwError, match="neighbour lists"):
+        eng.univar_nbrs()
+    xi = (np.random.default_rng(3).random((10, 50)) < 0.5).astype(np.int32)
+    eng.set_data_colmajor(xi, "mi")
+    eng.pw_univar_neighbors(alpha=0.5, n_obs_min=0)
+    eng.set_data_colmajor(xi[::-1].copy(), "mi")
+    with pytest.raises(fw.FwError, match="neighbour lists"):
+        eng.si_HITON_PC([0, 1], max_k=1)
     with pytest.raises(fw.FwError, match="levels"):
         e2 = fw.Engine(0)
         e2.set_data_colmajor(np.arange(60).reshape(3, 20).astype(np.int32) % 7, "mi")      # 7 levels > 4
