@@ -38,6 +38,8 @@ ABI_SYMBOLS = [
     "fw_pairwise", "fw_pairwise_copy", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_capacity",
     "fw_normalize_f32", "fw_get_data_f32", "fw_get_data_i32", "fw_set_data_csc_f32", "fw_set_data_csc_i32",
     "fw_host_register", "fw_host_unregister",
+    "fw_cor_gather", "fw_pairwise_prefetch",
+    "fw_comm_handle_bytes", "fw_comm_export", "fw_comm_attach", "fw_comm_detach", "fw_multi_set_data_f32", "fw_multi_cor",
     "fw_build_info",
 ]
 
@@ -119,6 +121,14 @@ def load_library():
         "fw_host_unregister": (i32, [vp, vp]),
         "fw_get_data_f32": (i32, [vp, vp, i64]),
         "fw_get_data_i32": (i32, [vp, vp, i64]),
+        "fw_cor_gather": (i32, [vp, vp, i64, vp]),
+        "fw_pairwise_prefetch": (i32, [vp, dbl, i64]),
+        "fw_comm_handle_bytes": (i32, []),
+        "fw_comm_export": (i32, [vp, i32, i32, i64, i64, vp]),
+        "fw_comm_attach": (i32, [vp, vp]),
+        "fw_comm_detach": (i32, [vp]),
+        "fw_multi_set_data_f32": (i32, [vp, vp, i64]),
+        "fw_multi_cor": (i32, [vp]),
         "fw_build_info": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
@@ -390,7 +400,41 @@ class Engine:
     def cor_device_ptr(self):
         return self.L.fw_cor_device_ptr(self.h)
 
-    # row-sharded cor_mat (multi-GPU): see parallel.sharded_cor
+    def cor_gather(self, idx):
+        """cor_mat[idx][:, idx] as an [m, m] float32 array (works on the full and on the row-sharded matrix)"""
+        ix = _i64(idx)
+        out = np.empty((len(ix), len(ix)), np.float32)
+        self._ck(self.L.fw_cor_gather(self.h, _p(ix), len(ix), _p(out)))
+        return out
+
+    def pairwise_prefetch(self, alpha=0.01, n_obs_min=0):
+        """announce the next pw_univar_neighbors(fz): the cor_mat GEMM collects its raw candidates in the epilogue"""
+        self._ck(self.L.fw_pairwise_prefetch(self.h, alpha, n_obs_min))
+
+    # -- multi-GPU group (include/fwgpu.h; parallel.attach_group does the handle exchange) -----------------------
+    def comm_export(self, rank, world, n, p):
+        buf = np.zeros(self.L.fw_comm_handle_bytes(), np.uint8)
+        self._ck(self.L.fw_comm_export(self.h, rank, world, n, p, _p(buf)))
+        return buf
+
+    def comm_attach(self, handles):
+        hb = np.ascontiguousarray(handles, dtype=np.uint8)
+        self._ck(self.L.fw_comm_attach(self.h, _p(hb)))
+
+    def comm_detach(self):
+        self._ck(self.L.fw_comm_detach(self.h))
+
+    def multi_set_data_ptr(self, host_slice_ptr, n, p, ld=None):
+        """this rank's columns of the table (host pointer at column p*rank/world, column-major, leading dimension ld)"""
+        self._ck(self.L.fw_multi_set_data_f32(self.h, C.c_void_p(host_slice_ptr), ld or n))
+        self.kind, self.n, self.p = "fz", n, p
+        self._cor_valid = False
+
+    def multi_cor(self):
+        self._ck(self.L.fw_multi_cor(self.h))
+        self._cor_valid = True
+
+    # row-sharded cor_mat with a host-side exchange (NCCL all-gather by the caller): see parallel.sharded_cor
     def adopt_cor_device_rows(self, dev_ptr, p, rows_allocated):
         self._ck(self.L.fw_adopt_cor_device_rows(self.h, C.c_void_p(dev_ptr), p, rows_allocated))
         self.p = p
@@ -527,7 +571,9 @@ class Engine:
             ml = int(self.levels()[0].max()) if kind in ("mi", "mi_nz") else None
             n_obs_min = auto_n_obs_min(kind, max_k, hps, max_level=ml)
         if kind == "fz" and not (getattr(self, "_cor_valid", False) and self.L.fw_cor_device_ptr(self.h)):
-            self.cor(want_host=False)                      # no cor_mat yet, or it belongs to a previous table
+            # no cor_mat yet, or it belongs to a previous table; the GEMM epilogue already collects the pairwise candidates
+            self.pairwise_prefetch(alpha, n_obs_min)
+            self.cor(want_host=False)
         uni = self.pw_univar_neighbors(alpha=alpha, hps=hps, n_obs_min=n_obs_min, FDR=FDR, kind=kind)
         tg = target_order(uni) if targets is None else _i64(targets)
         res = self.si_HITON_PC(tg, max_k=max_k, alpha=alpha, hps=hps, n_obs_min=n_obs_min, max_tests=max_tests, kind=kind, want_tpc=False)

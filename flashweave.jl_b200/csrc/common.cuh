@@ -25,6 +25,37 @@ __device__ __forceinline__ DevResult make_result(double s, double p, i64 df, boo
     return r;
 }
 
+// ---- the resident correlation matrix as the test kernels see it ------------------------------------------------------------
+// One GPU (world == 1): the full symmetric p x p Float32 matrix at shard[0].
+// Several GPUs: cor_mat stays ROW-SHARDED where the GEMM produced it and is never exchanged.  Only the upper triangle exists:
+// the 128-row tile rows are split into 2*world contiguous groups of h tile rows, rank r owns groups r and 2*world-1-r (equal
+// tile counts), stored back to back in its shard; shard[q] is rank q's buffer mapped into this process (CUDA IPC / peer access),
+// so a lookup is one NVLink read of the owner's HBM.  r(a, b) lives in row min(a, b), column max(a, b).
+constexpr int FW_MAX_RANKS = 8;
+struct CorView {
+    const float* shard[FW_MAX_RANKS];
+    i64 p;
+    int world, h;
+    __device__ __forceinline__ float at(i64 a, i64 b) const {
+        if (world == 1) return __ldg(shard[0] + a * p + b);
+        const i64 lo = a < b ? a : b, hi = a < b ? b : a;
+        const int tr = (int)(lo >> 7), g = tr / h;
+        const int owner = g < world ? g : 2 * world - 1 - g;
+        const i64 lrow = (i64)((g < world ? 0 : h) + (tr - g * h)) * 128 + (lo & 127);
+        return shard[owner][lrow * p + hi];
+    }
+    // first local row of tile row `tr` in its owner's shard, and the owner (host + device)
+    __host__ __device__ __forceinline__ int owner_of_tile_row(int tr) const { const int g = tr / h; return g < world ? g : 2 * world - 1 - g; }
+    __host__ __device__ __forceinline__ i64 local_row_of_tile_row(int tr) const { const int g = tr / h; return (i64)((g < world ? 0 : h) + (tr - g * h)) * 128; }
+};
+
+// ---- raw candidates of the univariate Fisher-z stage ---------------------------------------------------------------------------
+// A pair whose |r| reaches the (conservatively lowered) significance threshold, as the cor_mat GEMM epilogue (cor_tc.cuh) or the
+// one-pass scan of the resident matrix (pairwise.cuh) appends it: unordered, 12 bytes.  counters[0] = records appended (it keeps
+// counting past `cap`: the host then knows the size to retry with), counters[1] = NaN correlations seen in the upper triangle.
+struct PwRec { int x, y; float r; };
+struct PwEmit { PwRec* list; u64* counters; i64 cap; float r_lo; int on; };
+
 __device__ __forceinline__ i64 choose2(i64 n) { return n < 2 ? 0 : n * (n - 1) / 2; }
 __device__ __forceinline__ i64 choose3(i64 n) { return n < 3 ? 0 : n * (n - 1) * (n - 2) / 6; }
 

@@ -128,11 +128,39 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// Univariate Fisher-z stage fused into the epilogue (tests.jl:470-478 looks the same correlations up again): the finished tile
+// row of this thread is still in registers (acc[0..BN) = the clamped correlations of `row` with columns col0..), so the pairs
+// with |r| >= r_lo are appended to the raw-candidate list here instead of re-reading the 10 GB matrix: per warp one exclusive
+// scan of the hit counts and ONE global atomic, then every lane writes its own records.
+__device__ __forceinline__ void emit_candidates(const PwEmit& em, const float* acc, i64 row, i64 col0, i64 p, bool diag, bool live,
+                                                unsigned int n_hit, unsigned int n_nan, int lane) {
+    unsigned int incl = n_hit;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+    u64 base = 0;
+    if (lane == 31 && total) base = atomicAdd(&em.counters[0], (u64)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    const unsigned int nn = __reduce_add_sync(0xffffffffu, n_nan);
+    if (lane == 0 && nn) atomicAdd(&em.counters[1], (u64)nn);
+    if (!n_hit) return;
+    u64 pos = base + incl - n_hit;
+#pragma unroll
+    for (int j = 0; j < BN; ++j) {
+        const i64 col = col0 + j;
+        const float x = acc[j];
+        if (live && row < p && col < p && col > row && x == x && fabsf(x) >= em.r_lo) {
+            if ((i64)pos < em.cap) { PwRec rec; rec.x = (int)row; rec.y = (int)col; rec.r = x; em.list[pos] = rec; }
+            ++pos;
+        }
+    }
+}
+
 // Tiles: upper-triangular tile rows [bi0, bi0 + nbi) of an nb x nb tile grid (blockIdx.x enumerates them row-major).  mirror != 0
 // also writes the transposed tile (single-GPU mode); mirror == 0 (row-sharded mode) leaves the lower triangle to
 // cor_symmetrize_kernel after the ranks have exchanged their row blocks, and only mirrors inside diagonal tiles.
 __global__ void __launch_bounds__(NTHREADS, 1) cor_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                                                             float* __restrict__ C, i64 p, int num_kb, int nb, int bi0, int mirror) {
+                                                             float* __restrict__ C, i64 p, int num_kb, int nb, int bi0, int mirror, const PwEmit em, const int sh_world, const int sh_h) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B tiles need 1024-byte alignment
@@ -157,6 +185,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) cor_tc_kernel(const __grid_consta
         bi = r; bj = r + (int)(t - ((long long)r * nb - (long long)r * (r - 1) / 2));
     }
     const int n_chunks = (num_kb + CHUNK - 1) / CHUNK;
+    // row-sharded mode (several GPUs): tile row bi is stored at its local position in this rank's shard (common.cuh, CorView)
+    float* Cw = C;
+    if (sh_world > 1) { const int g = bi / sh_h; Cw = C + ((i64)((g < sh_world ? 0 : sh_h) + (bi - g * sh_h)) * 128 - (i64)bi * 128) * p; }
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -249,6 +280,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cor_tc_kernel(const __grid_consta
         // the last chunk's commit also covers every earlier MMA, including the cross accumulator
         const i64 row = (i64)bi * BM + q * 32 + lane;
         const bool diag = (bi == bj);
+        unsigned int n_hit = 0, n_nan = 0;
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
@@ -261,11 +293,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) cor_tc_kernel(const __grid_consta
                 if (row == col) x = 1.0f;                              // cov2cor!: unit diagonal
                 const bool ok = row < p && col < p && (!diag || col >= row);
                 if (ok) {
-                    C[row * p + col] = x;
-                    if (mirror || diag) C[col * p + row] = x;          // mirror (coalesced across the warp: consecutive rows)
+                    Cw[row * p + col] = x;
+                    if (mirror || diag) Cw[col * p + row] = x;         // mirror (coalesced across the warp: consecutive rows)
                 }
+                acc[c0 + j] = x;
+                if (em.on && ok && col > row) { if (x != x) ++n_nan; else if (fabsf(x) >= em.r_lo) ++n_hit; }
             }
         }
+        if (em.on) emit_candidates(em, acc, row, (i64)bj * BN, p, diag, true, n_hit, n_nan, lane);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -328,7 +363,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 cor_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-               float* __restrict__ C, i64 p, int num_kb, int nb, int bi0, int bi1, int mirror, int bjlo, int bjhi) {
+               float* __restrict__ C, i64 p, int num_kb, int nb, int bi0, int bi1, int mirror, int bjlo, int bjhi, const PwEmit em, const int sh_world, const int sh_h) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -367,6 +402,9 @@ cor_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         if (bj < bi) live = false;
     }
     const int n_chunks = (num_kb + CHUNK - 1) / CHUNK;
+    // row-sharded mode (several GPUs): tile row bi is stored at its local position in this rank's shard (common.cuh, CorView)
+    float* Cw = C;
+    if (sh_world > 1) { const int g = bi / sh_h; Cw = C + ((i64)((g < sh_world ? 0 : sh_h) + (bi - g * sh_h)) * 128 - (i64)bi * 128) * p; }
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2); }   // both CTAs release a stage
@@ -457,6 +495,7 @@ cor_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         }
         const i64 row = (i64)bi * BM + q * 32 + lane;
         const bool diag = (bi == bj);
+        unsigned int n_hit = 0, n_nan = 0;
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
@@ -469,11 +508,14 @@ cor_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 if (row == col) x = 1.0f;
                 const bool ok = live && row < p && col < p && (!diag || col >= row);
                 if (ok) {
-                    C[row * p + col] = x;
-                    if (mirror || diag) C[col * p + row] = x;
+                    Cw[row * p + col] = x;
+                    if (mirror || diag) Cw[col * p + row] = x;
                 }
+                acc[c0 + j] = x;
+                if (em.on && ok && col > row) { if (x != x) ++n_nan; else if (fabsf(x) >= em.r_lo) ++n_hit; }
             }
         }
+        if (em.on) emit_candidates(em, acc, row, (i64)bj * BN, p, diag, live, n_hit, n_nan, lane);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -519,38 +561,41 @@ static long long grouped_clusters(int bi0, int bi1, int bjlo, int bjhi) {
     }
     return c;
 }
-static cudaError_t run_rows(const Prepared& P, float* d_cor, i64 p, int bi0, int bi1, bool mirror, cudaStream_t st, int* n_launch, std::string* msg) {
+static cudaError_t run_rows(const Prepared& P, float* d_cor, i64 p, int bi0, int bi1, bool mirror, cudaStream_t st, int* n_launch, std::string* msg,
+                            const PwEmit& em = PwEmit{nullptr, nullptr, 0, 2.0f, 0}, int sh_world = 1, int sh_h = 1) {
     if (bi1 > P.nb) bi1 = P.nb;
     if (bi0 >= bi1) return cudaSuccess;
     if (use_cluster_kernel()) {
         const long long clusters = grouped_clusters(bi0, bi1, 0, P.nb);
         cudaError_t e = cudaFuncSetAttribute(cor_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute(cor_tc2_kernel)"; return e; }
-        cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(P.kp / BK), P.nb, bi0, bi1, mirror ? 1 : 0, 0, P.nb);
+        cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(P.kp / BK), P.nb, bi0, bi1, mirror ? 1 : 0, 0, P.nb, em, sh_world, sh_h);
         (*n_launch)++;
         e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "cor_tc2_kernel"; return e; }
         return cudaSuccess;
     }
     const long long first = (long long)bi0 * P.nb - (long long)bi0 * (bi0 - 1) / 2;
     const long long last = (long long)bi1 * P.nb - (long long)bi1 * (bi1 - 1) / 2;
-    cor_tc_kernel<<<(unsigned)(last - first), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(P.kp / BK), P.nb, bi0, mirror ? 1 : 0);
+    cor_tc_kernel<<<(unsigned)(last - first), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(P.kp / BK), P.nb, bi0, mirror ? 1 : 0, em, sh_world, sh_h);
     (*n_launch)++;
     cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "cor_tc_kernel"; return e; }
     return cudaSuccess;
 }
 
-static cudaError_t run(Scratch& S, const float* d_data, i64 n, i64 p, i64 ld, float* d_cor, cudaStream_t st, int* n_launch, std::string* msg) {
+static cudaError_t run(Scratch& S, const float* d_data, i64 n, i64 p, i64 ld, float* d_cor, cudaStream_t st, int* n_launch, std::string* msg,
+                       const PwEmit& em = PwEmit{nullptr, nullptr, 0, 2.0f, 0}) {
     Prepared P;
     cudaError_t e = prepare(S, P, d_data, n, p, ld, st, n_launch, msg);
     if (e != cudaSuccess) return e;
-    return run_rows(P, d_cor, p, 0, P.nb, true, st, n_launch, msg);
+    return run_rows(P, d_cor, p, 0, P.nb, true, st, n_launch, msg, em);
 }
 
 // Upload-overlapped cor_mat (one GPU): the host table is copied in column chunks on `copy_st`; as soon as chunk c has landed the
 // compute stream standardises its columns and runs the tiles (bi <= bj, bj in the chunk's tile columns) — a growing column band
 // of the upper triangle — so the PCIe transfer hides behind the GEMM.  Same tiles, same arithmetic as run().
 static cudaError_t run_overlapped(Scratch& S, const float* host, float* d_data, i64 n, i64 p, i64 host_ld, float* d_cor,
-                                  cudaStream_t st, cudaStream_t copy_st, cudaEvent_t* evs, int n_evs, int* n_launch, std::string* msg) {
+                                  cudaStream_t st, cudaStream_t copy_st, cudaEvent_t* evs, int n_evs, int* n_launch, std::string* msg,
+                                  const PwEmit& em = PwEmit{nullptr, nullptr, 0, 2.0f, 0}) {
     const i64 kp = (n + BK - 1) / BK * BK;
     const i64 p_pad = (p + BM - 1) / BM * BM;
     const int nb = (int)(p_pad / BM);
@@ -584,7 +629,7 @@ static cudaError_t run_overlapped(Scratch& S, const float* host, float* d_data, 
         standardize_split_kernel<256><<<(unsigned)(s1 - c0), 256, 0, st>>>(d_data, n, n, p, kp, zhi, zlo, c0);
         (*n_launch)++;
         const long long clusters = grouped_clusters(0, t1, t0, t1);
-        cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(kp / BK), nb, 0, t1, 1, t0, t1);
+        cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(kp / BK), nb, 0, t1, 1, t0, t1, em, 1, 1);
         (*n_launch)++;
         e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "cor_tc2_kernel (band)"; return e; }
         t0 = t1;

@@ -18,6 +18,7 @@
 #include "hiton.cuh"
 #include "pairwise.cuh"
 #include "cor_tc.cuh"
+#include "comm.cuh"
 #include "mi.cuh"
 #include "hiton_mi.cuh"
 #include "prep.cuh"
@@ -68,8 +69,16 @@ struct fw_ctx {
     // fz_nz: non-zero planes of the continuous table (fznz.cuh), built on first use
     DevBuf<unsigned int> d_nzmask; DevBuf<int> d_nnz_f; bool nz_ready = false;
 
-    // cor_mat
+    // cor_mat: the full symmetric matrix (d_cor), or - in a multi-GPU group - this rank's row shard (grp, CorView)
     DevBuf<float> d_cor; i64 cor_p = 0;
+    bool cor_sharded = false;
+    // raw candidates of the univariate Fisher-z stage (PwRec, common.cuh): collected by the cor_mat GEMM epilogue when
+    // fw_pairwise_prefetch announced the parameters, else by one pass over the resident matrix
+    struct Collect { bool armed = false, valid = false; double alpha = 0.0; i64 n_obs_min = 0; float r_lo = 2.0f; i64 cap = 0; } col;
+    DevBuf<PwRec> d_list; DevBuf<u64> d_listcnt; DevBuf<PwRec> d_gathered;
+    // multi-GPU group (comm.cuh)
+    fwcomm::Group grp;
+    DevBuf<float> g_table; DevBuf<float> g_cor; DevBuf<PwRec> g_list; DevBuf<u64> g_flags; DevBuf<int> g_err;
 
     // univariate neighbour lists (device-resident CSR + host copy of the offsets)
     DevBuf<i64> d_uni_off, d_uni_nbr; DevBuf<double> d_uni_stat, d_uni_p;
@@ -106,9 +115,44 @@ static int fail(fw_ctx* c, int code, const char* fmt, ...) {
 // non-zero planes and the univariate neighbour lists (fw_hiton_pc / fw_pairwise_copy then fail with FW_ERR_STATE instead of
 // silently running against the lists of another table)
 static void table_changed(fw_ctx* c) {
-    c->nz_ready = false; c->tcp.valid = false; c->cor_p = 0;
+    c->nz_ready = false; c->tcp.valid = false; c->cor_p = 0; c->cor_sharded = false; c->col.valid = false;
     c->uni_entries = -1; c->h_uni_off.clear();
 }
+static bool has_cor(const fw_ctx* c) { return c->cor_p > 0 && (c->cor_sharded ? c->grp.attached : c->d_cor.ptr != nullptr); }
+static CorView make_cor_view(const fw_ctx* c) {
+    CorView v;
+    for (int q = 0; q < FW_MAX_RANKS; ++q) v.shard[q] = nullptr;
+    v.p = c->cor_p;
+    if (c->cor_sharded) { v.world = c->grp.world; v.h = c->grp.h; for (int q = 0; q < c->grp.world; ++q) v.shard[q] = c->grp.cor_of(q); }
+    else { v.world = 1; v.h = 1; v.shard[0] = c->d_cor.ptr; }
+    return v;
+}
+
+
+// ---- multi-GPU group: device-side barrier (comm.cuh) -------------------------------------------------------------------------
+static const long long kCommTimeoutClk = 20000000000LL;          // ~10 s of SM clocks: a dead peer becomes an error, never a hang
+static int comm_barrier(fw_ctx* ctx) {
+    fwcomm::Group& G = ctx->grp;
+    G.seq++;
+    fwcomm::signal_kernel<<<1, 1, 0, ctx->stream>>>(G.flags_of(G.rank) + fwcomm::F_SEQ, G.seq);
+    fwcomm::PeerFlags pf;
+    for (int q = 0; q < FW_MAX_RANKS; ++q) pf.f[q] = q < G.world ? G.flags_of(q) + fwcomm::F_SEQ : nullptr;
+    fwcomm::wait_kernel<<<1, 32, 0, ctx->stream>>>(pf, G.world, G.seq, kCommTimeoutClk, G.d_err);
+    ctx->launches += 2;
+    cudaError_t e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) { ctx->err = std::string("group barrier launch failed: ") + cudaGetErrorString(e_); return FW_ERR_CUDA; }
+    return FW_OK;
+}
+// after a stream synchronisation: did a barrier time out?
+static int comm_check(fw_ctx* ctx) {
+    if (!ctx->grp.attached) return FW_OK;
+    int h = 0;
+    if (cudaMemcpy(&h, ctx->grp.d_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) { ctx->err = "group error flag unreadable"; return FW_ERR_CUDA; }
+    if (h) { ctx->err = "group barrier timed out waiting for rank " + std::to_string(h - 1) + " (every rank must issue the same sequence of collective calls)"; return FW_ERR_CUDA; }
+    return FW_OK;
+}
+
+static i64 list_capacity(i64 n_pairs) { return std::max<i64>(1, std::min<i64>(n_pairs, std::max<i64>((i64)1 << 16, n_pairs / 16))); }
 
 static FzConsts make_fz_consts(i64 n_rows, i64 n_obs_min) {
     FzConsts fc;
@@ -255,6 +299,101 @@ static int set_data_csc(fw_ctx* ctx, const int64_t* colptr, const int64_t* rowva
     return FW_OK;
 }
 
+// ---- raw candidates of the univariate Fisher-z stage ---------------------------------------------------------------------------
+// fw_pairwise_prefetch announced (alpha, n_obs_min): the cor_mat GEMM about to be launched appends every |r| >= r_lo of its
+// tiles to the candidate list in its epilogue (the list of the group buffer when the matrix is row-sharded)
+static int arm_collect(fw_ctx* ctx, bool sharded, PwEmit* em) {
+    em->list = nullptr; em->counters = nullptr; em->cap = 0; em->r_lo = 2.0f; em->on = 0;
+    ctx->col.valid = false;
+    if (!ctx->col.armed) return FW_OK;
+    const i64 p = ctx->p, n_pairs = p * (p - 1) / 2;
+    const FzConsts fc = make_fz_consts(ctx->n_obs, ctx->col.n_obs_min);
+    ctx->col.r_lo = pairwise_fz_r_lo(fc, ctx->n_obs, ctx->col.n_obs_min, ctx->col.alpha);
+    CK(ctx->d_listcnt.reserve(4));
+    if (sharded) { em->list = ctx->grp.list_of(ctx->grp.rank); em->cap = ctx->grp.list_cap; }
+    else { const i64 cap = std::max<i64>(list_capacity(n_pairs), (i64)ctx->d_list.cap); CK(ctx->d_list.reserve((size_t)cap)); em->list = ctx->d_list.ptr; em->cap = (i64)ctx->d_list.cap; }
+    CK(cudaMemsetAsync(ctx->d_listcnt.ptr, 0, 4 * sizeof(u64), ctx->stream));
+    em->counters = ctx->d_listcnt.ptr; em->r_lo = ctx->col.r_lo; em->on = 1;
+    ctx->col.cap = em->cap;
+    return FW_OK;
+}
+
+// pw_univar_neighbors for test_name "fz" on the resident cor_mat (tests.jl:470-478 + :372-407 + statfuns.jl:326-350)
+static int run_pairwise_fz(fw_ctx* ctx, double alpha, i64 n_obs_min, bool fdr, bool rel_only, PairwiseOut* po, int* nl) {
+    const i64 p = ctx->cor_p, n_pairs = p * (p - 1) / 2;
+    const FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
+    const float r_lo = pairwise_fz_r_lo(fc, ctx->n_obs, n_obs_min, alpha);
+    const bool multi = ctx->cor_sharded;
+    fwcomm::Group& G = ctx->grp;
+    std::string msg;
+    cudaStream_t st = ctx->stream;
+    const bool reuse = ctx->col.valid && ctx->col.alpha == alpha && ctx->col.n_obs_min == n_obs_min && ctx->col.r_lo == r_lo;
+    const PwRec* recs = nullptr; i64 nrec = 0, n_nan = 0;
+    u64 hc[2] = {0, 0};
+    CK(ctx->d_listcnt.reserve(4));
+    if (!multi) {
+        bool have = reuse;
+        i64 cap = (i64)ctx->d_list.cap;
+        if (have) {
+            CK(cudaMemcpyAsync(hc, ctx->d_listcnt.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if ((i64)hc[0] > ctx->col.cap) { have = false; cap = (i64)hc[0]; }          // the GEMM epilogue ran out of list space: re-scan with the exact size
+        } else cap = std::max<i64>(cap, list_capacity(n_pairs));
+        for (int attempt = 0; !have && attempt < 2; ++attempt) {
+            CK(ctx->d_list.reserve((size_t)cap));
+            CK(cudaMemsetAsync(ctx->d_listcnt.ptr, 0, 4 * sizeof(u64), st));
+            PwEmit em; em.list = ctx->d_list.ptr; em.counters = ctx->d_listcnt.ptr; em.cap = (i64)ctx->d_list.cap; em.r_lo = r_lo; em.on = 1;
+            cudaError_t e = pairwise_fz_emit(ctx->d_cor.ptr, p, 0, 0, p - 1, em, st, nl, &msg);
+            if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_pairwise: %s: %s", msg.c_str(), cudaGetErrorString(e));
+            CK(cudaMemcpyAsync(hc, ctx->d_listcnt.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if ((i64)hc[0] <= em.cap) have = true; else cap = (i64)hc[0];
+        }
+        NEED(have, FW_ERR_CUDA, "fw_pairwise: candidate list overflow");
+        ctx->col.valid = false;                                                         // (a re-scan replaced the collected list)
+        if (reuse && (i64)hc[0] <= ctx->col.cap) ctx->col.valid = true;
+        recs = ctx->d_list.ptr; nrec = (i64)hc[0]; n_nan = (i64)hc[1];
+    } else {
+        NEED(G.attached, FW_ERR_STATE, "fw_pairwise: the row-sharded cor_mat needs an attached group");
+        if (!reuse) {
+            // collective: every rank scans its own tile rows (peers may still be pulling the previous list: barrier first)
+            int st_ = comm_barrier(ctx); if (st_ != FW_OK) return st_;
+            CK(cudaMemsetAsync(ctx->d_listcnt.ptr, 0, 4 * sizeof(u64), st));
+            PwEmit em; em.list = G.list_of(G.rank); em.counters = ctx->d_listcnt.ptr; em.cap = G.list_cap; em.r_lo = r_lo; em.on = 1;
+            const int grp_id[2] = {G.rank, 2 * G.world - 1 - G.rank};
+            for (int k = 0; k < 2; ++k) {
+                const i64 g0 = (i64)grp_id[k] * G.h * 128, g1 = std::min<i64>(g0 + (i64)G.h * 128, p);
+                cudaError_t e = pairwise_fz_emit(G.cor_of(G.rank), p, g0, (i64)k * G.h * 128, g1 - g0, em, st, nl, &msg);
+                if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_pairwise: %s: %s", msg.c_str(), cudaGetErrorString(e));
+            }
+            CK(cudaMemcpyAsync(G.flags_of(G.rank) + fwcomm::F_LIST_N, ctx->d_listcnt.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+            st_ = comm_barrier(ctx); if (st_ != FW_OK) return st_;
+            ctx->col.valid = false;
+        }
+        // pull the peers' compact lists (global m and rank order of Benjamini-Hochberg need all of them, statfuns.jl:326-350)
+        u64 cnt[FW_MAX_RANKS][2];
+        for (int q = 0; q < G.world; ++q) CK(cudaMemcpyAsync(cnt[q], G.flags_of(q) + fwcomm::F_LIST_N, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        { int st_ = comm_check(ctx); if (st_ != FW_OK) return st_; }
+        for (int q = 0; q < G.world; ++q) {
+            NEED((i64)cnt[q][0] <= G.list_cap, FW_ERR_UNSUPPORTED, "fw_pairwise: rank %d collected %llu raw candidates, more than the group's list capacity %lld (univariate network too dense)",
+                 q, (unsigned long long)cnt[q][0], (long long)G.list_cap);
+            nrec += (i64)cnt[q][0]; n_nan += (i64)cnt[q][1];
+        }
+        CK(ctx->d_gathered.reserve((size_t)std::max<i64>(nrec, 1)));
+        i64 o = 0;
+        for (int q = 0; q < G.world; ++q) {
+            if (cnt[q][0]) CK(cudaMemcpyAsync(ctx->d_gathered.ptr + o, G.list_of(q), sizeof(PwRec) * cnt[q][0], cudaMemcpyDeviceToDevice, st));
+            o += (i64)cnt[q][0];
+        }
+        recs = ctx->d_gathered.ptr;
+    }
+    cudaError_t e = pairwise_fz_tail(ctx->pw, recs, nrec, n_nan, p, fc, ctx->n_obs, n_obs_min, alpha, fdr, rel_only, st, po, nl, &msg);
+    if (e != cudaSuccess && msg.find("unsupported size") != std::string::npos) return fail(ctx, FW_ERR_UNSUPPORTED, "fw_pairwise: %s", msg.c_str());
+    if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_pairwise: %s: %s", msg.c_str(), cudaGetErrorString(e));
+    return FW_OK;
+}
+
 extern "C" {
 
 const char* fw_build_info(void) {
@@ -293,6 +432,7 @@ int32_t fw_create(int32_t device, fw_ctx** out) {
 int32_t fw_destroy(fw_ctx* ctx) {
     if (!ctx) return FW_OK;
     cudaSetDevice(ctx->device);
+    fw_comm_detach(ctx);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 12; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
@@ -325,7 +465,7 @@ int32_t fw_set_index_base(fw_ctx* ctx, int32_t base) {
     ctx->index_base = base; return FW_OK;
 }
 void* fw_stream(fw_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
-int32_t fw_synchronize(fw_ctx* ctx) { if (!ctx) return FW_ERR_INVALID; CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return FW_OK; }
+int32_t fw_synchronize(fw_ctx* ctx) { if (!ctx) return FW_ERR_INVALID; CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return comm_check(ctx); }
 int64_t fw_launch_count(fw_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // device time (ms, CUDA events on the context's stream) of the last run of each phase:
@@ -604,6 +744,7 @@ int32_t fw_set_cor_f32(fw_ctx* ctx, const float* host_cor, int64_t p) {
     CK(ctx->d_cor.reserve((size_t)p * p));
     CK(cudaMemcpyAsync(ctx->d_cor.ptr, host_cor, sizeof(float) * (size_t)p * p, cudaMemcpyHostToDevice, ctx->stream));
     ctx->cor_p = p; if (ctx->p == 0) ctx->p = p;
+    ctx->cor_sharded = false; ctx->col.valid = false;
     CK(cudaStreamSynchronize(ctx->stream));          // the host buffer is borrowed for the duration of the call only
     return FW_OK;
 }
@@ -612,6 +753,7 @@ int32_t fw_adopt_cor_device(fw_ctx* ctx, const float* dev_cor, int64_t p) {
     NEED(dev_cor && p > 0, FW_ERR_INVALID, "fw_adopt_cor_device: bad arguments");
     ctx->d_cor.adopt(const_cast<float*>(dev_cor), (size_t)p * p);
     ctx->cor_p = p; if (ctx->p == 0) ctx->p = p;
+    ctx->cor_sharded = false; ctx->col.valid = false;
     return FW_OK;
 }
 int32_t fw_adopt_cor_device_rows(fw_ctx* ctx, const float* dev_cor, int64_t p, int64_t rows_allocated) {
@@ -619,6 +761,7 @@ int32_t fw_adopt_cor_device_rows(fw_ctx* ctx, const float* dev_cor, int64_t p, i
     NEED(dev_cor && p > 0 && rows_allocated >= p, FW_ERR_INVALID, "fw_adopt_cor_device_rows: bad arguments");
     ctx->d_cor.adopt(const_cast<float*>(dev_cor), (size_t)rows_allocated * p);
     ctx->cor_p = p; if (ctx->p == 0) ctx->p = p;
+    ctx->cor_sharded = false; ctx->col.valid = false;
     return FW_OK;
 }
 void* fw_cor_device_ptr(fw_ctx* ctx) { return ctx ? (void*)ctx->d_cor.ptr : nullptr; }
@@ -631,13 +774,15 @@ int32_t fw_upload_cor_f32(fw_ctx* ctx, const float* host, int64_t n, int64_t p, 
     CK(ctx->d_data_f32.reserve((size_t)n * p));
     if (!(ctx->d_cor.ptr && ctx->d_cor.owned && ctx->d_cor.cap >= (size_t)p * p)) CK(ctx->d_cor.reserve((size_t)p * p));
     std::string msg; int nl = 0;
+    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n;
+    table_changed(ctx);
+    PwEmit em; { int st_ = arm_collect(ctx, false, &em); if (st_ != FW_OK) return st_; }
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    cudaError_t e = cortc::run_overlapped(ctx->tc, host, ctx->d_data_f32.ptr, n, p, ld, ctx->d_cor.ptr, ctx->stream, ctx->copy_stream, ctx->chunk_ev, 12, &nl, &msg);
+    cudaError_t e = cortc::run_overlapped(ctx->tc, host, ctx->d_data_f32.ptr, n, p, ld, ctx->d_cor.ptr, ctx->stream, ctx->copy_stream, ctx->chunk_ev, 12, &nl, &msg, em);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_upload_cor_f32: %s: %s", msg.c_str(), cudaGetErrorString(e));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_valid[0] = true;
-    ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 0; ctx->n_obs = n;
-    table_changed(ctx); ctx->cor_p = p;
+    ctx->cor_p = p; ctx->cor_sharded = false; ctx->col.valid = ctx->col.armed;
     CK(cudaStreamSynchronize(ctx->copy_stream));     // every chunk has left the (borrowed) host buffer; the GEMM tail may still be running
     if (host_out) {
         CK(cudaMemcpyAsync(host_out, ctx->d_cor.ptr, sizeof(float) * (size_t)p * p, cudaMemcpyDeviceToHost, ctx->stream));
@@ -679,7 +824,7 @@ int32_t fw_cor_rows(fw_ctx* ctx, int32_t tile_row_begin, int32_t tile_row_end) {
 }
 int32_t fw_cor_symmetrize(fw_ctx* ctx) {
     if (!ctx) return FW_ERR_INVALID;
-    NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_cor_symmetrize: no cor_mat resident");
+    NEED(has_cor(ctx), FW_ERR_STATE, "fw_cor_symmetrize: no cor_mat resident");
     CK(cudaSetDevice(ctx->device));
     const unsigned nb = (unsigned)((ctx->cor_p + 31) / 32);
     cortc::cor_symmetrize_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(ctx->d_cor.ptr, ctx->cor_p);
@@ -696,16 +841,180 @@ int32_t fw_cor_matrix(fw_ctx* ctx, float* host_out) {
     if (!(ctx->d_cor.ptr && ctx->d_cor.owned && ctx->d_cor.cap >= (size_t)p * p)) CK(ctx->d_cor.reserve((size_t)p * p));
     std::string msg;
     int nl = 0;
+    PwEmit em; { int st_ = arm_collect(ctx, false, &em); if (st_ != FW_OK) return st_; }
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    cudaError_t e = cortc::run(ctx->tc, ctx->d_data_f32.ptr, ctx->n, p, ctx->ld, ctx->d_cor.ptr, ctx->stream, &nl, &msg);
+    cudaError_t e = cortc::run(ctx->tc, ctx->d_data_f32.ptr, ctx->n, p, ctx->ld, ctx->d_cor.ptr, ctx->stream, &nl, &msg, em);
     ctx->launches += nl;
     if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_cor_matrix: %s: %s", msg.c_str(), cudaGetErrorString(e));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_valid[0] = true;
-    ctx->cor_p = p;
+    ctx->cor_p = p; ctx->cor_sharded = false; ctx->col.valid = ctx->col.armed;
     if (host_out) {
         CK(cudaMemcpyAsync(host_out, ctx->d_cor.ptr, sizeof(float) * (size_t)p * p, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    return FW_OK;
+}
+
+int32_t fw_pairwise_prefetch(fw_ctx* ctx, double alpha, int64_t n_obs_min) {
+    if (!ctx) return FW_ERR_INVALID;
+    ctx->col.armed = alpha > 0.0;                    // alpha <= 0 disarms
+    ctx->col.alpha = alpha; ctx->col.n_obs_min = n_obs_min; ctx->col.valid = false;
+    return FW_OK;
+}
+
+int32_t fw_cor_gather(fw_ctx* ctx, const int64_t* idx, int64_t m, float* host_out) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(has_cor(ctx), FW_ERR_STATE, "fw_cor_gather: no cor_mat resident");
+    NEED(m >= 0 && (m == 0 || (idx && host_out)), FW_ERR_INVALID, "fw_cor_gather: NULL argument");
+    if (m == 0) return FW_OK;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<i64> h(m);
+    for (i64 i = 0; i < m; ++i) { h[i] = idx[i] - ctx->index_base; NEED(h[i] >= 0 && h[i] < ctx->cor_p, FW_ERR_INVALID, "fw_cor_gather: variable index out of range"); }
+    DevBuf<i64> di; DevBuf<float> dout;
+    CK(di.reserve(m)); CK(dout.reserve((size_t)m * m));
+    CK(cudaMemcpyAsync(di.ptr, h.data(), sizeof(i64) * m, cudaMemcpyHostToDevice, ctx->stream));
+    fwcomm::cor_gather_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, ctx->stream>>>(make_cor_view(ctx), di.ptr, m, dout.ptr);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host_out, dout.ptr, sizeof(float) * (size_t)m * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FW_OK;
+}
+
+// ---- multi-GPU group (comm.cuh) ---------------------------------------------------------------------------------------------
+int32_t fw_comm_handle_bytes(void) { return (int32_t)sizeof(fwcomm::Handle); }
+
+int32_t fw_comm_export(fw_ctx* ctx, int32_t rank, int32_t world, int64_t n, int64_t p, void* handle_out) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(handle_out && world >= 1 && world <= FW_MAX_RANKS && rank >= 0 && rank < world && n > 0 && p >= world, FW_ERR_INVALID,
+         "fw_comm_export: bad arguments (rank %d of %d, n = %lld, p = %lld; at most %d ranks)", rank, world, (long long)n, (long long)p, FW_MAX_RANKS);
+    NEED(!ctx->grp.attached, FW_ERR_STATE, "fw_comm_export: context is attached to a group (fw_comm_detach first)");
+    CK(cudaSetDevice(ctx->device));
+    fwcomm::Group& G = ctx->grp;
+    G.rank = rank; G.world = world; G.n = n; G.p = p;
+    G.nb = (int)((p + 127) / 128); G.h = (G.nb + 2 * world - 1) / (2 * world);
+    const i64 n_pairs = p * (p - 1) / 2;
+    G.list_cap = std::max<i64>((i64)1 << 16, std::min<i64>(n_pairs, n_pairs / (16 * (i64)world) + ((i64)1 << 16)));
+    const i64 cols = G.col0(rank + 1) - G.col0(rank);
+    CK(ctx->g_table.reserve((size_t)std::max<i64>(cols, 1) * n));
+    CK(ctx->g_cor.reserve((size_t)G.shard_rows() * p));
+    CK(ctx->g_list.reserve((size_t)G.list_cap));
+    CK(ctx->g_flags.reserve(fwcomm::N_FLAGS));
+    CK(ctx->g_err.reserve(4));
+    CK(cudaMemset(ctx->g_flags.ptr, 0, sizeof(u64) * fwcomm::N_FLAGS));
+    CK(cudaMemset(ctx->g_err.ptr, 0, sizeof(int) * 4));
+    G.own[fwcomm::B_TABLE] = ctx->g_table.ptr; G.own[fwcomm::B_COR] = ctx->g_cor.ptr; G.own[fwcomm::B_LIST] = ctx->g_list.ptr; G.own[fwcomm::B_FLAGS] = ctx->g_flags.ptr;
+    G.d_err = ctx->g_err.ptr; G.seq = 0;
+    fwcomm::Handle H; memset(&H, 0, sizeof(H));
+    H.pid = (int64_t)getpid(); H.device = ctx->device; H.rank = rank; H.world = world; H.n = n; H.p = p; H.list_cap = G.list_cap;
+    for (int b = 0; b < 4; ++b) { CK(cudaIpcGetMemHandle(&H.ipc[b], G.own[b])); H.raw[b] = G.own[b]; }
+    memcpy(handle_out, &H, sizeof(H));
+    G.exported = true;
+    return FW_OK;
+}
+
+int32_t fw_comm_detach(fw_ctx* ctx) {
+    if (!ctx) return FW_ERR_INVALID;
+    fwcomm::Group& G = ctx->grp;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int q = 0; q < FW_MAX_RANKS; ++q) for (int b = 0; b < 4; ++b) {
+        if (G.opened[q][b] && G.peer[q][b]) cudaIpcCloseMemHandle(G.peer[q][b]);
+        G.opened[q][b] = false; G.peer[q][b] = nullptr;
+    }
+    G.attached = false;
+    if (ctx->cor_sharded) { ctx->cor_sharded = false; ctx->cor_p = 0; }
+    ctx->col.valid = false;
+    return FW_OK;
+}
+
+int32_t fw_comm_attach(fw_ctx* ctx, const void* handles) {
+    if (!ctx) return FW_ERR_INVALID;
+    fwcomm::Group& G = ctx->grp;
+    NEED(handles, FW_ERR_INVALID, "fw_comm_attach: handles is NULL");
+    NEED(G.exported && !G.attached, FW_ERR_STATE, "fw_comm_attach: call fw_comm_export first (and fw_comm_detach before re-attaching)");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t me = (int64_t)getpid();
+    for (int q = 0; q < G.world; ++q) {
+        fwcomm::Handle H; memcpy(&H, (const char*)handles + (size_t)q * sizeof(H), sizeof(H));
+        NEED(H.rank == q && H.world == G.world && H.n == G.n && H.p == G.p && H.list_cap == G.list_cap, FW_ERR_INVALID,
+             "fw_comm_attach: handle %d does not describe rank %d of this group (rank %d, world %d, n %lld, p %lld)", q, q, H.rank, H.world, (long long)H.n, (long long)H.p);
+        if (q == G.rank) { for (int b = 0; b < 4; ++b) G.peer[q][b] = G.own[b]; continue; }
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, ctx->device, H.device));
+        NEED(can, FW_ERR_UNSUPPORTED, "fw_comm_attach: device %d cannot access device %d (no NVLink / P2P path)", ctx->device, H.device);
+        if (H.pid == me) {
+            cudaError_t e_ = cudaDeviceEnablePeerAccess(H.device, 0);
+            if (e_ == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e_ = cudaSuccess; }
+            if (e_ != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", H.device, cudaGetErrorString(e_));
+            for (int b = 0; b < 4; ++b) G.peer[q][b] = H.raw[b];
+        } else {
+            for (int b = 0; b < 4; ++b) {
+                cudaError_t e_ = cudaIpcOpenMemHandle(&G.peer[q][b], H.ipc[b], cudaIpcMemLazyEnablePeerAccess);
+                if (e_ != cudaSuccess) { fw_comm_detach(ctx); return fail(ctx, FW_ERR_CUDA, "cudaIpcOpenMemHandle (rank %d, buffer %d): %s", q, b, cudaGetErrorString(e_)); }
+                G.opened[q][b] = true;
+            }
+        }
+    }
+    G.attached = true; G.seq = 0;
+    return FW_OK;
+}
+
+// upload this rank's columns [p*rank/world, p*(rank+1)/world) of the table; after the call every rank's slice is in place
+int32_t fw_multi_set_data_f32(fw_ctx* ctx, const float* host_slice, int64_t ld) {
+    if (!ctx) return FW_ERR_INVALID;
+    fwcomm::Group& G = ctx->grp;
+    NEED(G.attached, FW_ERR_STATE, "fw_multi_set_data_f32: no group attached (fw_comm_export / fw_comm_attach)");
+    NEED(host_slice && ld >= G.n, FW_ERR_INVALID, "fw_multi_set_data_f32: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const i64 cols = G.col0(G.rank + 1) - G.col0(G.rank);
+    { int st_ = comm_barrier(ctx); if (st_ != FW_OK) return st_; }       // every rank has finished reading the previous table / cor_mat / lists
+    if (cols > 0) CK(cudaMemcpy2DAsync(ctx->g_table.ptr, G.n * sizeof(float), host_slice, ld * sizeof(float), G.n * sizeof(float), (size_t)cols, cudaMemcpyHostToDevice, ctx->stream));
+    { int st_ = comm_barrier(ctx); if (st_ != FW_OK) return st_; }       // every slice is in place
+    ctx->n = G.n; ctx->p = G.p; ctx->ld = G.n; ctx->data_kind = 2; ctx->n_obs = G.n;
+    table_changed(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));                               // the host buffer is borrowed for the duration of the call only
+    return comm_check(ctx);
+}
+
+// cor_mat = Float32.(cor(data)) (learning.jl:42-44) computed by the group: this rank's tile rows into its own shard
+int32_t fw_multi_cor(fw_ctx* ctx) {
+    if (!ctx) return FW_ERR_INVALID;
+    fwcomm::Group& G = ctx->grp;
+    NEED(G.attached && ctx->data_kind == 2, FW_ERR_STATE, "fw_multi_cor: no group table resident (fw_multi_set_data_f32)");
+    CK(cudaSetDevice(ctx->device));
+    const i64 n = G.n, p = G.p;
+    const i64 kp = (n + cortc::BK - 1) / cortc::BK * cortc::BK, p_pad = (p + cortc::BM - 1) / cortc::BM * cortc::BM;
+    CK(ctx->tc.reserve((size_t)2 * p_pad * kp));
+    __nv_bfloat16* zhi = ctx->tc.z; __nv_bfloat16* zlo = ctx->tc.z + (size_t)p_pad * kp;
+    std::string msg; int nl = 0;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    {   // fused all-gather + standardise: every column is read from its owner's slice over NVLink
+        fwcomm::PeerSlices ps;
+        for (int q = 0; q <= FW_MAX_RANKS; ++q) ps.col0[q] = G.col0(q < G.world ? q : G.world);
+        for (int q = 0; q < FW_MAX_RANKS; ++q) ps.s[q] = q < G.world ? (const float*)G.peer[q][fwcomm::B_TABLE] : nullptr;
+        const int staged = n * (i64)sizeof(float) <= 200 * 1024 ? 1 : 0;
+        const size_t smem = staged ? (size_t)n * sizeof(float) : 0;
+        CK(cudaFuncSetAttribute(fwcomm::standardize_split_peer_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        fwcomm::standardize_split_peer_kernel<256><<<(unsigned)p_pad, 256, smem, ctx->stream>>>(ps, G.world, n, p, kp, zhi, zlo, staged);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    cudaError_t e = cortc::encode_map(&ctx->tcp.tm_hi, zhi, kp, p_pad, &msg);
+    if (e == cudaSuccess) e = cortc::encode_map(&ctx->tcp.tm_lo, zlo, kp, p_pad, &msg);
+    if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_multi_cor: %s", msg.c_str());
+    ctx->tcp.kp = kp; ctx->tcp.p_pad = p_pad; ctx->tcp.nb = (int)(p_pad / cortc::BM); ctx->tcp.valid = true;
+    PwEmit em; { int st_ = arm_collect(ctx, true, &em); if (st_ != FW_OK) return st_; }
+    const int grp_id[2] = {G.rank, 2 * G.world - 1 - G.rank};
+    for (int k = 0; k < 2; ++k) {
+        e = cortc::run_rows(ctx->tcp, ctx->g_cor.ptr, p, grp_id[k] * G.h, (grp_id[k] + 1) * G.h, false, ctx->stream, &nl, &msg, em, G.world, G.h);
+        if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_multi_cor: %s: %s", msg.c_str(), cudaGetErrorString(e));
+    }
+    ctx->launches += nl;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_valid[0] = true;
+    if (em.on) CK(cudaMemcpyAsync(G.flags_of(G.rank) + fwcomm::F_LIST_N, ctx->d_listcnt.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+    { int st_ = comm_barrier(ctx); if (st_ != FW_OK) return st_; }       // the whole distributed cor_mat (and every rank's candidate list) is complete
+    ctx->cor_p = p; ctx->cor_sharded = true; ctx->col.valid = ctx->col.armed;
     return FW_OK;
 }
 
@@ -721,7 +1030,7 @@ int32_t fw_test_batch(fw_ctx* ctx, int32_t kind, int64_t n_tests, const int64_t*
     if (nzk) { int st_ = ensure_nz_table(ctx, &nzt); if (st_ != FW_OK) return st_; }
     if (disc) NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_test_batch: no discrete table resident (fw_set_data_i32)");
     else if (!nzk) {
-        NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_test_batch: no cor_mat resident (fw_cor_matrix / fw_set_cor_f32)");
+        NEED(has_cor(ctx), FW_ERR_STATE, "fw_test_batch: no cor_mat resident (fw_cor_matrix / fw_set_cor_f32)");
         NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_test_batch: number of observations unknown (fw_set_data_f32 / fw_set_n_obs)");
     }
     if (n_tests == 0) return FW_OK;
@@ -759,7 +1068,7 @@ int32_t fw_test_batch(fw_ctx* ctx, int32_t kind, int64_t n_tests, const int64_t*
     } else {
         FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
         int threads = 128; i64 blocks = (n_tests + threads - 1) / threads;
-        fz_test_batch_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->d_cor.ptr, p, n_tests, dx.ptr, dy.ptr, dk.ptr, dz.ptr, fc, ctx->n_obs, n_obs_min, dout.ptr);
+        fz_test_batch_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(make_cor_view(ctx), p, n_tests, dx.ptr, dy.ptr, dk.ptr, dz.ptr, fc, ctx->n_obs, n_obs_min, dout.ptr);
     }
     ctx->launches++;
     CK(cudaGetLastError());
@@ -782,7 +1091,7 @@ int32_t fw_test_subsets_batch(fw_ctx* ctx, int32_t kind, int64_t n_jobs, const i
     if (nzk) { int st_ = ensure_nz_table(ctx, &nzt); if (st_ != FW_OK) return st_; }
     if (disc) NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_test_subsets: no discrete table resident (fw_set_data_i32)");
     else if (!nzk) {
-        NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_test_subsets: no cor_mat resident");
+        NEED(has_cor(ctx), FW_ERR_STATE, "fw_test_subsets: no cor_mat resident");
         NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_test_subsets: number of observations unknown");
     }
     if (n_jobs == 0) return FW_OK;
@@ -843,7 +1152,7 @@ int32_t fw_test_subsets_batch(fw_ctx* ctx, int32_t kind, int64_t n_jobs, const i
         for (int c = 0; c < 5; ++c) cls[c].clear();
     }
     SubsetsArgs a;
-    a.cor = ctx->d_cor.ptr; a.p = p; a.X = dx.ptr; a.Y = dy.ptr; a.z_off = dzo.ptr; a.z_idx = dzi.ptr;
+    a.cv = make_cor_view(ctx); a.p = p; a.X = dx.ptr; a.Y = dy.ptr; a.z_off = dzo.ptr; a.z_idx = dzi.ptr;
     a.max_k = max_k; a.alpha = alpha; a.max_tests = max_tests; a.fc = make_fz_consts(ctx->n_obs, n_obs_min);
     a.out = dres.ptr; a.out_Zs = dZs.ptr; a.out_k = dk.ptr; a.num_tests = dnt.ptr; a.frac = dfr.ptr; a.executed_total = ctx->d_exec.ptr;
     a.counter = ctx->d_counter.ptr;
@@ -916,7 +1225,7 @@ int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_
     if (nzk) { int st_ = ensure_nz_table(ctx, &nzt); if (st_ != FW_OK) return st_; }
     if (disc) NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_pairwise: no discrete table resident (fw_set_data_i32)");
     else if (!nzk) {
-        NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_pairwise: no cor_mat resident (fw_cor_matrix / fw_set_cor_f32)");
+        NEED(has_cor(ctx), FW_ERR_STATE, "fw_pairwise: no cor_mat resident (fw_cor_matrix / fw_set_cor_f32)");
         NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_pairwise: number of observations unknown");
     }
     CK(cudaSetDevice(ctx->device));
@@ -931,9 +1240,10 @@ int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_
     } else if (nzk) {
         e = pairwise_fznz_run(ctx->pw, ctx->nzplanes, nzt, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0, ctx->stream, &po, &nl, &msg);
     } else {
-        FzConsts fc = make_fz_consts(ctx->n_obs, n_obs_min);
-        e = pairwise_fz_run(ctx->pw, ctx->d_cor.ptr, p, fc, ctx->n_obs, n_obs_min, alpha, fdr != 0, correct_reliable_only != 0,
-                            ctx->sm_count, ctx->stream, &po, &nl, &msg);
+        int st_ = run_pairwise_fz(ctx, alpha, n_obs_min, fdr != 0, correct_reliable_only != 0, &po, &nl);
+        ctx->launches += nl; nl = 0;
+        if (st_ != FW_OK) return st_;
+        e = cudaSuccess;
     }
     ctx->launches += nl;
     if (e != cudaSuccess && msg.find("unsupported size") != std::string::npos) return fail(ctx, FW_ERR_UNSUPPORTED, "fw_pairwise: %s", msg.c_str());
@@ -1039,7 +1349,7 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
     if (nzk) { int st_ = ensure_nz_table(ctx, &nzt); if (st_ != FW_OK) return st_; }
     if (disc) NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_hiton_pc: no discrete table resident (fw_set_data_i32)");
     else if (!nzk) {
-        NEED(ctx->d_cor.ptr && ctx->cor_p > 0, FW_ERR_STATE, "fw_hiton_pc: no cor_mat resident");
+        NEED(has_cor(ctx), FW_ERR_STATE, "fw_hiton_pc: no cor_mat resident");
         NEED(ctx->n_obs >= 0, FW_ERR_STATE, "fw_hiton_pc: number of observations unknown");
     }
     NEED(ctx->uni_entries >= 0, FW_ERR_STATE, "fw_hiton_pc: no neighbour lists resident (fw_pairwise / fw_set_univar_nbrs)");
@@ -1142,7 +1452,7 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         }
     }
     HitonArgs a;
-    a.cor = nzk ? nullptr : ctx->d_cor.ptr; a.p = p;
+    a.cv = make_cor_view(ctx); a.p = p;
     a.uni_off = ctx->d_uni_off.ptr; a.uni_nbr = ctx->d_uni_nbr.ptr; a.uni_stat = ctx->d_uni_stat.ptr; a.uni_p = ctx->d_uni_p.ptr;
     a.targets = dt.ptr; a.out_off = doff.ptr; a.counter = ctx->d_counter.ptr;
     a.max_k = max_k; a.alpha = alpha; a.max_tests = max_tests; a.fc = make_fz_consts(ctx->n_obs < 0 ? 0 : ctx->n_obs, n_obs_min);

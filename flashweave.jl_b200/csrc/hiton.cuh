@@ -17,7 +17,7 @@
 
 struct HitonArgs {
     // resident inputs
-    const float* cor; i64 p;                 // cor_mat (p x p, symmetric)
+    CorView cv; i64 p;                       // cor_mat (p x p, symmetric; row-sharded over the GPUs of the group)
     const i64* uni_off; const i64* uni_nbr;  // univariate neighbour CSR over all p variables
     const double* uni_stat; const double* uni_p;
     // work list
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
                 // gather the candidate's correlations with T and the members into slot ys
                 for (int s = tid; s <= M; s += THREADS) {
                     i64 other = (s == 0) ? T : member[s - 1];
-                    float v = __ldg(a.cor + cand * a.p + other);
+                    float v = a.cv.at(cand, other);
                     R[ys * ld + s] = v; R[s * ld + ys] = v;
                 }
             } else {
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
 // Batched test_subsets: one CTA per (X, Y, Z_total) job.
 // -------------------------------------------------------------------------------------------
 struct SubsetsArgs {
-    const float* cor; i64 p;
+    CorView cv; i64 p;
     const i64* X; const i64* Y; const i64* z_off; const i64* z_idx;
     const int* sel; int n_sel; int* counter;
     int max_k; double alpha; i64 max_tests; FzConsts fc;
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(THREADS) subsets_fz_kernel(SubsetsArgs a) {
                 int i = e / nv, j = e % nv;
                 i64 vi = i == 0 ? a.X[job] : (i == 1 ? a.Y[job] : a.z_idx[z0 + i - 2]);
                 i64 vj = j == 0 ? a.X[job] : (j == 1 ? a.Y[job] : a.z_idx[z0 + j - 2]);
-                R[i * ld + j] = __ldg(a.cor + vi * a.p + vj);
+                R[i * ld + j] = a.cv.at(vi, vj);
             }
             __syncthreads();
         } else {
@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(THREADS) subsets_fz_kernel(SubsetsArgs a) {
 // -------------------------------------------------------------------------------------------
 // Independent conditional tests, one thread each (fw_test_batch, kind fz): test(X,Y,Zs,...)
 // -------------------------------------------------------------------------------------------
-__global__ void fz_test_batch_kernel(const float* cor, i64 p, i64 n_tests, const i64* X, const i64* Y, const int* k,
+__global__ void fz_test_batch_kernel(const CorView cv, i64 p, i64 n_tests, const i64* X, const i64* Y, const int* k,
                                      const i64* Zs, FzConsts fc, i64 n_rows, i64 n_obs_min, DevResult* out) {
     i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tests) return;
@@ -648,13 +648,13 @@ __global__ void fz_test_batch_kernel(const float* cor, i64 p, i64 n_tests, const
     int kk = k[t];
     if (kk == 0) {
         // tests.jl:108-160 with a precomputed cor_mat (:149-156)
-        double stat = (n_rows >= n_obs_min) ? (double)__ldg(cor + var[0] * p + var[1]) : 0.0;
+        double stat = (n_rows >= n_obs_min) ? (double)cv.at(var[0], var[1]) : 0.0;
         if (n_rows < n_obs_min) { out[t] = make_result(0.0, 1.0, 0, 0 >= n_obs_min); return; }
         out[t] = make_result(stat, fz_pval_dev(stat, fc), 0, true);
         return;
     }
     for (int i = kk + 2; i < 5; ++i) var[i] = var[0];
-    CorGlobal r; r.cor = cor; r.p = p; r.var = var;
+    CorGlobal r; r.cv = cv; r.var = var;
     FzTest ft = fz_cond_test(r, 0, 1, 2, 3, 4, kk, fc);
     out[t] = make_result(ft.stat, ft.pval, 0, ft.suff);
 }

@@ -4,10 +4,15 @@
 // condensed_stats_to_dict (tests.jl:372-388), all on the device.
 //
 // HBM-bound: the algorithmic traffic is one 4-byte correlation per pair (2*p*(p-1) bytes
-// for the upper triangle), read twice (count pass + write pass) with fully coalesced
-// 128-byte row segments.  The exact p-value (fp64 log + erfc) is only evaluated for pairs
-// whose |r| is within reach of the alpha threshold; everything else is rejected by a
-// conservative float compare, so the fp64 pipe stays off the critical path.
+// for the upper triangle).  Raw candidates (|r| within reach of the alpha threshold: a
+// conservative float compare) are collected either for free in the epilogue of the cor_mat
+// GEMM (cor_tc.cuh, when fw_pairwise_prefetch announced the parameters) or by ONE coalesced
+// pass over the resident matrix (pw_fz_emit_kernel); the exact p-value (fp64 log + erfc) is
+// evaluated for the candidates only (~1 % of the pairs), densely, by pw_fz_select_kernel.
+// The candidates are unordered: Benjamini-Hochberg's result does not depend on the order of
+// tied p-values (every member of a tie receives the same adjusted value: the running minimum
+// of p*m/i reaches all of them from the last rank of the tie), and the neighbour lists are
+// sorted by (row, column) key afterwards.
 #pragma once
 #include <cub/cub.cuh>
 #include <string>
@@ -37,59 +42,62 @@ struct PairwiseScratch {
     ~PairwiseScratch() { for (int i = 0; i < 20; ++i) if (bufs[i]) cudaFree(bufs[i]); }
 };
 
-// One CTA per row X: counts (pass 0) or writes in ascending-Y order (pass 1) the pairs with raw p < alpha.
-// row_cnt[X] = {#raw-significant, #reliable (non-NaN p)}.
-template <int THREADS, int PASS>
-__global__ void __launch_bounds__(THREADS) pw_fz_rows_kernel(const float* __restrict__ cor, i64 p, FzConsts fc, double alpha, float r_lo,
-                                                             int reliable_only, int suff_all,
-                                                             unsigned int* row_sig, unsigned int* row_rel, const i64* row_base,
-                                                             int* c_x, int* c_y, double* c_p, double* c_stat) {
-    const i64 X = blockIdx.x;
+// One pass over the upper triangle of the locally held cor_mat rows: one CTA per row X, coalesced 128-byte row segments, every
+// |r| >= r_lo (or NaN: counted) becomes a raw candidate.  Hits are compacted into a per-warp shared-memory queue and flushed
+// with ONE global atomic per >= 64 records, so the append costs ~2e5 atomics at C4 instead of one per warp iteration.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) pw_fz_emit_kernel(const float* __restrict__ rows, i64 p, i64 row_global0, i64 row_local0, PwEmit e) {
+    constexpr int WARPS = THREADS / 32, QCAP = 96;
+    __shared__ PwRec q[WARPS][QCAP];
+    const i64 X = row_global0 + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* row = cor + X * p;
-    __shared__ unsigned int s_w[THREADS / 32];
-    __shared__ unsigned int s_base;
-    unsigned int n_sig = 0, n_rel = 0;
-    if (PASS == 1 && tid == 0) s_base = 0;
-    if (PASS == 1) __syncthreads();
-    const i64 base_out = PASS == 1 ? row_base[X] : 0;
+    const float* row = rows + (row_local0 + blockIdx.x) * p;
+    int qn = 0;                                         // warp-uniform
+    unsigned int n_nan = 0;
+    auto flush = [&]() {
+        u64 pos0 = 0;
+        if (lane == 0) pos0 = atomicAdd(&e.counters[0], (u64)qn);
+        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+        for (int i = lane; i < qn; i += 32) if ((i64)(pos0 + i) < e.cap) e.list[pos0 + i] = q[warp][i];
+        __syncwarp();
+        qn = 0;
+    };
     for (i64 y0 = X + 1; y0 < p; y0 += THREADS) {
         const i64 Y = y0 + tid;
-        bool sig = false, rel = false;
-        double pv = 0.0; float r = 0.0f;
+        bool hit = false; float r = 0.0f;
         if (Y < p) {
-            r = __ldg(row + Y);
-            // tests.jl:397-402: unreliable tests are stored as NaN; a NaN correlation gives a NaN p-value
-            rel = !isnan(r) && (suff_all || !reliable_only);
-            if (rel && fabsf(r) >= r_lo) {
-                pv = fz_pval_dev((double)r, fc);
-                sig = pv < alpha;
-            }
+            r = row[Y];
+            if (r != r) ++n_nan; else hit = fabsf(r) >= e.r_lo;
         }
-        if (PASS == 0) {
-            n_sig += sig; n_rel += rel;
-        } else {
-            unsigned int bal = __ballot_sync(0xffffffffu, sig);
-            if (lane == 0) s_w[warp] = __popc(bal);
-            __syncthreads();
-            unsigned int woff = 0, tot = 0;
-            for (int w = 0; w < THREADS / 32; ++w) { unsigned int c = s_w[w]; if (w < warp) woff += c; tot += c; }
-            unsigned int b = s_base;
-            if (sig) {
-                i64 pos = base_out + b + woff + __popc(bal & ((1u << lane) - 1u));
-                c_x[pos] = (int)X; c_y[pos] = (int)Y; c_p[pos] = pv; c_stat[pos] = (double)r;
-            }
-            __syncthreads();
-            if (tid == 0) s_base = b + tot;
+        const unsigned int bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+            if (hit) { PwRec rec; rec.x = (int)X; rec.y = (int)Y; rec.r = r; q[warp][qn + __popc(bal & ((1u << lane) - 1u))] = rec; }
+            qn += __popc(bal);
+            __syncwarp();
+            if (qn >= 64) flush();
         }
     }
-    if (PASS == 0) {
-        typedef cub::BlockReduce<unsigned int, THREADS> BR;
-        __shared__ typename BR::TempStorage tmp;
-        unsigned int ts = BR(tmp).Sum(n_sig);
-        __syncthreads();
-        unsigned int tr = BR(tmp).Sum(n_rel);
-        if (tid == 0) { row_sig[X] = ts; row_rel[X] = tr; }
+    if (qn) flush();
+    n_nan = __reduce_add_sync(0xffffffffu, n_nan);
+    if (lane == 0 && n_nan) atomicAdd(&e.counters[1], (u64)n_nan);
+}
+
+// exact p-value of every raw candidate; the raw-significant ones (p < alpha) are appended (unordered, one atomic per warp) to the
+// compacted arrays the Benjamini-Hochberg stage works on
+__global__ void pw_fz_select_kernel(const PwRec* __restrict__ recs, i64 n, FzConsts fc, double alpha, u64* counter,
+                                    int* c_x, int* c_y, double* c_p, double* c_stat) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool sig = false; PwRec rec; double pv = 0.0;
+    if (i < n) { rec = recs[i]; pv = fz_pval_dev((double)rec.r, fc); sig = pv < alpha; }
+    const unsigned int bal = __ballot_sync(0xffffffffu, sig);
+    if (!bal) return;
+    u64 pos0 = 0;
+    if (lane == 0) pos0 = atomicAdd(counter, (u64)__popc(bal));
+    pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+    if (sig) {
+        const u64 pos = pos0 + (u64)__popc(bal & ((1u << lane) - 1u));
+        c_x[pos] = rec.x; c_y[pos] = rec.y; c_p[pos] = pv; c_stat[pos] = (double)rec.r;
     }
 }
 
@@ -239,73 +247,61 @@ __global__ void pw_gather_pairs(const unsigned int* perm, const int* sx, const i
     if (i < n) { unsigned int j = perm[i]; dx[i] = sx[j]; dy[i] = sy[j]; dp[i] = sp[j]; ds[i] = ss[j]; }
 }
 
-static cudaError_t pairwise_fz_run(PairwiseScratch& S, const float* d_cor, i64 p, FzConsts fc, i64 n_rows, i64 n_obs_min, double alpha,
-                                   bool fdr, bool reliable_only, int sm_count, cudaStream_t st, PairwiseOut* out, int* n_launch, std::string* msg) {
-    (void)sm_count;
+// conservative |r| pre-filter of the univariate Fisher-z test: p < alpha  <=>  |r| > tanh(z_alpha / sqrt(n-3)); 1e-4 relative safety band.
+// 2.0f: nothing can be significant (n - 3 <= 0: z = 0, p = 1; rows < n_obs_min: p = 1)
+static float pairwise_fz_r_lo(const FzConsts& fc, i64 n_rows, i64 n_obs_min, double alpha) {
+    if (!(fc.sf_pos && n_rows >= n_obs_min) || !(alpha > 0.0)) return 2.0f;
+    if (alpha >= 1.0) return 0.0f;
+    double lo = 0.0, hi = 40.0;                    // z_alpha from erfc(z/sqrt2) = alpha by bisection (host, once)
+    for (int it = 0; it < 200; ++it) { double mid = 0.5 * (lo + hi); if (std::erfc(mid * 0.70710678118654752440) > alpha) lo = mid; else hi = mid; }
+    return (float)(std::tanh(lo / (2.0 * fc.half_sqrt_sf)) * (1.0 - 1e-4));
+}
+
+// one pass over `n_rows` locally held rows (global row ids row_global0.., stored from local row row_local0 of `rows`)
+static cudaError_t pairwise_fz_emit(const float* rows, i64 p, i64 row_global0, i64 row_local0, i64 n_rows, const PwEmit& e, cudaStream_t st,
+                                    int* n_launch, std::string* msg) {
+    if (n_rows <= 0) return cudaSuccess;
+    pw_fz_emit_kernel<256><<<(unsigned)n_rows, 256, 0, st>>>(rows, p, row_global0, row_local0, e);
+    (*n_launch)++;
+    PWCK(cudaGetLastError(), "pw_fz_emit_kernel");
+    return cudaSuccess;
+}
+
+// second half: exact p-values of the nrec raw candidates (of all ranks), Benjamini-Hochberg, neighbour CSR
+static cudaError_t pairwise_fz_tail(PairwiseScratch& S, const PwRec* recs, i64 nrec, i64 n_nan, i64 p, FzConsts fc, i64 n_rows, i64 n_obs_min, double alpha,
+                                    bool fdr, bool reliable_only, cudaStream_t st, PairwiseOut* out, int* n_launch, std::string* msg) {
     const int T = 256;
     const i64 n_pairs = p * (p - 1) / 2;
     out->n_tests = n_pairs;
-    // suff_power of every univariate fz test is (n >= n_obs_min) (tests.jl:159); below that the stat is 0 and p is 1
-    const int suff_all = n_rows >= n_obs_min ? 1 : 0;
-    // conservative pre-filter: p < alpha  <=>  |r| > tanh(z_alpha / sqrt(n-3)); keep a 1e-4 relative safety band
-    float r_lo = 2.0f;   // nothing can be significant when n - 3 <= 0 (z = 0, p = 1) or rows < n_obs_min (p = 1)
-    if (fc.sf_pos && suff_all) {
-        // z_alpha from erfc(z/sqrt2) = alpha by bisection (host, once)
-        double lo = 0.0, hi = 40.0;
-        for (int it = 0; it < 200; ++it) { double mid = 0.5 * (lo + hi); if (std::erfc(mid * 0.70710678118654752440) > alpha) lo = mid; else hi = mid; }
-        double rc = std::tanh(lo / (2.0 * fc.half_sqrt_sf));
-        r_lo = (float)(rc * (1.0 - 1e-4));
-        if (!(alpha > 0.0)) r_lo = 2.0f;
-        if (alpha >= 1.0) r_lo = 0.0f;
-    }
-    unsigned int *row_sig, *row_rel; i64 *row_sig64, *row_base, *tot2;
-    PWCK(S.get(0, sizeof(unsigned int) * (p + 1), (void**)&row_sig), "alloc");
-    PWCK(S.get(1, sizeof(unsigned int) * (p + 1), (void**)&row_rel), "alloc");
-    PWCK(S.get(2, sizeof(i64) * (p + 1), (void**)&row_sig64), "alloc");
-    PWCK(S.get(3, sizeof(i64) * (p + 1), (void**)&row_base), "alloc");
-    PWCK(S.get(4, sizeof(i64) * 4, (void**)&tot2), "alloc");
-    PWCK(cudaMemsetAsync(row_sig, 0, sizeof(unsigned int) * (p + 1), st), "memset");
-    PWCK(cudaMemsetAsync(row_rel, 0, sizeof(unsigned int) * (p + 1), st), "memset");
-    pw_fz_rows_kernel<T, 0><<<(unsigned)p, T, 0, st>>>(d_cor, p, fc, alpha, r_lo, reliable_only ? 1 : 0, suff_all, row_sig, row_rel, nullptr, nullptr, nullptr, nullptr, nullptr);
-    (*n_launch)++;
-    PWCK(cudaGetLastError(), "pw_fz_rows_kernel<0>");
-    // exclusive scan of the per-row counts (+ totals)
-    void* tmp = nullptr; size_t tmp_bytes = 0, need = 0;
-    pw_u32_to_i64<<<pw_blocks(p + 1, T), T, 0, st>>>(row_sig, row_sig64, p + 1); (*n_launch)++;
-    cub::DeviceScan::ExclusiveSum(nullptr, need, row_sig64, row_base, (int)(p + 1), st);
-    tmp_bytes = need;
-    PWCK(S.get(5, tmp_bytes, &tmp), "alloc");
-    PWCK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, row_sig64, row_base, (int)(p + 1), st), "scan"); (*n_launch)++;
-    i64* rel64 = row_sig64;   // reuse after the scan
-    pw_u32_to_i64<<<pw_blocks(p + 1, T), T, 0, st>>>(row_rel, rel64, p + 1); (*n_launch)++;
-    cub::DeviceReduce::Sum(nullptr, need, rel64, tot2, (int)(p + 1), st);
-    if (need > tmp_bytes) { tmp_bytes = need; PWCK(S.get(5, tmp_bytes, &tmp), "alloc"); }
-    PWCK(cub::DeviceReduce::Sum(tmp, tmp_bytes, rel64, tot2, (int)(p + 1), st), "reduce"); (*n_launch)++;
-    i64 h_tot[2] = {0, 0};
-    PWCK(cudaMemcpyAsync(&h_tot[0], row_base + p, sizeof(i64), cudaMemcpyDeviceToHost, st), "d2h");
-    PWCK(cudaMemcpyAsync(&h_tot[1], tot2, sizeof(i64), cudaMemcpyDeviceToHost, st), "d2h");
-    PWCK(cudaStreamSynchronize(st), "sync");
-    const i64 nf = h_tot[0];
-    // tests.jl:521-526: m = number of tests, minus the NaN ones when correct_reliable_only
-    i64 n_nan = n_pairs - h_tot[1];
-    const i64 m = reliable_only ? n_pairs - n_nan : n_pairs;
-    // (without correct_reliable_only the NaN count only contains NaN correlations, which the reference keeps in m)
-    out->n_reliable = h_tot[1]; out->n_raw_sig = nf;
-
+    // suff_power of every univariate fz test is (n >= n_obs_min) (tests.jl:159); tests.jl:397-402: unreliable tests are stored as NaN,
+    // a NaN correlation gives a NaN p-value; tests.jl:521-526: m = number of tests, minus the NaN ones when correct_reliable_only
+    const bool suff_all = n_rows >= n_obs_min;
+    const i64 n_rel = (suff_all || !reliable_only) ? n_pairs - n_nan : 0;
+    const i64 m = reliable_only ? n_rel : n_pairs;
+    out->n_reliable = n_rel;
     i64* d_off; PWCK(S.get(6, sizeof(i64) * (p + 1), (void**)&d_off), "alloc");
     out->d_off = d_off;
+    i64 nf = 0;
+    int *c_x = nullptr, *c_y = nullptr; double *c_p = nullptr, *c_stat = nullptr;
+    if (nrec > 0 && n_rel > 0) {
+        u64* cnt; PWCK(S.get(4, sizeof(u64) * 4, (void**)&cnt), "alloc");
+        PWCK(S.get(7, sizeof(int) * nrec, (void**)&c_x), "alloc");
+        PWCK(S.get(8, sizeof(int) * nrec, (void**)&c_y), "alloc");
+        PWCK(S.get(9, sizeof(double) * nrec, (void**)&c_p), "alloc");
+        PWCK(S.get(10, sizeof(double) * nrec, (void**)&c_stat), "alloc");
+        PWCK(cudaMemsetAsync(cnt, 0, sizeof(u64), st), "memset");
+        pw_fz_select_kernel<<<pw_blocks(nrec, T), T, 0, st>>>(recs, nrec, fc, alpha, cnt, c_x, c_y, c_p, c_stat); (*n_launch)++;
+        PWCK(cudaGetLastError(), "pw_fz_select_kernel");
+        u64 h = 0;
+        PWCK(cudaMemcpyAsync(&h, cnt, sizeof(u64), cudaMemcpyDeviceToHost, st), "d2h");
+        PWCK(cudaStreamSynchronize(st), "sync");
+        nf = (i64)h;
+    }
+    out->n_raw_sig = nf;
     if (nf == 0) {
         PWCK(cudaMemsetAsync(d_off, 0, sizeof(i64) * (p + 1), st), "memset");
         out->n_entries = 0; out->d_nbr = nullptr; out->d_stat = nullptr; out->d_adjp = nullptr;
         return cudaSuccess;
     }
-    int *c_x, *c_y; double *c_p, *c_stat;
-    PWCK(S.get(7, sizeof(int) * nf, (void**)&c_x), "alloc");
-    PWCK(S.get(8, sizeof(int) * nf, (void**)&c_y), "alloc");
-    PWCK(S.get(9, sizeof(double) * nf, (void**)&c_p), "alloc");
-    PWCK(S.get(10, sizeof(double) * nf, (void**)&c_stat), "alloc");
-    pw_fz_rows_kernel<T, 1><<<(unsigned)p, T, 0, st>>>(d_cor, p, fc, alpha, r_lo, reliable_only ? 1 : 0, suff_all, nullptr, nullptr, row_base, c_x, c_y, c_p, c_stat);
-    (*n_launch)++;
-    PWCK(cudaGetLastError(), "pw_fz_rows_kernel<1>");
     return pairwise_finish(S, c_x, c_y, c_p, c_stat, nf, m, p, alpha, fdr, st, out, n_launch, msg);
 }

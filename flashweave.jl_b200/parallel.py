@@ -55,7 +55,29 @@ class MergedResult:
         return self._pc[i]
 
 
-# ---- row-sharded correlation matrix -------------------------------------------------------------------------------------
+# ---- the GPUs of one node as a group (include/fwgpu.h "multi-GPU"; csrc/comm.cuh) ------------------------------------------
+def exchange_handles(dist, blob):
+    """all-gather the ranks' fixed-size fw_comm_export blobs (a few hundred bytes; setup, not data path)"""
+    world = dist.get_world_size()
+    bucket = [None] * world
+    dist.all_gather_object(bucket, bytes(bytearray(np.asarray(blob, np.uint8))))
+    return np.frombuffer(b"".join(bucket), np.uint8).copy()
+
+
+def attach_group(dist, eng, n, p):
+    """fw_comm_export on every rank, exchange of the handles, fw_comm_attach: afterwards Engine.multi_set_data_ptr /
+    multi_cor / pw_univar_neighbors / si_HITON_PC work on the row-sharded cor_mat without any further collective."""
+    blob = eng.comm_export(dist.get_rank(), dist.get_world_size(), n, p)
+    eng.comm_attach(exchange_handles(dist, blob))
+    dist.barrier()                                   # every rank has mapped its peers before anyone starts a pass
+
+
+def table_slice(p, rank, world):
+    """columns [p*rank/world, p*(rank+1)/world) of the table belong to `rank` (the library's partition)"""
+    return p * rank // world, p * (rank + 1) // world
+
+
+# ---- row-sharded correlation matrix with a host-side NCCL exchange (superseded by the group API above) -------------------------------------------------------------------------------------
 def cor_groups(n_tile_rows, world):
     """Split the tile rows of the upper-triangular cor_mat GEMM into 2*world equal contiguous groups; rank r owns group r
     (long tile rows) and group 2*world-1-r (short ones), so every rank computes the same number of 128x128 tiles.

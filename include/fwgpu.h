@@ -134,6 +134,32 @@ int32_t fw_cor_prepare(fw_ctx* ctx, int32_t* n_tile_rows);
 int32_t fw_cor_rows(fw_ctx* ctx, int32_t tile_row_begin, int32_t tile_row_end);
 int32_t fw_cor_symmetrize(fw_ctx* ctx);
 
+/* cor(idx[i], idx[j]) for a list of m variables (row-major m x m): a sub-matrix of the resident cor_mat without moving all of
+ * it - the only way to look at a row-sharded matrix from the host */
+int32_t fw_cor_gather(fw_ctx* ctx, const int64_t* idx, int64_t m, float* host_out);
+
+/* ---- multi-GPU: the GPUs of one node as a group -------------------------------------------------------------------------
+ * Replaces the worker pool / RemoteChannels of src/interleaved.jl:76-93 and the SharedArray table of src/learning.jl:553-560
+ * for parallel="single" semantics (targets are independent given the pairwise stage, src/learning.jl:137-138).  One context per
+ * GPU, normally one process per GPU.  Setup: every rank calls fw_comm_export (allocates its share of an n x p job and writes a
+ * fixed-size opaque handle of fw_comm_handle_bytes() bytes), the host language all-gathers the handles (Distributed /
+ * torch.distributed / a file), every rank calls fw_comm_attach with the world x handle_bytes blob in rank order (CUDA IPC
+ * mappings; plain peer access between contexts of one process).  From then on no collective library and no host round trip is
+ * involved in the data path (csrc/comm.cuh): each rank uploads 1/world of the table columns over its own PCIe link
+ * (fw_multi_set_data_f32: host_slice points at column p*rank/world of the column-major table), fw_multi_cor computes the rank's
+ * tile rows of cor_mat - reading every column from its owner's HBM over NVLink inside the standardising kernel - and leaves the
+ * matrix ROW-SHARDED; fw_pairwise (FW_FZ) pulls the peers' compact candidate lists for the global Benjamini-Hochberg step;
+ * fw_hiton_pc, fw_test_batch, fw_test_subsets and fw_cor_gather dereference the owners' shards through the peer mappings.
+ * The fw_multi_* calls and fw_pairwise are COLLECTIVE in a group: every rank must issue the same sequence (ordering between
+ * ranks is a device-side barrier on the ranks' own streams, with a time-out: a missing peer is an error, never a hang).
+ * Results are identical to one GPU.  Contexts of one process need one host thread per context. */
+int32_t fw_comm_handle_bytes(void);
+int32_t fw_comm_export(fw_ctx* ctx, int32_t rank, int32_t world, int64_t n, int64_t p, void* handle_out);
+int32_t fw_comm_attach(fw_ctx* ctx, const void* handles /* world x fw_comm_handle_bytes(), rank order */);
+int32_t fw_comm_detach(fw_ctx* ctx);
+int32_t fw_multi_set_data_f32(fw_ctx* ctx, const float* host_slice, int64_t ld);
+int32_t fw_multi_cor(fw_ctx* ctx);
+
 /* ---- single tests ---------------------------------------------------------------------- */
 /* test(X, Y, Zs, data, test_obj, ...) for a batch of independent tests
  * (src/tests.jl:28 / :108 with k = 0, :184 / :250 with k in 1..3).  Zs is n_tests x 3,
@@ -167,6 +193,11 @@ int32_t fw_test_subsets_batch(fw_ctx* ctx, int32_t kind, int64_t n_jobs, const i
  * and can be copied out as CSR. */
 int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_t n_obs_min,
                     int32_t fdr, int32_t correct_reliable_only, int64_t* n_entries);
+/* Announce the (alpha, n_obs_min) of the next fw_pairwise(FW_FZ): fw_cor_matrix / fw_upload_cor_f32 / fw_multi_cor then collect
+ * the raw candidates (|r| within reach of the threshold) in the GEMM epilogue, where every tile is still in registers, and
+ * fw_pairwise does not read the p x p matrix again (src/tests.jl:470-478 looks each correlation up a second time).  Purely an
+ * optimisation: with other parameters, or without the announcement, fw_pairwise scans the resident matrix once.  alpha <= 0 disarms. */
+int32_t fw_pairwise_prefetch(fw_ctx* ctx, double alpha, int64_t n_obs_min);
 int32_t fw_pairwise_copy(fw_ctx* ctx, int64_t* offsets /* p+1 */, int64_t* nbr, double* stat, double* adjp);
 /* install caller-provided neighbour lists (the `all_univar_nbrs` argument of LGL, src/learning.jl:213,235-242) */
 int32_t fw_set_univar_nbrs(fw_ctx* ctx, const int64_t* offsets /* p+1 */, const int64_t* nbr,

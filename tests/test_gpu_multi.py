@@ -1,13 +1,23 @@
-"""Multi-GPU tests (need >= 2 CUDA devices; skipped otherwise): the row-sharded cor_mat (balanced tile-row groups, two in-place
-NCCL all-gathers, symmetrise) is bit-identical to the single-GPU fw_cor_matrix, and target-sharded HITON-PC merges to the
-single-GPU graph."""
+"""Multi-GPU tests (need >= 2 CUDA devices; skipped otherwise) of the library's group path (include/fwgpu.h "multi-GPU",
+csrc/comm.cuh): every rank uploads its columns, fw_multi_cor computes its tile rows reading the peers' slices over NVLink and
+leaves cor_mat row-sharded, fw_pairwise pulls the peers' candidate lists, fw_hiton_pc reads the owners' shards through peer
+mappings.  Everything must be bit-identical to one GPU: cor_mat (fw_cor_gather), neighbour lists, PC sets, graph.
+Two set-ups: one process per GPU (CUDA IPC handles exchanged through torch.distributed) and two contexts in one process (plain
+peer access, one host thread per context)."""
 import os
 import socket
+import threading
 
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+P, N = 1100, 700                       # 9 tile rows -> groups of 3 (world 2); the last group is short
+
+
+def _table(synth):
+    return np.ascontiguousarray(np.concatenate([synth.clique(600, N, B=12, seed=1), synth.chain(500, N, B=20, seed=2)]))
 
 
 def _free_port():
@@ -16,6 +26,30 @@ def _free_port():
     port = s.getsockname()[1]
     s.close()
     return port
+
+
+def _single(fw, x, dev=0):
+    eng = fw.Engine(dev)
+    eng.set_data_colmajor(x, "fz")
+    cor = eng.cor()
+    uni = eng.pw_univar_neighbors(alpha=0.01, n_obs_min=20)
+    order = fw.target_order(uni)
+    res = eng.si_HITON_PC(order, max_k=3, alpha=0.01, n_obs_min=20, want_tpc=False)
+    return cor, uni, order, res, fw.assemble_graph(res, uni, "fz"), eng.pairwise_stats()
+
+
+def _rank_pass(fw, par, eng, x, rank, world, prefetch):
+    """one pass of the group pipeline on this rank; returns (cor sub-matrix, uni, packed PC lists of the shard)"""
+    c0, c1 = par.table_slice(P, rank, world)
+    eng.pairwise_prefetch(0.01 if prefetch else 0.0, 20)
+    xs = np.ascontiguousarray(x[c0:c1])
+    eng.multi_set_data_ptr(xs.ctypes.data, N, P)
+    eng.multi_cor()
+    uni = eng.pw_univar_neighbors(alpha=0.01, n_obs_min=20)
+    order = fw.target_order(uni)
+    res = eng.si_HITON_PC(par.shard_targets(order, rank, world), max_k=3, alpha=0.01, n_obs_min=20, want_tpc=False)
+    eng.synchronize()
+    return eng.cor_gather(np.arange(P)), uni, par.pack_result(res), eng.pairwise_stats()
 
 
 def _worker(rank, world, port, q):
@@ -27,44 +61,30 @@ def _worker(rank, world, port, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     fw = fwload.load(); par = fwload.load_sub("parallel"); synth = fwload.load_sub("synth")
-    p, n = 1100, 700                       # 9 tile rows -> padded to a multiple of 2*world
-    d_x = torch.empty((p, n), dtype=torch.float32, device="cuda")
-    if rank == 0:
-        d_x.copy_(torch.from_numpy(np.concatenate([synth.clique(600, n, B=12, seed=1), synth.chain(500, n, B=20, seed=2)])))
-    par.broadcast_table(dist, d_x, src=0)
-    torch.cuda.synchronize()
+    x = _table(synth)
     eng = fw.Engine(rank)
-    eng.adopt_data_device(d_x.data_ptr(), n, p, "fz")
-    h, nb_pad = par.cor_groups((p + 127) // 128, world)
-    d_cor = torch.full((nb_pad * 128, p), float("nan"), dtype=torch.float32, device="cuda")
-    eng.adopt_cor_device_rows(d_cor.data_ptr(), p, d_cor.shape[0])
-    par.sharded_cor(dist, eng, d_cor)
-    eng.synchronize()
-    sharded = d_cor[:p].cpu().numpy()
-    # single-GPU result on the same device
-    eng1 = fw.Engine(rank)
-    eng1.adopt_data_device(d_x.data_ptr(), n, p, "fz")
-    single = eng1.cor()
-    same = bool((sharded == single).all())
-    # target-sharded HITON-PC on the sharded cor_mat
-    uni = eng.pw_univar_neighbors(alpha=0.01, n_obs_min=20)
-    order = fw.target_order(uni)
-    res = eng.si_HITON_PC(par.shard_targets(order, rank, world), max_k=3, alpha=0.01, n_obs_min=20, want_tpc=False)
-    bucket = par.gather_results(dist, par.pack_result(res), dst=0)
+    par.attach_group(dist, eng, N, P)
+    out = []
+    for prefetch in (True, False, True):                 # repeated passes: the barrier protocol must hold across passes
+        cor, uni, packed, stats = _rank_pass(fw, par, eng, x, rank, world, prefetch)
+        bucket = par.gather_results(dist, packed, dst=0)
+        if rank == 0:
+            merged = par.MergedResult(bucket)
+            out.append((cor, uni, fw.assemble_graph(merged, uni, "fz"), int(merged.num_tests.sum()), stats))
     if rank == 0:
-        merged = par.MergedResult(bucket)
-        edges = fw.assemble_graph(merged, uni, "fz")
-        eng1.pw_univar_neighbors(alpha=0.01, n_obs_min=20)
-        full = eng1.si_HITON_PC(order, max_k=3, alpha=0.01, n_obs_min=20, want_tpc=False)
-        edges1 = fw.assemble_graph(full, uni, "fz")
-        q.put((same, float(np.abs(sharded - single).max()), edges == edges1, int(merged.num_tests.sum()), int(full.num_tests.sum())))
-    else:
-        q.put((same, 0.0, True, 0, 0))
+        cor1, uni1, order1, res1, edges1, stats1 = _single(fw, x, 0)
+        ok = True
+        for cor, uni, edges, nt, stats in out:
+            ok &= bool((cor == cor1).all()) and bool((uni.offsets == uni1.offsets).all()) and bool((uni.nbr == uni1.nbr).all())
+            ok &= bool((uni.stat == uni1.stat).all()) and bool((uni.pval == uni1.pval).all()) and edges == edges1
+            ok &= nt == int(res1.num_tests.sum()) and stats == stats1
+        q.put((ok, float(np.abs(out[0][0] - cor1).max()), len(edges1)))
     dist.barrier()
+    eng.comm_detach()
     dist.destroy_process_group()
 
 
-def test_sharded_cor_and_hiton_two_gpus():
+def test_group_two_processes_ipc():
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -76,10 +96,47 @@ def test_sharded_cor_and_hiton_two_gpus():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for pr in procs:
         pr.start()
-    outs = [q.get(timeout=300) for _ in range(world)]
+    ok, err, ne = q.get(timeout=300)
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
-    for same, err, eq, nt, nt1 in outs:
-        assert same, "sharded cor_mat differs from the single-GPU one (max |diff| %g)" % err
-        assert eq and nt == nt1
+    assert ok, "group result differs from the single-GPU one (max |cor diff| %g)" % err
+    assert ne > 500
+
+
+def test_group_one_process_two_contexts():
+    import torch
+    import fwload
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    fw = fwload.load(); par = fwload.load_sub("parallel"); synth = fwload.load_sub("synth")
+    x = _table(synth)
+    world = 2
+    engs = [fw.Engine(r) for r in range(world)]
+    blobs = [engs[r].comm_export(r, world, N, P) for r in range(world)]
+    allh = np.concatenate(blobs)
+    for e in engs:
+        e.comm_attach(allh)
+    outs, errs = [None] * world, []
+
+    def run(r):
+        try:
+            outs[r] = _rank_pass(fw, par, engs[r], x, r, world, True)
+        except Exception as ex:          # noqa: BLE001
+            errs.append(ex)
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not errs, errs
+    cor1, uni1, order1, res1, edges1, stats1 = _single(fw, x, 0)
+    for r in range(world):
+        cor, uni, packed, stats = outs[r]
+        assert (cor == cor1).all() and (uni.offsets == uni1.offsets).all() and (uni.nbr == uni1.nbr).all() and (uni.stat == uni1.stat).all()
+        assert stats == stats1
+    merged = par.MergedResult([outs[r][2] for r in range(world)])
+    assert fw.assemble_graph(merged, uni1, "fz") == edges1
+    for e in engs:
+        e.comm_detach()
