@@ -14,8 +14,7 @@ interleaved.jl hands targets to workers): scaling = "strong".  No collective in 
           them (src/tests.jl:322, early exit honoured).
   e2e   : the same count divided by the time of the whole pipeline through the C ABI from HOST buffers: H2D of the table
           from pinned host memory, cor_mat, pairwise stage + BH, HITON-PC of the shard, D2H of the neighbour lists.
-          fz, N = 1: column chunks of the upload hidden behind the GEMM (fw_upload_cor_f32), the pairwise candidates collected
-          in the GEMM epilogue.  fz, N > 1: the library's group path (include/fwgpu.h "multi-GPU"): every rank uploads 1/N of
+          fz, N = 1: column chunks of the upload hidden behind the GEMM (fw_upload_cor_f32).  fz, N > 1: the library's group path (include/fwgpu.h "multi-GPU"): every rank uploads 1/N of
           the columns, the standardising kernel reads the peers' slices over NVLink, cor_mat stays row-sharded and is read
           through peer mappings; no NCCL call in the data path (torch.distributed only sets the group up and reduces the
           timings).  Other kinds, N > 1: table and pairwise stage replicated, targets sharded.
@@ -73,6 +72,7 @@ def parse():
     ap.add_argument("--cpu-blocks", type=int, default=256, help="blocks of the table in the CPU-baseline sample")
     ap.add_argument("--parity-blocks", type=int, default=64, help="blocks whose targets the oracle re-checks against the engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prefetch", action="store_true", help="collect the pairwise candidates in the cor_mat GEMM epilogue (fw_pairwise_prefetch) instead of one scan of the matrix")
     a = ap.parse_args()
     p, n, kind, si, desc = CONFIGS[a.config]
     a.p, a.n, a.kind, a.seed_idx, a.desc = a.p or p, a.n or n, kind, si, desc
@@ -301,7 +301,8 @@ def main_ours(a, rank, world, local_rank):
         """e2e: host table -> neighbour lists of this rank's target shard, through the C ABI."""
         t0 = time.perf_counter()
         if kind == "fz":
-            eng.pairwise_prefetch(a.alpha, nom)
+            if a.prefetch:
+                eng.pairwise_prefetch(a.alpha, nom)
             if not group:
                 eng.upload_and_cor(host_x.data_ptr(), n=n, p=p)       # upload chunked and hidden behind the cor_mat GEMM
             else:

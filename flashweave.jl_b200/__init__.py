@@ -571,9 +571,7 @@ class Engine:
             ml = int(self.levels()[0].max()) if kind in ("mi", "mi_nz") else None
             n_obs_min = auto_n_obs_min(kind, max_k, hps, max_level=ml)
         if kind == "fz" and not (getattr(self, "_cor_valid", False) and self.L.fw_cor_device_ptr(self.h)):
-            # no cor_mat yet, or it belongs to a previous table; the GEMM epilogue already collects the pairwise candidates
-            self.pairwise_prefetch(alpha, n_obs_min)
-            self.cor(want_host=False)
+            self.cor(want_host=False)                      # no cor_mat yet, or it belongs to a previous table
         uni = self.pw_univar_neighbors(alpha=alpha, hps=hps, n_obs_min=n_obs_min, FDR=FDR, kind=kind)
         tg = target_order(uni) if targets is None else _i64(targets)
         res = self.si_HITON_PC(tg, max_k=max_k, alpha=alpha, hps=hps, n_obs_min=n_obs_min, max_tests=max_tests, kind=kind, want_tpc=False)

@@ -128,29 +128,25 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// Univariate Fisher-z stage fused into the epilogue (tests.jl:470-478 looks the same correlations up again): the finished tile
-// row of this thread is still in registers (acc[0..BN) = the clamped correlations of `row` with columns col0..), so the pairs
-// with |r| >= r_lo are appended to the raw-candidate list here instead of re-reading the 10 GB matrix: per warp one exclusive
-// scan of the hit counts and ONE global atomic, then every lane writes its own records.
-__device__ __forceinline__ void emit_candidates(const PwEmit& em, const float* acc, i64 row, i64 col0, i64 p, bool diag, bool live,
-                                                unsigned int n_hit, unsigned int n_nan, int lane) {
+// Univariate Fisher-z stage fused into the epilogue (tests.jl:470-478 looks the same correlations up again): the 32 finished
+// correlations of this thread's row are still in registers (v[j] = clamped r(row, col0 + j), hitmask bit j = "|r| >= r_lo"), so
+// the raw candidates are appended to the list here instead of re-reading the 10 GB matrix: per warp and 32-column chunk one
+// exclusive scan of the hit counts and ONE global atomic, then every lane writes its own records.
+__device__ __forceinline__ void emit_chunk(const PwEmit& em, const uint32_t* v, unsigned int hitmask, i64 row, i64 col0, int lane) {
+    const unsigned int n_hit = __popc(hitmask);
     unsigned int incl = n_hit;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
     const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (!total) return;                                  // warp-uniform
     u64 base = 0;
-    if (lane == 31 && total) base = atomicAdd(&em.counters[0], (u64)total);
+    if (lane == 31) base = atomicAdd(&em.counters[0], (u64)total);
     base = __shfl_sync(0xffffffffu, base, 31);
-    const unsigned int nn = __reduce_add_sync(0xffffffffu, n_nan);
-    if (lane == 0 && nn) atomicAdd(&em.counters[1], (u64)nn);
-    if (!n_hit) return;
     u64 pos = base + incl - n_hit;
 #pragma unroll
-    for (int j = 0; j < BN; ++j) {
-        const i64 col = col0 + j;
-        const float x = acc[j];
-        if (live && row < p && col < p && col > row && x == x && fabsf(x) >= em.r_lo) {
-            if ((i64)pos < em.cap) { PwRec rec; rec.x = (int)row; rec.y = (int)col; rec.r = x; em.list[pos] = rec; }
+    for (int j = 0; j < 32; ++j) {
+        if ((hitmask >> j) & 1u) {
+            if ((i64)pos < em.cap) { PwRec rec; rec.x = (int)row; rec.y = (int)(col0 + j); rec.r = __uint_as_float(v[j]); em.list[pos] = rec; }
             ++pos;
         }
     }
@@ -280,11 +276,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) cor_tc_kernel(const __grid_consta
         // the last chunk's commit also covers every earlier MMA, including the cross accumulator
         const i64 row = (i64)bi * BM + q * 32 + lane;
         const bool diag = (bi == bj);
-        unsigned int n_hit = 0, n_nan = 0;
+        unsigned int n_nan = 0;
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_base + lane_base + 256u + (uint32_t)c0, v);
+            unsigned int hitmask = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const i64 col = (i64)bj * BN + c0 + j;
@@ -296,11 +293,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) cor_tc_kernel(const __grid_consta
                     Cw[row * p + col] = x;
                     if (mirror || diag) Cw[col * p + row] = x;         // mirror (coalesced across the warp: consecutive rows)
                 }
-                acc[c0 + j] = x;
-                if (em.on && ok && col > row) { if (x != x) ++n_nan; else if (fabsf(x) >= em.r_lo) ++n_hit; }
+                v[j] = __float_as_uint(x);
+                if (em.on && ok && col > row) { if (x != x) ++n_nan; else if (fabsf(x) >= em.r_lo) hitmask |= 1u << j; }
             }
+            if (em.on) emit_chunk(em, v, hitmask, row, (i64)bj * BN + c0, lane);
         }
-        if (em.on) emit_candidates(em, acc, row, (i64)bj * BN, p, diag, true, n_hit, n_nan, lane);
+        if (em.on) { n_nan = __reduce_add_sync(0xffffffffu, n_nan); if (lane == 0 && n_nan) atomicAdd(&em.counters[1], (u64)n_nan); }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -495,11 +493,12 @@ cor_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         }
         const i64 row = (i64)bi * BM + q * 32 + lane;
         const bool diag = (bi == bj);
-        unsigned int n_hit = 0, n_nan = 0;
+        unsigned int n_nan = 0;
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_base + lane_base + 256u + (uint32_t)c0, v);
+            unsigned int hitmask = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const i64 col = (i64)bj * BN + c0 + j;
@@ -511,11 +510,12 @@ cor_tc2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                     Cw[row * p + col] = x;
                     if (mirror || diag) Cw[col * p + row] = x;
                 }
-                acc[c0 + j] = x;
-                if (em.on && ok && col > row) { if (x != x) ++n_nan; else if (fabsf(x) >= em.r_lo) ++n_hit; }
+                v[j] = __float_as_uint(x);
+                if (em.on && ok && col > row) { if (x != x) ++n_nan; else if (fabsf(x) >= em.r_lo) hitmask |= 1u << j; }
             }
+            if (em.on) emit_chunk(em, v, hitmask, row, (i64)bj * BN + c0, lane);
         }
-        if (em.on) emit_candidates(em, acc, row, (i64)bj * BN, p, diag, live, n_hit, n_nan, lane);
+        if (em.on) { n_nan = __reduce_add_sync(0xffffffffu, n_nan); if (lane == 0 && n_nan) atomicAdd(&em.counters[1], (u64)n_nan); }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

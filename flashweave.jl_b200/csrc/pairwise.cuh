@@ -47,7 +47,7 @@ struct PairwiseScratch {
 // with ONE global atomic per >= 64 records, so the append costs ~2e5 atomics at C4 instead of one per warp iteration.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) pw_fz_emit_kernel(const float* __restrict__ rows, i64 p, i64 row_global0, i64 row_local0, PwEmit e) {
-    constexpr int WARPS = THREADS / 32, QCAP = 96;
+    constexpr int WARPS = THREADS / 32, QCAP = 96;     // a flush happens at >= 64 queued records; one ballot adds at most 32
     __shared__ PwRec q[WARPS][QCAP];
     const i64 X = row_global0 + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -62,19 +62,32 @@ __global__ void __launch_bounds__(THREADS) pw_fz_emit_kernel(const float* __rest
         __syncwarp();
         qn = 0;
     };
-    for (i64 y0 = X + 1; y0 < p; y0 += THREADS) {
-        const i64 Y = y0 + tid;
-        bool hit = false; float r = 0.0f;
-        if (Y < p) {
-            r = row[Y];
-            if (r != r) ++n_nan; else hit = fabsf(r) >= e.r_lo;
-        }
+    auto consider = [&](i64 Y, float r, bool in_range) {
+        bool hit = false;
+        if (in_range) { if (r != r) ++n_nan; else hit = fabsf(r) >= e.r_lo; }
         const unsigned int bal = __ballot_sync(0xffffffffu, hit);
         if (bal) {
             if (hit) { PwRec rec; rec.x = (int)X; rec.y = (int)Y; rec.r = r; q[warp][qn + __popc(bal & ((1u << lane) - 1u))] = rec; }
             qn += __popc(bal);
             __syncwarp();
             if (qn >= 64) flush();
+        }
+    };
+    if ((p & 3) == 0) {
+        // 16-byte loads: the row base is 16-byte aligned when p % 4 == 0; the first vector is masked below Y = X + 1
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        for (i64 v0 = (X + 1) >> 2; v0 < (p >> 2); v0 += THREADS) {
+            const i64 v = v0 + tid;
+            const bool in = v < (p >> 2);
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in) f = __ldg(row4 + v);
+            const i64 Y = v << 2;
+            consider(Y, f.x, in && Y > X); consider(Y + 1, f.y, in && Y + 1 > X); consider(Y + 2, f.z, in && Y + 2 > X); consider(Y + 3, f.w, in && Y + 3 > X);
+        }
+    } else {
+        for (i64 y0 = X + 1; y0 < p; y0 += THREADS) {
+            const i64 Y = y0 + tid;
+            consider(Y, Y < p ? row[Y] : 0.0f, Y < p);
         }
     }
     if (qn) flush();
