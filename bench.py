@@ -159,6 +159,33 @@ def host_threads():
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
+def bind_to_gpu_numa(dev):
+    """Run this process (and first-touch its pinned buffers) on the NUMA node the GPU hangs off, as numactl / NCCL would: the
+    H2D copy of a rank's table slice then does not cross the socket interconnect.  Returns (previous affinity, node) or (None, None)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(dev)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) > 4:
+            bus = bus[-12:]                                          # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if not cpus:
+            return None, None
+        os.sched_setaffinity(0, cpus)
+        return prev, node
+    except Exception:
+        return None, None
+
+
 def blas_cor_f32(x_pn, threads):
     """cor(data) the way the reference evaluates it (src/learning.jl:44: Statistics.cor of a Float32 matrix = centred columns,
     one BLAS Gram product in Float32, cov2cor!), with all host threads."""
@@ -251,6 +278,7 @@ def main_ours(a, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
+    prev_affinity, numa_node = bind_to_gpu_numa(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -291,11 +319,16 @@ def main_ours(a, rank, world, local_rank):
     host_np = host_x.numpy()
     eng = fw.Engine(local_rank)
     group = dist is not None and kind == "fz"
+    slice_host = None
     if group:
         par.attach_group(dist, eng, n, p)            # handle exchange, once (setup)
+        # this rank's columns in its own pinned buffer (first-touched on the GPU's NUMA node): what a worker that owns 1/N of the table holds
+        c0, c1 = par.table_slice(p, rank, world)
+        slice_host = torch.empty((c1 - c0, n), dtype=t_dtype, pin_memory=True)
+        slice_host.copy_(host_x[c0:c1])
     ext = torch.cuda.ExternalStream(eng.stream)
 
-    phase_wall = {"table_and_cor_ms": [], "pairwise_ms": [], "hiton_ms": []}
+    phase_wall = {"table_and_cor_ms": [], "pairwise_ms": [], "hiton_ms": [], "upload_ms": []}
 
     def pipeline():
         """e2e: host table -> neighbour lists of this rank's target shard, through the C ABI."""
@@ -306,8 +339,8 @@ def main_ours(a, rank, world, local_rank):
             if not group:
                 eng.upload_and_cor(host_x.data_ptr(), n=n, p=p)       # upload chunked and hidden behind the cor_mat GEMM
             else:
-                c0, _ = par.table_slice(p, rank, world)
-                eng.multi_set_data_ptr(host_x.data_ptr() + c0 * n * 4, n, p)
+                eng.multi_set_data_ptr(slice_host.data_ptr(), n, p)
+                phase_wall["upload_ms"].append((time.perf_counter() - t0) * 1e3)
                 eng.multi_cor()
             eng.synchronize()
         elif kind == "mi":
@@ -333,7 +366,7 @@ def main_ours(a, rank, world, local_rank):
     barrier()
     launches0 = eng.launch_count()
     e2e_t = []
-    phase = {"cor_ms": [], "pairwise_ms": [], "hiton_ms": []}
+    phase = {"cor_ms": [], "pairwise_ms": [], "hiton_ms": [], "cor_standardise_ms": [], "cor_barrier_wait_ms": []}
     for k in phase_wall:
         phase_wall[k].clear()
     for _ in range(a.steps):
@@ -347,6 +380,9 @@ def main_ours(a, rank, world, local_rank):
         for k in phase:
             phase[k].append(lt[k])
     e2e_launches = (eng.launch_count() - launches0) / max(a.steps, 1)
+    if world > 1:                                    # every rank's phases on stderr (skew between ranks)
+        sys.stderr.write("[rank %d] e2e %.2f ms; device %s; wall %s\n" % (rank, float(np.mean(e2e_t)) * 1e3, {k: round(float(np.mean(v)), 2) for k, v in phase.items()},
+                                                                          {k: round(float(np.mean(v)), 2) for k, v in phase_wall.items() if v}))
     tests_rank = int(res.num_tests.sum())
     if kind == "fz":
         h2d = p * n * 4 // world if group else p * n * 4
@@ -362,21 +398,6 @@ def main_ours(a, rank, world, local_rank):
             eng.cor(want_host=False); eng.synchronize()
             gemm_ms.append(eng.last_timing()["cor_ms"])
         eng.pw_univar_neighbors(alpha=a.alpha, n_obs_min=nom, want_host=False)
-
-    # ---- parity sample: the oracle re-runs a sample of this rank's targets on the engine's own inputs --------------------
-    parity = None
-    if rank == 0 and a.parity_blocks > 0:
-        from oracle import parity as opar
-        uni = eng.univar_nbrs()
-        lim = a.parity_blocks * a.B
-        pos = np.nonzero(np.asarray(shard) < lim)[0]
-        parity = opar.sampled_hiton_parity(eng, kind, host_np, pos, res, uni, a.max_k, a.alpha, nom, n_threads=host_threads())
-        parity["sample"] = "this rank's targets among the first %d blocks (variables < %d)" % (a.parity_blocks, lim)
-        if kind == "fz":
-            # and against Float32(cor in fp64), i.e. without the tensor-core rounding of cor_mat (ADVICE r1): edge-set difference
-            U = np.arange(min(lim, p))
-            c64 = np.corrcoef(host_np[U].astype(np.float64)).astype(np.float32)
-            parity["cor_mat_max_abs_err_vs_fp64"] = float(np.abs(eng.cor_gather(U) - c64).max())
 
     # ---- device-resident region (the contract's K timed steps) -------------------------------------------
     for _ in range(a.warmup):
@@ -399,6 +420,23 @@ def main_ours(a, rank, world, local_rank):
     launches = eng.launch_count() - launches1
     exec_k = eng.hiton_exec_by_k()
     tests_exec = res.tests_executed
+
+    # ---- parity sample: the oracle re-runs a sample of this rank's targets on the engine's own inputs --------------------
+    parity = None
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)       # the oracle legs (parity sample, CPU baseline) use every host core
+    if rank == 0 and a.parity_blocks > 0:
+        from oracle import parity as opar
+        uni = eng.univar_nbrs()
+        lim = a.parity_blocks * a.B
+        pos = np.nonzero(np.asarray(shard) < lim)[0]
+        parity = opar.sampled_hiton_parity(eng, kind, host_np, pos, res, uni, a.max_k, a.alpha, nom, n_threads=host_threads())
+        parity["sample"] = "this rank's targets among the first %d blocks (variables < %d)" % (a.parity_blocks, lim)
+        if kind == "fz":
+            # and against Float32(cor in fp64), i.e. without the tensor-core rounding of cor_mat (ADVICE r1): edge-set difference
+            U = np.arange(min(lim, p))
+            c64 = np.corrcoef(host_np[U].astype(np.float64)).astype(np.float32)
+            parity["cor_mat_max_abs_err_vs_fp64"] = float(np.abs(eng.cor_gather(U) - c64).max())
 
     # ---- reduce over ranks: max time, sum of tests ----------------------------------------------------------
     stats = torch.tensor([dev_ms, float(np.mean(e2e_t)) * 1e3, float(tests_rank), float(tests_exec), float(launches), float(h2d), float(d2h)],
@@ -466,14 +504,14 @@ def main_ours(a, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "tests/s", "h2d_bytes_per_step": sm[5].item(), "d2h_bytes_per_step": sm[6].item(),
                 "ms_per_step": e2e_ms_max, "gpu_launches_per_step": e2e_launches,
                 "phases_device_ms_rank0": {k: float(np.mean(v)) for k, v in phase.items()},
-                "phases_wall_ms_rank0": {k: float(np.mean(v)) for k, v in phase_wall.items()},
+                "phases_wall_ms_rank0": {k: float(np.mean(v)) for k, v in phase_wall.items() if v},
                 "pairwise_tests_per_s": p * (p - 1) / 2 / (float(np.mean(phase_wall["pairwise_ms"])) * 1e-3),
                 "multi_gpu_path": ("library group (CUDA IPC peer mappings over NVLink, row-sharded cor_mat, no NCCL in the data path)" if group else
                                    ("replicated table + pairwise stage, sharded targets" if world > 1 else "single GPU"))},
         "gpu_launches": int(sm[4].item()),
         "roofline": roofline,
         "clocks": clocks,
-        "setup": {"table_gen_s": gen_s},
+        "setup": {"table_gen_s": gen_s, "numa_node_of_gpu": numa_node, "host_cores_bound": host_threads()},
     }
     if kind == "fz":
         if dist is None:

@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "fw_hiton_exec_by_k",
     "fw_set_data_f32", "fw_set_data_i32", "fw_adopt_data_f32_device", "fw_set_n_obs", "fw_levels", "fw_cor_matrix",
     "fw_set_cor_f32", "fw_adopt_cor_device", "fw_cor_device_ptr", "fw_adopt_cor_device_rows", "fw_cor_prepare", "fw_cor_rows", "fw_cor_symmetrize", "fw_upload_cor_f32", "fw_test_batch", "fw_test_subsets", "fw_test_subsets_batch",
-    "fw_pairwise", "fw_pairwise_copy", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_capacity",
+    "fw_pairwise", "fw_pairwise_copy", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_ex", "fw_hiton_pc_capacity",
     "fw_normalize_f32", "fw_get_data_f32", "fw_get_data_i32", "fw_set_data_csc_f32", "fw_set_data_csc_i32",
     "fw_host_register", "fw_host_unregister",
     "fw_cor_gather", "fw_pairwise_prefetch",
@@ -113,6 +113,7 @@ def load_library():
         "fw_set_univar_nbrs": (i32, [vp, vp, vp, vp, vp]),
         "fw_pairwise_stats": (i32, [vp, vp, vp, vp]),
         "fw_hiton_pc": (i32, [vp, i32, i64, vp, i32, dbl, i64, i64, i64] + [vp] * 11),
+        "fw_hiton_pc_ex": (i32, [vp, i32, i64, vp, i32, dbl, i64, i64, i64] + [vp] * 4 + [vp] * 11 + [vp] * 7),
         "fw_hiton_pc_capacity": (i32, [vp, i64, vp, vp]),
         "fw_normalize_f32": (i32, [vp, vp, i64, i64, i64, i32, i32, C.POINTER(i64), C.POINTER(i64), vp, vp]),
         "fw_set_data_csc_f32": (i32, [vp, vp, vp, vp, i64, i64]),
@@ -185,6 +186,15 @@ class HitonResult:
         b = a + self.tpc_count[i]
         return self.tpc_nbr[a:b], self.tpc_stat[a:b], self.tpc_p[a:b]
 
+    def rejections(self, i):
+        """HitonState.state_rejections of target i (track_rejections=True): {candidate: (Zs, TestResult tuple, (num_tests, frac))}"""
+        r = self.rej
+        a = self.off[i]
+        out = {}
+        for j in range(a, a + int(r["count"][i])):
+            out[int(r["nbr"][j])] = (tuple(int(z) for z in r["Zs"][j, :r["k"][j]]), r["res"][j].astuple(), (int(r["ntests"][j]), float(r["frac"][j])))
+        return out
+
 
 class Engine:
     """One `fw_ctx`: the reference's test_obj + data + cor_mat, resident on one B200."""
@@ -237,9 +247,9 @@ class Engine:
 
     def last_timing(self):
         """device ms of the last cor / pairwise / hiton phases (CUDA events on the engine's stream)"""
-        out = np.zeros(4)
-        self._ck(self.L.fw_last_timing(self.h, _p(out), 4))
-        return {"cor_ms": out[0], "pairwise_ms": out[1], "hiton_ms": out[2]}
+        out = np.zeros(6)
+        self._ck(self.L.fw_last_timing(self.h, _p(out), 6))
+        return {"cor_ms": out[0], "pairwise_ms": out[1], "hiton_ms": out[2], "cor_standardise_ms": out[4], "cor_barrier_wait_ms": out[5]}
 
     def hiton_exec_by_k(self):
         out = np.zeros(3, np.int64)
@@ -530,8 +540,9 @@ class Engine:
 
     # -- HITON-PC ---------------------------------------------------------------------------------
     def si_HITON_PC(self, targets, max_k=3, alpha=0.01, hps=5, n_obs_min=0, max_tests=10_000_000, kind=None, want_tpc=True,
-                    buffers=None, reuse_buffers=False):
-        """si_HITON_PC for each target (hiton.jl:283-400; parallel="single" semantics: no whitelist)."""
+                    buffers=None, reuse_buffers=False, whitelists=None, blacklists=None, track_rejections=False):
+        """si_HITON_PC for each target (hiton.jl:283-400).  whitelists / blacklists: one iterable of variables per target
+        (hiton.jl:20-38; empty everywhere = parallel="single" semantics); track_rejections: HitonResult.rejections(i)."""
         t = _i64(np.atleast_1d(targets))
         nt = len(t)
         cap = C.c_int64(0)
@@ -556,16 +567,42 @@ class Engine:
                         b["pinned"].append(k)
         ex = C.c_int64(0)
         tp = want_tpc
-        self._ck(self.L.fw_hiton_pc(self.h, KINDS[kind or self.kind], nt, _p(t), max_k, alpha, hps, n_obs_min, max_tests,
-                                    _p(b["off"]), _p(b["pcc"]), _p(b["pcn"]), _p(b["pcs"]), _p(b["pcp"]),
-                                    _p(b["tpcc"]), _p(b["tpcn"]) if tp else None, _p(b["tpcs"]) if tp else None, _p(b["tpcp"]) if tp else None,
-                                    _p(b["ntests"]), C.byref(ex)))
-        return HitonResult(t, b["off"][:nt + 1], b["pcc"][:nt], b["pcn"], b["pcs"], b["pcp"], b["tpcc"][:nt], b["tpcn"], b["tpcs"], b["tpcp"],
-                           b["ntests"][:nt], int(ex.value))
+
+        def csr(lists):
+            if lists is None:
+                return None, None
+            assert len(lists) == nt, "one list per target"
+            off = np.zeros(nt + 1, np.int64)
+            off[1:] = np.cumsum([len(l) for l in lists])
+            idx = _i64(np.concatenate([np.asarray(list(l), np.int64) for l in lists]) if off[-1] else np.zeros(0, np.int64))
+            return off, idx
+        wlo, wli = csr(whitelists)
+        blo, bli = csr(blacklists)
+        rej = None
+        if track_rejections:
+            rej = {"count": np.zeros(max(nt, 1), np.int64), "nbr": np.zeros(cp, np.int64), "Zs": np.zeros((cp, 3), np.int64), "k": np.zeros(cp, np.int32),
+                   "res": (TestResult * cp)(), "ntests": np.zeros(cp, np.int64), "frac": np.zeros(cp)}
+        self._ck(self.L.fw_hiton_pc_ex(self.h, KINDS[kind or self.kind], nt, _p(t), max_k, alpha, hps, n_obs_min, max_tests,
+                                       _p(wlo), _p(wli), _p(blo), _p(bli),
+                                       _p(b["off"]), _p(b["pcc"]), _p(b["pcn"]), _p(b["pcs"]), _p(b["pcp"]),
+                                       _p(b["tpcc"]), _p(b["tpcn"]) if tp else None, _p(b["tpcs"]) if tp else None, _p(b["tpcp"]) if tp else None,
+                                       _p(b["ntests"]), C.byref(ex),
+                                       _p(rej["count"]) if rej else None, _p(rej["nbr"]) if rej else None, _p(rej["Zs"]) if rej else None,
+                                       _p(rej["k"]) if rej else None, C.cast(rej["res"], C.c_void_p) if rej else None,
+                                       _p(rej["ntests"]) if rej else None, _p(rej["frac"]) if rej else None))
+        res = HitonResult(t, b["off"][:nt + 1], b["pcc"][:nt], b["pcn"], b["pcs"], b["pcp"], b["tpcc"][:nt], b["tpcn"], b["tpcs"], b["tpcp"],
+                          b["ntests"][:nt], int(ex.value))
+        res.rej = rej
+        return res
 
     # -- LGL ------------------------------------------------------------------------------------------
-    def LGL(self, max_k=3, alpha=0.01, hps=5, n_obs_min=-1, max_tests=10_000_000, FDR=True, targets=None, kind=None):
-        """learning.jl:203-279 with parallel="single": cor -> pairwise -> HITON-PC per target -> OR-rule graph."""
+    def LGL(self, max_k=3, alpha=0.01, hps=5, n_obs_min=-1, max_tests=10_000_000, FDR=True, targets=None, kind=None, parallel="single",
+            track_rejections=False):
+        """learning.jl:203-279: cor -> pairwise -> HITON-PC per target -> OR-rule graph.
+        parallel="single" (learning.jl:137-138): targets are independent, one launch for all of them.
+        parallel="single_il": the reference's default schedule with ONE worker (interleaved.jl:60-179): two initial jobs with empty
+        whitelists, then one target at a time whose whitelist is its neighbourhood in the graph of all finished targets
+        (feed-forward, interleaved.jl:124-128) - each job is one fw_hiton_pc_ex call, the loop is the host's."""
         kind = kind or self.kind
         if n_obs_min < 0:
             ml = int(self.levels()[0].max()) if kind in ("mi", "mi_nz") else None
@@ -574,10 +611,44 @@ class Engine:
             self.cor(want_host=False)                      # no cor_mat yet, or it belongs to a previous table
         uni = self.pw_univar_neighbors(alpha=alpha, hps=hps, n_obs_min=n_obs_min, FDR=FDR, kind=kind)
         tg = target_order(uni) if targets is None else _i64(targets)
-        res = self.si_HITON_PC(tg, max_k=max_k, alpha=alpha, hps=hps, n_obs_min=n_obs_min, max_tests=max_tests, kind=kind, want_tpc=False)
+        kw = dict(max_k=max_k, alpha=alpha, hps=hps, n_obs_min=n_obs_min, max_tests=max_tests, kind=kind, want_tpc=False, track_rejections=track_rejections)
+        if parallel == "single" or max_k == 0:
+            res = self.si_HITON_PC(tg, **kw)
+        elif parallel == "single_il":
+            sched = list(tg[:2][::-1]) + list(tg[2:])      # the FIFO of the two initial jobs is served second-first (interleaved.jl:136-141)
+            graph = {int(t): set() for t in range(self.p)}
+            parts = []
+            for i, T in enumerate(sched):
+                wl = sorted(graph[int(T)]) if i >= 2 else []
+                r = self.si_HITON_PC([T], whitelists=[wl], **kw)
+                nb, st, pv = r.pc(0)
+                parts.append((int(T), nb.copy(), st.copy(), pv.copy(), int(r.num_tests[0]), r.tests_executed, r.rejections(0) if track_rejections else None))
+                for v in nb:
+                    graph[int(T)].add(int(v)); graph[int(v)].add(int(T))
+            res = _ListResult(parts)
+        else:
+            raise ValueError("parallel must be 'single' or 'single_il'")
         edges = assemble_graph(res, uni, kind)
         return {"edges": edges, "cond_tests": int(res.num_tests.sum()), "tests_executed": res.tests_executed,
                 "pair_tests": self.p * (self.p - 1) // 2, "hiton": res, "univar": uni}
+
+
+class _ListResult:
+    """per-target results of sequential single-target calls, with the accessors of HitonResult"""
+
+    def __init__(self, parts):
+        self.targets = np.asarray([q[0] for q in parts], np.int64)
+        self._pc = [(q[1], q[2], q[3]) for q in parts]
+        self.num_tests = np.asarray([q[4] for q in parts], np.int64)
+        self.tests_executed = int(sum(q[5] for q in parts))
+        self._rej = [q[6] for q in parts]
+        self.pc_count = np.asarray([len(q[1]) for q in parts], np.int64)
+
+    def pc(self, i):
+        return self._pc[i]
+
+    def rejections(self, i):
+        return self._rej[i]
 
 
 # ---- host logic shared with the tests (pure Python, no compute) --------------------------------------
@@ -639,8 +710,38 @@ def assemble_graph(res, uni, kind):
     return sorted((a, b, w) for (a, b), w in edges.items())
 
 
+def julia_float_str(x):
+    """string(::Float64) of Julia (what src/io.jl:355 writes): shortest round-trip digits; positional notation for
+    1e-4 <= |x| < 1e6 with at least one fractional digit, otherwise d.ddde[-]x (Base.Ryu.writeshortest as `show` calls it)"""
+    x = float(x)
+    if math.isnan(x):
+        return "NaN"
+    if math.isinf(x):
+        return "Inf" if x > 0 else "-Inf"
+    if x == 0.0:
+        return "-0.0" if math.copysign(1.0, x) < 0 else "0.0"
+    sign = "-" if x < 0 else ""
+    digits, exp = ("%r" % abs(x)), 0
+    m, _, e = digits.partition("e")
+    exp = int(e) if e else 0
+    ip, _, fp = m.partition(".")
+    ds = (ip + fp).lstrip("0")
+    point = len(ip) + exp - (len(ip + fp) - len((ip + fp).lstrip("0")))      # decimal exponent: value = 0.ds * 10^point
+    ds = ds.rstrip("0") or "0"
+    e10 = point - 1                                                             # value = d.ddd * 10^e10
+    if -4 <= e10 < 6:
+        if point <= 0:
+            return sign + "0." + "0" * (-point) + ds
+        if point >= len(ds):
+            return sign + ds + "0" * (point - len(ds)) + ".0"
+        return sign + ds[:point] + "." + ds[point:]
+    return sign + ds[0] + "." + (ds[1:] or "0") + "e" + str(e10)
+
+
 def write_edgelist(path, edges, header=None, meta_mask=None, p=None):
-    """io.jl:338-359 edgelist format (`# header`, `# meta mask`, then `a<TAB>b<TAB>weight`)."""
+    """io.jl:338-359 edgelist format (`# header`, `# meta mask`, then `a<TAB>b<TAB>weight`).  Edges in the order `edges(G)` of the
+    reference's SimpleWeightedGraph yields them: the upper triangle of the sparse weight matrix column by column, i.e. sorted by
+    (larger endpoint, smaller endpoint)."""
     if header is None:
         header = ["X%d" % (i + 1) for i in range(p)]
     if meta_mask is None:
@@ -648,5 +749,5 @@ def write_edgelist(path, edges, header=None, meta_mask=None, p=None):
     with open(path, "w") as f:
         f.write("# header\t" + ",".join(header) + "\n")
         f.write("# meta mask\t" + ",".join("true" if m else "false" for m in meta_mask) + "\n")
-        for a, b, w in edges:
-            f.write("%s\t%s\t%r\n" % (header[a], header[b], w))
+        for a, b, w in sorted(((min(a, b), max(a, b), w) for a, b, w in edges), key=lambda e: (e[1], e[0])):
+            f.write("%s\t%s\t%s\n" % (header[a], header[b], julia_float_str(w)))

@@ -89,6 +89,8 @@ struct fw_ctx {
     // per-phase device timing (CUDA events on `stream`), see fw_last_timing
     cudaEvent_t ev[8] = {nullptr};
     bool ev_valid[4] = {false, false, false, false};
+    cudaEvent_t evx[3] = {nullptr, nullptr, nullptr};   // fw_multi_cor: after the standardising kernel, before / after the closing group barrier
+    bool evx_valid = false;
 
     // scratch
     DevBuf<int> d_counter; DevBuf<u64> d_exec;
@@ -238,7 +240,7 @@ static const int kCaps[4] = {32, 64, 128, 224};
 static size_t hiton_smem_bytes(int cap, bool r_in_smem, int nz_words = -1, bool cache = false) {
     size_t o = r_in_smem ? sizeof(float) * (size_t)cap * cap : 0;
     o = (o + 15) & ~(size_t)15;
-    o += sizeof(i64) * (cap + 1) + 4 * sizeof(double) * cap + sizeof(i64) * cap + 2 * sizeof(int) * cap;
+    o += sizeof(i64) * (cap + 1) + 4 * sizeof(double) * cap + sizeof(i64) * cap + 3 * sizeof(int) * cap + (size_t)cap;
     o = (o + 15) & ~(size_t)15;
     if (nz_words >= 0) o += sizeof(i64) * cap + 2 * sizeof(double) * cap + sizeof(unsigned int) * nz_words + 16 + FZNZ_GRAM_BYTES;
     o = (o + 15) & ~(size_t)15;
@@ -423,6 +425,7 @@ int32_t fw_create(int32_t device, fw_ctx** out) {
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     if (ctx->d_counter.reserve(16) != cudaSuccess || ctx->d_exec.reserve(16) != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_NOMEM, "scratch allocation failed"); }
     for (int i = 0; i < 8; ++i) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_CUDA, "cudaEventCreate failed"); }
+    for (int i = 0; i < 3; ++i) if (cudaEventCreate(&ctx->evx[i]) != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_CUDA, "cudaEventCreate failed"); }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_CUDA, "cudaStreamCreate failed"); }
     for (int i = 0; i < 12; ++i) if (cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return fail(nullptr, FW_ERR_CUDA, "cudaEventCreate failed"); }
     *out = ctx;
@@ -435,6 +438,7 @@ int32_t fw_destroy(fw_ctx* ctx) {
     fw_comm_detach(ctx);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 3; ++i) if (ctx->evx[i]) cudaEventDestroy(ctx->evx[i]);
     for (int i = 0; i < 12; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     delete ctx;
@@ -479,6 +483,15 @@ int32_t fw_last_timing(fw_ctx* ctx, double* out_ms, int32_t n) {
         float ms = 0.f;
         CK(cudaEventSynchronize(ctx->ev[2 * i + 1]));
         CK(cudaEventElapsedTime(&ms, ctx->ev[2 * i], ctx->ev[2 * i + 1]));
+        out_ms[i] = (double)ms;
+    }
+    // [4] = standardise + split part of out[0] in fw_multi_cor (reads the peers' table slices), [5] = wait in its closing group barrier
+    for (int i = 4; i < n && i < 6; ++i) {
+        out_ms[i] = -1.0;
+        if (!ctx->evx_valid) continue;
+        float ms = 0.f;
+        CK(cudaEventSynchronize(ctx->evx[2]));
+        if (i == 4) CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->evx[0])); else CK(cudaEventElapsedTime(&ms, ctx->evx[1], ctx->evx[2]));
         out_ms[i] = (double)ms;
     }
     return FW_OK;
@@ -999,6 +1012,7 @@ int32_t fw_multi_cor(fw_ctx* ctx) {
         fwcomm::standardize_split_peer_kernel<256><<<(unsigned)p_pad, 256, smem, ctx->stream>>>(ps, G.world, n, p, kp, zhi, zlo, staged);
         ctx->launches++;
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->evx[0], ctx->stream));
     }
     cudaError_t e = cortc::encode_map(&ctx->tcp.tm_hi, zhi, kp, p_pad, &msg);
     if (e == cudaSuccess) e = cortc::encode_map(&ctx->tcp.tm_lo, zlo, kp, p_pad, &msg);
@@ -1013,7 +1027,9 @@ int32_t fw_multi_cor(fw_ctx* ctx) {
     ctx->launches += nl;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->ev_valid[0] = true;
     if (em.on) CK(cudaMemcpyAsync(G.flags_of(G.rank) + fwcomm::F_LIST_N, ctx->d_listcnt.ptr, 2 * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->evx[1], ctx->stream));
     { int st_ = comm_barrier(ctx); if (st_ != FW_OK) return st_; }       // the whole distributed cor_mat (and every rank's candidate list) is complete
+    CK(cudaEventRecord(ctx->evx[2], ctx->stream)); ctx->evx_valid = true;
     ctx->cor_p = p; ctx->cor_sharded = true; ctx->col.valid = ctx->col.armed;
     return FW_OK;
 }
@@ -1340,6 +1356,19 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
                     int64_t* pc_off, int64_t* pc_count, int64_t* pc_nbr, double* pc_stat, double* pc_p,
                     int64_t* tpc_count, int64_t* tpc_nbr, double* tpc_stat, double* tpc_p,
                     int64_t* num_tests, int64_t* tests_executed_total) {
+    return fw_hiton_pc_ex(ctx, kind, n_targets, targets, max_k, alpha, hps, n_obs_min, max_tests, nullptr, nullptr, nullptr, nullptr,
+                          pc_off, pc_count, pc_nbr, pc_stat, pc_p, tpc_count, tpc_nbr, tpc_stat, tpc_p, num_tests, tests_executed_total,
+                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int32_t fw_hiton_pc_ex(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t* targets,
+                       int32_t max_k, double alpha, int64_t hps, int64_t n_obs_min, int64_t max_tests,
+                       const int64_t* wl_off, const int64_t* wl_idx, const int64_t* bl_off, const int64_t* bl_idx,
+                       int64_t* pc_off, int64_t* pc_count, int64_t* pc_nbr, double* pc_stat, double* pc_p,
+                       int64_t* tpc_count, int64_t* tpc_nbr, double* tpc_stat, double* tpc_p,
+                       int64_t* num_tests, int64_t* tests_executed_total,
+                       int64_t* rej_count, int64_t* rej_nbr, int64_t* rej_Zs, int32_t* rej_k, fw_test_result* rej_result,
+                       int64_t* rej_num_tests, double* rej_frac) {
     if (!ctx) return FW_ERR_INVALID;
     NEED(kind >= FW_MI && kind <= FW_FZ_NZ, FW_ERR_INVALID, "fw_hiton_pc: unknown test kind %d", kind);
     NEED(max_k >= 0 && max_k <= 3, FW_ERR_UNSUPPORTED, "fw_hiton_pc: max_k = %d not in 0..3", max_k);
@@ -1398,6 +1427,7 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
             if (pc_count) pc_count[t] = cnt;
             if (tpc_count) tpc_count[t] = 0;
             if (num_tests) num_tests[t] = 0;
+            if (rej_count) rej_count[t] = 0;
             for (i64 i = 0; i < cnt; ++i) {
                 if (pc_nbr) pc_nbr[hoff[t] + i] = un[e0 + i] + base;
                 if (pc_stat) pc_stat[hoff[t] + i] = us[e0 + i];
@@ -1409,8 +1439,41 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         return FW_OK;
     }
 
+    // whitelists / blacklists (CSR over the target list, src/hiton.jl:20-38) and rejection records (src/hiton.jl:72-74)
+    const bool track = rej_count != nullptr;
+    NEED(!track || (rej_nbr && rej_Zs && rej_k && rej_result && rej_num_tests && rej_frac), FW_ERR_INVALID, "fw_hiton_pc_ex: rejection tracking needs all rej_* arrays");
+    HitonLists lists; memset(&lists, 0, sizeof(lists));
+    DevBuf<i64> dwlo, dwli, dblo, dbli, drejc, drejn, drejz, drejt; DevBuf<int> drejk; DevBuf<DevResult> drejr; DevBuf<double> drejf;
+    {
+        const int64_t* offs[2] = {wl_off, bl_off}; const int64_t* idxs[2] = {wl_idx, bl_idx};
+        DevBuf<i64>* doff[2] = {&dwlo, &dblo}; DevBuf<i64>* didx[2] = {&dwli, &dbli};
+        for (int w = 0; w < 2; ++w) {
+            if (!offs[w]) continue;
+            NEED(offs[w][0] == 0, FW_ERR_INVALID, "fw_hiton_pc_ex: list offsets must start at 0");
+            for (i64 t = 0; t < n_targets; ++t) NEED(offs[w][t + 1] >= offs[w][t], FW_ERR_INVALID, "fw_hiton_pc_ex: list offsets not monotone");
+            const i64 nl = offs[w][n_targets];
+            if (nl == 0) continue;
+            NEED(idxs[w], FW_ERR_INVALID, "fw_hiton_pc_ex: list indices are NULL");
+            std::vector<i64> h(nl);
+            for (i64 i = 0; i < nl; ++i) { h[i] = idxs[w][i] - base; NEED(h[i] >= 0 && h[i] < p, FW_ERR_INVALID, "fw_hiton_pc_ex: list entry out of range"); }
+            CK(doff[w]->reserve(n_targets + 1)); CK(didx[w]->reserve(nl));
+            CK(cudaMemcpyAsync(doff[w]->ptr, offs[w], sizeof(i64) * (n_targets + 1), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(didx[w]->ptr, h.data(), sizeof(i64) * nl, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));                       // h goes out of scope
+            if (w == 0) { lists.wl_off = dwlo.ptr; lists.wl_idx = dwli.ptr; } else { lists.bl_off = dblo.ptr; lists.bl_idx = dbli.ptr; }
+        }
+    }
+    if (track) {
+        CK(drejc.reserve(n_targets)); CK(drejn.reserve(cap_total)); CK(drejz.reserve((size_t)cap_total * 3)); CK(drejk.reserve(cap_total));
+        CK(drejr.reserve(cap_total)); CK(drejt.reserve(cap_total)); CK(drejf.reserve(cap_total));
+        CK(cudaMemsetAsync(drejc.ptr, 0, sizeof(i64) * n_targets, ctx->stream));
+        lists.rej_count = drejc.ptr; lists.rej_nbr = drejn.ptr; lists.rej_Zs = drejz.ptr; lists.rej_k = drejk.ptr; lists.rej_res = drejr.ptr;
+        lists.rej_ntests = drejt.ptr; lists.rej_frac = drejf.ptr;
+    }
+
     if (disc) {
         HitonMiArgs ma;
+        ma.lists = lists;
         ma.t = make_mi_table(ctx, kind); ma.hps = hps;
         ma.uni_off = ctx->d_uni_off.ptr; ma.uni_nbr = ctx->d_uni_nbr.ptr; ma.uni_stat = ctx->d_uni_stat.ptr; ma.uni_p = ctx->d_uni_p.ptr;
         ma.targets = dt.ptr; ma.out_off = doff.ptr; ma.counter = ctx->d_counter.ptr;
@@ -1431,7 +1494,7 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         std::vector<int> hstatus(n_targets);
         for (int round = 0; round < 2 && !sel.empty(); ++round) {
             ma.cap = caps[round];
-            size_t smem = sizeof(i64) * (ma.cap + 1) + 4 * sizeof(double) * ma.cap + sizeof(i64) * ma.cap + 2 * sizeof(int) * ma.cap + tabs + 16;
+            size_t smem = sizeof(i64) * (ma.cap + 1) + 4 * sizeof(double) * ma.cap + sizeof(i64) * ma.cap + 2 * sizeof(int) * ma.cap + (((size_t)ma.cap + 15) & ~(size_t)15) + tabs + 16;
             NEED(smem <= 220 * 1024, FW_ERR_UNSUPPORTED, "fw_hiton_pc: a target has %lld candidates; too many for the discrete kernel", (long long)need - 2);
             int n_sel = (int)sel.size();
             CK(cudaMemcpyAsync(dsel.ptr, sel.data(), sizeof(int) * n_sel, cudaMemcpyHostToDevice, ctx->stream));
@@ -1462,6 +1525,7 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
     a.tpc_nbr = dtpcn.ptr; a.tpc_stat = dtpcs.ptr; a.tpc_p = dtpcp.ptr; a.tpc_count = dtpcc.ptr;
     a.num_tests = dnt.ptr; a.executed_total = ctx->d_exec.ptr; a.status = dstatus.ptr;
     if (nzk) { a.nzt = nzt; a.n_obs_min = n_obs_min; }
+    a.lists = lists;
     const int nzw = nzk ? nzt.W : -1;
 
     // capacity classes: a target needs at most (#candidates + 2) slots; start optimistic (<= 64) and
@@ -1487,12 +1551,14 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         int grid = 1;
         if (c < 4) {
             a.cap = kCaps[c]; a.gscratch = nullptr;
-            const bool cache = !nzk && c == 0;            // per-candidate level-1/level-2 tables fit next to R in the 32-slot class
+            // per-candidate level-1/level-2 tables fit next to R in the 32-slot class; the table scan does not recover the positions of
+            // the returned subset, which rejection records need: tracking runs the generic scan
+            const bool cache = !nzk && c == 0 && !track;
             size_t smem = hiton_smem_bytes(a.cap, true, nzw, cache);
             NEED(smem <= 220 * 1024, FW_ERR_UNSUPPORTED, "fw_hiton_pc: target does not fit shared memory (n = %lld rows, %d slots)", (long long)ctx->n, a.cap);
             if (nzk) { CK(grid_for(hiton_fz_kernel<256, 2, true, false, false>, 256, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<256, 2, true, false, false><<<grid, 256, smem, ctx->stream>>>(a); }
-            else if (c == 0) { CK(grid_for(hiton_fz_kernel<128, 4, false, false, true>, 128, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<128, 4, false, false, true><<<grid, 128, smem, ctx->stream>>>(a); }
-            else if (c == 1) { CK(grid_for(hiton_fz_kernel<128, 2, false, false, false>, 128, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<128, 2, false, false, false><<<grid, 128, smem, ctx->stream>>>(a); }
+            else if (cache) { CK(grid_for(hiton_fz_kernel<128, 4, false, false, true>, 128, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<128, 4, false, false, true><<<grid, 128, smem, ctx->stream>>>(a); }
+            else if (c <= 1) { CK(grid_for(hiton_fz_kernel<128, 2, false, false, false>, 128, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<128, 2, false, false, false><<<grid, 128, smem, ctx->stream>>>(a); }
             else { CK(grid_for(hiton_fz_kernel<256, 2, false, false, false>, 256, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<256, 2, false, false, false><<<grid, 256, smem, ctx->stream>>>(a); }
         } else {
             i64 need = 0; for (int t : sel) need = std::max<i64>(need, hoff[t + 1] - hoff[t] + 2);
@@ -1533,9 +1599,22 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         if (tpc_stat) CK(cudaMemcpyAsync(tpc_stat, dtpcs.ptr, sizeof(double) * ne, cudaMemcpyDeviceToHost, ctx->stream));
         if (tpc_p) CK(cudaMemcpyAsync(tpc_p, dtpcp.ptr, sizeof(double) * ne, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    if (track) {
+        CK(cudaMemcpyAsync(rej_count, drejc.ptr, sizeof(i64) * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+        if (hoff[n_targets] > 0) {
+            const i64 ne = hoff[n_targets];
+            CK(cudaMemcpyAsync(rej_nbr, drejn.ptr, sizeof(i64) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(rej_Zs, drejz.ptr, sizeof(i64) * ne * 3, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(rej_k, drejk.ptr, sizeof(int) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(rej_result, drejr.ptr, sizeof(DevResult) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(rej_num_tests, drejt.ptr, sizeof(i64) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(rej_frac, drejf.ptr, sizeof(double) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
     u64 hexec[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(hexec, ctx->d_exec.ptr, 4 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    { int st_ = comm_check(ctx); if (st_ != FW_OK) return st_; }
     if (tests_executed_total) *tests_executed_total = (i64)hexec[0];
     for (int i = 0; i < 3; ++i) ctx->exec_by_k[i] = (i64)hexec[i + 1];
     if (base) {
@@ -1546,6 +1625,10 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
         for (i64 t = 0; t < n_targets; ++t) {
             if (pc_nbr) for (i64 i = 0; i < pcc[t]; ++i) pc_nbr[hoff[t] + i] += base;
             if (tpc_nbr) for (i64 i = 0; i < tpcc[t]; ++i) tpc_nbr[hoff[t] + i] += base;
+            if (track) for (i64 i = 0; i < rej_count[t]; ++i) {
+                rej_nbr[hoff[t] + i] += base;
+                for (int j = 0; j < 3; ++j) if (rej_Zs[(hoff[t] + i) * 3 + j] >= 0) rej_Zs[(hoff[t] + i) * 3 + j] += base;
+            }
         }
     }
     return FW_OK;

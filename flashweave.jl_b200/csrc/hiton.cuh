@@ -37,6 +37,7 @@ struct HitonArgs {
     int* status;                             // per target: 0 ok, 1 capacity overflow (re-run with larger cap)
     // fz_nz only: the table and its non-zero planes; correlations are recomputed per (T, candidate) view
     NzTable nzt; i64 n_obs_min;
+    HitonLists lists;                        // whitelists / blacklists / rejection records (all optional)
 };
 
 struct FzSlotTest {
@@ -88,9 +89,16 @@ struct FzScanShared { u64 fail_idx; int n_cont; int c_idx[128]; double c_stat[12
 // The accepted list of a scan without materialising it: a run of consecutive slots followed by a stored tail.  Interleaving
 // phase: slots 1..M (no tail).  Elimination phase of candidate slot c: the untested slots c+1..M, then the candidates accepted
 // so far in acceptance order (hiton.jl:134-147: the candidate is deleted from `accepted` and pushed back when it survives).
+// With whitelists the processed whitelisted slots are never deleted from `accepted` (hiton.jl:124-131 skips check_candidate!), so
+// they precede the untested run (prefix list `pre`) and appear once more among the pushed entries of the tail.
 struct AccView {
     int n_head, head_base; const int* tail;
-    __device__ __forceinline__ int operator[](int j) const { return j < n_head ? head_base + j : tail[j - n_head]; }
+    int n_pre; const int* pre;
+    __device__ __forceinline__ int operator[](int j) const {
+        if (j < n_pre) return pre[j];
+        j -= n_pre;
+        return j < n_head ? head_base + j : tail[j - n_head];
+    }
 };
 
 template <int THREADS>
@@ -372,6 +380,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
     i64* member = reinterpret_cast<i64*>(smem + o); o += sizeof(i64) * cap;
     int* acc = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;
     int* pc_slot = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;
+    int* wl_slot = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;           // processed whitelisted slots (elimination phase)
+    unsigned char* sflag = smem + o; o += (size_t)cap;                                  // per slot: list flags of the member
     o = (o + 15) & ~(size_t)15;
     // fz_nz scratch: slot -> variable, per-variable (mean, norm), row mask of the current view
     i64* slotvar = reinterpret_cast<i64*>(smem + o); if (NZ) o += sizeof(i64) * cap;
@@ -382,7 +392,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
     const FzTab tb = fz_tab_layout((int)o);      // only carved (and only valid) when CACHE
     __shared__ EvalShared sh;
     __shared__ EvalOut ev;
-    __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_cnt[2], s_spec;
+    __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_cnt[2], s_spec, s_npre, s_nrej;
     __shared__ FzScanShared fsh;
     __shared__ i64 s_ntests;
     __shared__ u64 s_exec, s_exk[3];
@@ -408,7 +418,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
         int* order = a.cand_order + o0;
 
         // ---- prepare_interleaving_phase (hiton.jl:199-220): p < alpha, stable sort by p ----
-        if (tid == 0) { s_nc = 0; s_M = 0; s_ntests = 0; s_exec = 0; s_exk[0] = s_exk[1] = s_exk[2] = 0; s_spec = 0; }
+        if (tid == 0) { s_nc = 0; s_M = 0; s_ntests = 0; s_exec = 0; s_exk[0] = s_exk[1] = s_exk[2] = 0; s_spec = 0; s_npre = 0; s_nrej = 0; }
         __syncthreads();
         for (int i = tid; i < n_uni; i += THREADS) {
             double pi = a.uni_p[e0 + i];
@@ -418,13 +428,23 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
                     double pj = a.uni_p[e0 + j];
                     if (pj < a.alpha && (pj < pi || (pj == pi && j < i))) ++rank;
                 }
-                order[rank] = i;
+                order[rank] = i | (hiton_list_flags(a.lists, tsel, a.uni_nbr[e0 + i]) << 28);
                 atomicAdd(&s_nc, 1);
             }
         }
         __syncthreads();
         const int n_c = s_nc;
         bool overflow = false;
+        const bool track = a.lists.rej_count != nullptr;
+        // rejection record of the candidate just scanned (thread 0; hiton.jl:72-74).  pos -> variable through the accepted list
+        auto reject = [&](i64 cand, const AccView& av) {
+            const i64 r = o0 + s_nrej;
+            a.lists.rej_nbr[r] = cand; a.lists.rej_k[r] = ev.k;
+            for (int i = 0; i < 3; ++i) a.lists.rej_Zs[r * 3 + i] = i < ev.k ? member[av[ev.pos[i]] - 1] : -1;
+            a.lists.rej_res[r] = make_result(ev.stat, ev.pval, ev.df, ev.suff != 0);
+            a.lists.rej_ntests[r] = ev.num_tests; a.lists.rej_frac[r] = ev.total > 0 ? (double)ev.num_tests / (double)ev.total : 0.0;
+            s_nrej = s_nrej + 1;
+        };
 
         // One barrier-separated serial section per candidate: thread 0 consumes the scan result (`ev`), does the accept /
         // reject bookkeeping of update_sig_result! (hiton.jl:53-78) and prepares the accepted list of the next candidate.
@@ -432,7 +452,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
         for (int ci = 0; ci < n_c; ++ci) {
             const int M = s_M;                         // accepted so far; acc[0..M) = slots 1..M (kept by thread 0)
             if (M + 2 > cap) { overflow = true; break; }
-            const int ui = order[ci];
+            const int ui = order[ci] & HITON_ORDER_MASK, lf = order[ci] >> 28;
+            if (lf == 2) continue;                     // blacklisted (and not whitelisted): skipped untested (hiton.jl:31-34)
             const i64 cand = a.uni_nbr[e0 + ui];
             const int ys = M + 1;
             if constexpr (!NZ) {
@@ -447,22 +468,26 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
             }
             __syncthreads();
             bool accept = false;                       // meaningful in thread 0 only
-            if (M == 0) {
+            if (lf & 1) {
+                // whitelisted: accepted untested with (NaN, NaN) (hiton.jl:20-29)
+                if (tid == 0) { tpc_stat[M] = __longlong_as_double(0x7ff8000000000000LL); tpc_p[M] = tpc_stat[M]; accept = true; }
+            } else if (M == 0) {
                 // accepted empty: accept with the univariate result (hiton.jl:57-59)
                 if (tid == 0) { tpc_stat[0] = a.uni_stat[e0 + ui]; tpc_p[0] = a.uni_p[e0 + ui]; accept = true; }
             } else {
                 FzSlotTest tf; tf.r.R = R; tf.r.ld = ld; tf.x = 0; tf.y = ys; tf.fc = a.fc;
                 bool run = true;
+                AccView av; av.n_head = M; av.head_base = 1; av.tail = pc_slot; av.n_pre = 0; av.pre = wl_slot;
                 if constexpr (NZ) {
                     // cor_subset! on the rows where T != 0 and candidate != 0 (tests.jl:293-308; hiton.jl:41-50,85)
                     const int rows = fznz_subcor_block<THREADS>(a.nzt, slotvar, M + 2, 0, ys, R, ld, vmask, mom, s_cnt);
                     run = !(a.n_obs_min > (i64)rows);                     // else (0, 1, 0, false), zero tests: rejected
                     tf.fc = nz_consts(rows, a.n_obs_min);
+                    if (!run && track && tid == 0) { ev.stat = 0.0; ev.pval = 1.0; ev.df = 0; ev.suff = 0; ev.k = 0; ev.num_tests = 0; ev.total = 0; reject(cand, av); }
                 }
                 if (run) {
                     bool cached = false;
                     if constexpr (CACHE) {
-                        AccView av; av.n_head = M; av.head_base = 1; av.tail = pc_slot;
                         cached = (M >= 3 && a.max_k >= 3 && max_tests_free) && fz_build_tables<THREADS>(R, ld, 0, ys, av, M, tb, tri_off, &fsh);
                         if (cached) eval_subsets_fz_cached<THREADS, false>(tf.r, tb, 0, ys, av, M, a.alpha, tf.fc, tri_off, &fsh, &ev, s_spec != 0);
                     }
@@ -470,11 +495,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
                     if (tid == 0) {
                         s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
                         if (ev.sig) { tpc_stat[M] = ev.stat; tpc_p[M] = ev.pval; accept = true; }
+                        else if (track) reject(cand, av);
                         s_spec = (cached && ev.sig && ev.num_tests == ev.total) ? 1 : 0;
                     }
                 }
             }
-            if (tid == 0 && accept) { member[M] = cand; acc[M] = M + 1; s_M = M + 1; }
+            if (tid == 0 && accept) { member[M] = cand; acc[M] = M + 1; sflag[M + 1] = (unsigned char)lf; s_M = M + 1; }
             __syncthreads();
         }
         if (overflow) {
@@ -489,14 +515,19 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
         if (tid == 0) s_npc = 0;
         __syncthreads();
         for (int c = 1; c <= M; ++c) {
-            const int npc0 = s_npc;
-            const int macc = (M - c) + npc0;
-            AccView av; av.n_head = M - c; av.head_base = c + 1; av.tail = pc_slot;
+            const int npc0 = s_npc, npre = s_npre;
+            const int macc = npre + (M - c) + npc0;
+            AccView av; av.n_head = M - c; av.head_base = c + 1; av.tail = pc_slot; av.n_pre = npre; av.pre = wl_slot;
             bool accept = false;                       // thread 0 only
-            if (macc == 0) {
+            if (sflag[c] & 1) {
+                // whitelisted: (NaN, NaN), pushed onto `accepted` again while its original entry stays (hiton.jl:20-29, 124-131)
+                __syncthreads();
+                if (tid == 0) { pcs_stat[npc0] = __longlong_as_double(0x7ff8000000000000LL); pcs_p[npc0] = pcs_stat[npc0]; wl_slot[npre] = c; s_npre = npre + 1; accept = true; }
+            } else if (macc == 0) {
                 __syncthreads();                       // every thread has read s_npc before thread 0 may advance it (no scan, hence no barrier, on this path)
                 if (tid == 0) { pcs_stat[npc0] = tpc_stat[c - 1]; pcs_p[npc0] = tpc_p[c - 1]; accept = true; }   // support_dict = TPC_dict
             } else {
+                if (macc + 2 > cap) { overflow = true; break; }          // duplicates of whitelisted members outgrew the class: re-run in the next one
                 FzSlotTest tf; tf.r.R = R; tf.r.ld = ld; tf.x = 0; tf.y = c; tf.fc = a.fc;
                 bool run = true;
                 if constexpr (NZ) {
@@ -505,11 +536,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
                     const int rows = fznz_subcor_block<THREADS>(a.nzt, slotvar, M + 1, 0, c, R, ld, vmask, mom, s_cnt);
                     run = !(a.n_obs_min > (i64)rows);
                     tf.fc = nz_consts(rows, a.n_obs_min);
+                    if (!run && track && tid == 0) { ev.stat = 0.0; ev.pval = 1.0; ev.df = 0; ev.suff = 0; ev.k = 0; ev.num_tests = 0; ev.total = 0; reject(member[c - 1], av); }
                 }
                 if (run) {
                     bool cached = false;
                     if constexpr (CACHE) {
-                        cached = (macc >= 3 && a.max_k >= 3 && max_tests_free) && fz_build_tables<THREADS>(R, ld, 0, c, av, macc, tb, tri_off, &fsh);
+                        cached = (macc >= 3 && macc <= FZ_CACHE_CAP - 2 && a.max_k >= 3 && max_tests_free) && fz_build_tables<THREADS>(R, ld, 0, c, av, macc, tb, tri_off, &fsh);
                         if (cached) eval_subsets_fz_cached<THREADS, false>(tf.r, tb, 0, c, av, macc, a.alpha, tf.fc, tri_off, &fsh, &ev, s_spec != 0);
                     }
                     if (!cached) {
@@ -520,12 +552,17 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
                     if (tid == 0) {
                         s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
                         if (ev.sig) { pcs_stat[npc0] = ev.stat; pcs_p[npc0] = ev.pval; accept = true; }
+                        else if (track) reject(member[c - 1], av);
                         s_spec = (cached && ev.sig && ev.num_tests == ev.total) ? 1 : 0;
                     }
                 }
             }
             if (tid == 0 && accept) { pc_slot[npc0] = c; s_npc = npc0 + 1; }
             __syncthreads();
+        }
+        if (overflow) {
+            if (tid == 0) a.status[tsel] = 1;
+            continue;
         }
 
         // ---- update_PC_dict! (hiton.jl:249-256) and write-out ---------------------------------
@@ -551,6 +588,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
         }
         if (tid == 0) {
             a.pc_count[tsel] = npc; a.tpc_count[tsel] = M; a.num_tests[tsel] = s_ntests; a.status[tsel] = 0;
+            if (track) a.lists.rej_count[tsel] = s_nrej;
             atomicAdd(a.executed_total, s_exec);
             atomicAdd(a.executed_total + 1, s_exk[0]); atomicAdd(a.executed_total + 2, s_exk[1]); atomicAdd(a.executed_total + 3, s_exk[2]);
         }

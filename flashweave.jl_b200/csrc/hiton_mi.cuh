@@ -203,6 +203,7 @@ struct HitonMiArgs {
     i64* pc_nbr; double* pc_stat; double* pc_p; i64* pc_count;
     i64* tpc_nbr; double* tpc_stat; double* tpc_p; i64* tpc_count;
     i64* num_tests; u64* executed_total; int* status;
+    HitonLists lists;                        // whitelists / blacklists / rejection records (all optional; subsets.cuh)
 };
 
 template <int THREADS, int TPT>
@@ -220,13 +221,14 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
     i64* var = reinterpret_cast<i64*>(smem + o); o += sizeof(i64) * cap;           // slot -> variable: 0 = T, 1..M members, M+1 candidate
     int* acc = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;
     int* pc_slot = reinterpret_cast<int*>(smem + o); o += sizeof(int) * cap;
+    unsigned char* sflag = smem + o; o += ((size_t)cap + 15) & ~(size_t)15;          // per slot: list flags of the member
     int* tabs = reinterpret_cast<int*>(smem + o);
     int* tab = tabs + warp * tab_ints;
     int* cnt = tabs + (THREADS / 32) * tab_ints;                                     // batched binary scan: [warps][32][32] ints
     const bool bin_table = (L == 2 && !a.t.nz);
     __shared__ EvalShared sh;
     __shared__ EvalOut ev;
-    __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_accept;
+    __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_accept, s_nrej;
     __shared__ i64 s_ntests;
     __shared__ u64 s_exec, s_exk[3];
 
@@ -242,13 +244,23 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
         const int n_uni = (int)(a.uni_off[T + 1] - e0);
         const i64 o0 = a.out_off[tsel];
         int* order = a.cand_order + o0;
-        if (tid == 0) { s_nc = 0; s_M = 0; s_ntests = 0; s_exec = 0; s_exk[0] = s_exk[1] = s_exk[2] = 0; var[0] = T; }
+        if (tid == 0) { s_nc = 0; s_M = 0; s_ntests = 0; s_exec = 0; s_exk[0] = s_exk[1] = s_exk[2] = 0; var[0] = T; s_nrej = 0; }
         __syncthreads();
+        const bool track = a.lists.rej_count != nullptr;
         // hiton.jl:182-183,300-302: a discrete target with fewer than 2 levels has no neighbours
         if (a.t.levels[T] < 2) {
-            if (tid == 0) { a.pc_count[tsel] = 0; a.tpc_count[tsel] = 0; a.num_tests[tsel] = 0; a.status[tsel] = 0; }
+            if (tid == 0) { a.pc_count[tsel] = 0; a.tpc_count[tsel] = 0; a.num_tests[tsel] = 0; a.status[tsel] = 0; if (track) a.lists.rej_count[tsel] = 0; }
             continue;
         }
+        // rejection record of the candidate just scanned (thread 0; hiton.jl:72-74): positions of `ev` refer to acc[0..)
+        auto reject = [&](i64 cand) {
+            const i64 r = o0 + s_nrej;
+            a.lists.rej_nbr[r] = cand; a.lists.rej_k[r] = ev.k;
+            for (int i = 0; i < 3; ++i) a.lists.rej_Zs[r * 3 + i] = i < ev.k ? var[acc[ev.pos[i]]] : -1;
+            a.lists.rej_res[r] = make_result(ev.stat, ev.pval, ev.df, ev.suff != 0);
+            a.lists.rej_ntests[r] = ev.num_tests; a.lists.rej_frac[r] = ev.total > 0 ? (double)ev.num_tests / (double)ev.total : 0.0;
+            s_nrej = s_nrej + 1;
+        };
         for (int i = tid; i < n_uni; i += THREADS) {
             double pi = a.uni_p[e0 + i];
             if (pi < a.alpha) {
@@ -257,7 +269,7 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
                     double pj = a.uni_p[e0 + j];
                     if (pj < a.alpha && (pj < pi || (pj == pi && j < i))) ++rank;
                 }
-                order[rank] = i;
+                order[rank] = i | (hiton_list_flags(a.lists, tsel, a.uni_nbr[e0 + i]) << 28);
                 atomicAdd(&s_nc, 1);
             }
         }
@@ -268,12 +280,16 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
         for (int ci = 0; ci < n_c; ++ci) {
             const int M = s_M;
             if (M + 2 > cap) { overflow = true; break; }
-            const int ui = order[ci];
+            const int ui = order[ci] & HITON_ORDER_MASK, lf = order[ci] >> 28;
+            if (lf == 2) continue;                     // blacklisted (and not whitelisted): skipped untested (hiton.jl:31-34)
             const i64 cand = a.uni_nbr[e0 + ui];
             const int ys = M + 1;
             if (tid == 0) { var[ys] = cand; s_accept = 0; }
             __syncthreads();
-            if (M == 0) {
+            if (lf & 1) {
+                // whitelisted: accepted untested with (NaN, NaN) (hiton.jl:20-29)
+                if (tid == 0) { tpc_stat[M] = __longlong_as_double(0x7ff8000000000000LL); tpc_p[M] = tpc_stat[M]; s_accept = 1; }
+            } else if (M == 0) {
                 if (tid == 0) { tpc_stat[0] = a.uni_stat[e0 + ui]; tpc_p[0] = a.uni_p[e0 + ui]; s_accept = 1; }
             } else {
                 for (int s = tid; s < M; s += THREADS) acc[s] = s + 1;
@@ -286,10 +302,11 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
                 if (tid == 0) {
                     s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
                     if (ev.sig) { tpc_stat[M] = ev.stat; tpc_p[M] = ev.pval; s_accept = 1; }
+                    else if (track) reject(cand);
                 }
             }
             __syncthreads();
-            if (s_accept) { if (tid == 0) s_M = M + 1; }      // var[M+1] already holds the candidate = member M
+            if (s_accept) { if (tid == 0) { s_M = M + 1; sflag[M + 1] = (unsigned char)lf; } }      // var[M+1] already holds the candidate = member M
             __syncthreads();
         }
         if (overflow) { if (tid == 0) a.status[tsel] = 1; continue; }
@@ -299,14 +316,18 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
         if (tid == 0) { s_macc = M; s_npc = 0; }
         __syncthreads();
         for (int c = 1; c <= M; ++c) {
+            const bool wl = (sflag[c] & 1) != 0;
             if (tid == 0) {
-                int w = 0, macc = s_macc;
-                for (int j = 0; j < macc; ++j) { int v = acc[j]; if (v != c) acc[w++] = v; }
-                s_macc = w; s_accept = 0;
+                // deleteat!(accepted, findall(in(candidate), accepted)) (hiton.jl:134-136); a whitelisted member stays and is pushed again
+                if (!wl) { int w = 0, macc = s_macc; for (int j = 0; j < macc; ++j) { int v = acc[j]; if (v != c) acc[w++] = v; } s_macc = w; }
+                s_accept = 0;
             }
             __syncthreads();
             const int macc = s_macc;
-            if (macc == 0) {
+            if (macc + 2 > cap) { overflow = true; break; }              // duplicates of whitelisted members outgrew the class
+            if (wl) {
+                if (tid == 0) { pcs_stat[s_npc] = __longlong_as_double(0x7ff8000000000000LL); pcs_p[s_npc] = pcs_stat[s_npc]; s_accept = 1; }
+            } else if (macc == 0) {
                 if (tid == 0) { pcs_stat[s_npc] = tpc_stat[c - 1]; pcs_p[s_npc] = tpc_p[c - 1]; s_accept = 1; }
             } else {
                 MiSlotTest tf; tf.t = a.t; tf.var = var; tf.x = 0; tf.y = c; tf.hps = a.hps; tf.tab = tab;
@@ -317,12 +338,14 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
                 if (tid == 0) {
                     s_ntests += ev.num_tests; s_exec += (u64)ev.executed; s_exk[0] += (u64)ev.ex_k[0]; s_exk[1] += (u64)ev.ex_k[1]; s_exk[2] += (u64)ev.ex_k[2];
                     if (ev.sig) { pcs_stat[s_npc] = ev.stat; pcs_p[s_npc] = ev.pval; s_accept = 1; }
+                    else if (track) reject(var[c]);
                 }
             }
             __syncthreads();
             if (tid == 0 && s_accept) { acc[s_macc] = c; s_macc = s_macc + 1; pc_slot[s_npc] = c; s_npc = s_npc + 1; }
             __syncthreads();
         }
+        if (overflow) { if (tid == 0) a.status[tsel] = 1; continue; }
         const int npc = s_npc;
         for (int i = tid; i < npc; i += THREADS) {
             int c = pc_slot[i];
@@ -336,6 +359,7 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
         }
         if (tid == 0) {
             a.pc_count[tsel] = npc; a.tpc_count[tsel] = M; a.num_tests[tsel] = s_ntests; a.status[tsel] = 0;
+            if (track) a.lists.rej_count[tsel] = s_nrej;
             atomicAdd(a.executed_total, s_exec);
             atomicAdd(a.executed_total + 1, s_exk[0]); atomicAdd(a.executed_total + 2, s_exk[1]); atomicAdd(a.executed_total + 3, s_exk[2]);
         }

@@ -23,6 +23,24 @@ struct EvalOut {
     i64 ex_k[3];        // ... of which with |Zs| = 1, 2, 3
 };
 
+// Per-target whitelists / blacklists of si_HITON_PC (src/hiton.jl:20-38: a whitelisted candidate is accepted untested with
+// (NaN, NaN) - and, in the elimination phase, pushed a SECOND time onto `accepted`; a blacklisted one is skipped) and the optional
+// rejection records of track_rejections (src/hiton.jl:72-74: candidate -> (Zs, TestResult, (num_tests, frac))).  Lists are CSR
+// over the launch's target list; rejection slots share the targets' output ranges (a target rejects at most its candidate count).
+struct HitonLists {
+    const i64* wl_off; const i64* wl_idx;
+    const i64* bl_off; const i64* bl_idx;
+    i64* rej_count; i64* rej_nbr; i64* rej_Zs; int* rej_k; DevResult* rej_res; i64* rej_ntests; double* rej_frac;
+};
+// bit 0: candidate is whitelisted, bit 1: blacklisted
+__device__ __forceinline__ int hiton_list_flags(const HitonLists& L, int tsel, i64 cand) {
+    int f = 0;
+    if (L.wl_off) for (i64 i = L.wl_off[tsel]; i < L.wl_off[tsel + 1]; ++i) if (L.wl_idx[i] == cand) { f |= 1; break; }
+    if (L.bl_off) for (i64 i = L.bl_off[tsel]; i < L.bl_off[tsel + 1]; ++i) if (L.bl_idx[i] == cand) { f |= 2; break; }
+    return f;
+}
+constexpr int HITON_ORDER_MASK = 0x0fffffff;            // cand_order[rank] = position in the univariate list | list flags << 28
+
 struct EvalShared {
     u64 fail_idx;
     double w_p[32];

@@ -68,7 +68,8 @@ int32_t fw_host_unregister(fw_ctx* ctx, void* ptr);
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 int64_t fw_launch_count(fw_ctx* ctx);
 /* device time in ms (CUDA events on the context's stream) of the last run of each phase:
- * out[0] cor_mat kernels, out[1] pairwise-stage kernels, out[2] HITON-PC kernel(s), out[3] reserved; -1 = not run */
+ * out[0] cor_mat kernels, out[1] pairwise-stage kernels, out[2] HITON-PC kernel(s), out[3] reserved, out[4] the standardising
+ * kernel inside out[0] of fw_multi_cor, out[5] the wait in fw_multi_cor's closing group barrier; -1 = not run */
 int32_t fw_last_timing(fw_ctx* ctx, double* out_ms, int32_t n);
 
 /* ---- data (the `data` argument of every reference test function) ----------------------- */
@@ -205,7 +206,7 @@ int32_t fw_set_univar_nbrs(fw_ctx* ctx, const int64_t* offsets /* p+1 */, const 
 /* counters of the last fw_pairwise: tests evaluated, reliable (non-NaN) tests = BH's m, raw p < alpha */
 int32_t fw_pairwise_stats(fw_ctx* ctx, int64_t* n_tests, int64_t* n_reliable, int64_t* n_raw_sig);
 
-/* ---- per-target loop: si_HITON_PC, src/hiton.jl:283-400 (time_limit = 0, no white/blacklist) ---- */
+/* ---- per-target loop: si_HITON_PC, src/hiton.jl:283-400 (time_limit = 0) ---- */
 /* Runs interleaving + elimination for every target in targets[] on the device, one CTA per
  * target, against the resident neighbour lists (fw_pairwise / fw_set_univar_nbrs).
  * Outputs per target t (slot range pc_off[t]..pc_off[t+1], capacity = its candidate count):
@@ -218,6 +219,22 @@ int32_t fw_hiton_pc(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t*
                     int64_t* pc_off /* n_targets+1 */, int64_t* pc_count, int64_t* pc_nbr, double* pc_stat, double* pc_p,
                     int64_t* tpc_count, int64_t* tpc_nbr, double* tpc_stat, double* tpc_p,
                     int64_t* num_tests, int64_t* tests_executed_total);
+/* The same with the remaining keyword arguments of si_HITON_PC (src/hiton.jl:283-292):
+ *  - whitelist / blacklist per target as CSR over targets[] (wl_off[n_targets+1], wl_idx[]; NULL = none), src/hiton.jl:20-38:
+ *    a whitelisted candidate is accepted untested with (NaN, NaN) in both phases - in the elimination phase it is pushed onto
+ *    `accepted` a second time, exactly as the reference does - a blacklisted one is skipped.  This is what the feed-forward
+ *    schedule of src/interleaved.jl:124-128 (the reference's default single_il / multi_il modes) passes per target job;
+ *  - track_rejections (src/hiton.jl:72-74): rej_count != NULL requests HitonState.state_rejections, per target in its slot range
+ *    pc_off[t]..: rejected candidate, the subset Zs (rej_k entries of rej_Zs[3], -1 padded) and TestResult that rejected it,
+ *    (num_tests, frac) of that test_subsets call. */
+int32_t fw_hiton_pc_ex(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64_t* targets,
+                       int32_t max_k, double alpha, int64_t hps, int64_t n_obs_min, int64_t max_tests,
+                       const int64_t* wl_off, const int64_t* wl_idx, const int64_t* bl_off, const int64_t* bl_idx,
+                       int64_t* pc_off, int64_t* pc_count, int64_t* pc_nbr, double* pc_stat, double* pc_p,
+                       int64_t* tpc_count, int64_t* tpc_nbr, double* tpc_stat, double* tpc_p,
+                       int64_t* num_tests, int64_t* tests_executed_total,
+                       int64_t* rej_count, int64_t* rej_nbr, int64_t* rej_Zs, int32_t* rej_k, fw_test_result* rej_result,
+                       int64_t* rej_num_tests, double* rej_frac);
 /* tests executed by the last fw_hiton_pc with |Zs| = 1, 2, 3 (for the algorithmic-bytes figure of the roofline) */
 int32_t fw_hiton_exec_by_k(fw_ctx* ctx, int64_t* out3);
 /* capacity query for the arrays above: sum over targets of their candidate counts */

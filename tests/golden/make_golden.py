@@ -13,7 +13,7 @@ Run once in the build container:  python tests/golden/make_golden.py
       -> raw counts and the six expected normalisations (test/preprocessing.jl:48-84) for the normalisation step
 
 Outputs: tests/golden/hmp_inputs.npz, tests/golden/tests_expected.json,
-         tests/golden/learning_expected.json, tests/golden/prep_fixtures.npz,
+         tests/golden/learning_expected.json, tests/golden/edgelists/*.edgelist (verbatim), tests/golden/prep_fixtures.npz,
          tests/golden/meta_onehot.json
 """
 import json
@@ -92,6 +92,11 @@ def main():
         graphs[name] = sorted(edges)
     with open(os.path.join(OUT, "learning_expected.json"), "w") as f:
         json.dump(graphs, f, indent=0)
+    # the raw files too (a few KB): the edgelist writer is compared with them byte for byte (src/io.jl:338-359)
+    import shutil
+    os.makedirs(os.path.join(OUT, "edgelists"), exist_ok=True)
+    for fn in sorted(os.listdir(ld)):
+        shutil.copyfile(os.path.join(ld, fn), os.path.join(OUT, "edgelists", fn))
     print("wrote", os.listdir(OUT))
 
 
