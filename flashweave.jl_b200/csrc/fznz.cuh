@@ -239,6 +239,14 @@ __device__ void fznz_gram_block(const float* __restrict__ data, i64 ldv, int n, 
     }
     __syncthreads();
     const int n_pairs = nv * (nv - 1) / 2;
+    // Diagonal: only read when a whitelisted member occurs twice in a conditioning set (hiton.jl:20-29).  cor_subset! then sees the
+    // variable in two columns of the view and stores their computed correlation at cor_mat[Z, Z] (statfuns.jl:146-152 with X == Y):
+    // the same moments with G_ab = G_aa, i.e. 1 up to rounding, or 0 for a variable that is constant on the view (NaN -> 0)
+    for (int a = tid; a < nv; a += THREADS) {
+        const double g = G[a * FZNZ_GMAX + a], sa = G[a * FZNZ_GMAX + nv];
+        const double rr = fznz_r_from_moments(g, g, g, sa, sa, (double)rows);
+        R[a * ld + a] = isnan(rr) ? 0.0f : (float)rr;
+    }
     for (int e = tid; e < n_pairs; e += THREADS) {
         int a, b; unrank2_small(e, nv, a, b);
         const double rr = fznz_r_from_moments(G[a * FZNZ_GMAX + a], G[b * FZNZ_GMAX + b], G[a * FZNZ_GMAX + b],
@@ -310,6 +318,10 @@ __device__ int fznz_subcor_block(const NzTable& t, const i64* var, int nv, int x
         if (live && cls == 0) mom[it] = v;
     }
     __syncthreads();
+    for (int a = tid; a < nv; a += THREADS) {                                 // the diagonal: see fznz_gram_block
+        const double rr = fznz_r_from_moments(mom[2 * a + 1], mom[2 * a + 1], mom[2 * a + 1], mom[2 * a], mom[2 * a], (double)rows);
+        R[a * ld + a] = isnan(rr) ? 0.0f : (float)rr;
+    }
     const int n_pairs = nv * (nv - 1) / 2;
     for (int e = warp * 4 + sub; e < ((n_pairs + 3) & ~3); e += (THREADS / 32) * 4) {
         const bool live = e < n_pairs;

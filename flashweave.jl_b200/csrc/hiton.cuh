@@ -458,8 +458,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
             const int ys = M + 1;
             if constexpr (!NZ) {
                 // gather the candidate's correlations with T and the members into slot ys
-                for (int s = tid; s <= M; s += THREADS) {
-                    i64 other = (s == 0) ? T : member[s - 1];
+                // (incl. the diagonal entry cor_mat[cand, cand]: a whitelisted member can occur twice in a conditioning set, hiton.jl:20-29)
+                for (int s = tid; s <= M + 1; s += THREADS) {
+                    i64 other = (s == 0) ? T : (s == ys ? cand : member[s - 1]);
                     float v = a.cv.at(cand, other);
                     R[ys * ld + s] = v; R[s * ld + ys] = v;
                 }

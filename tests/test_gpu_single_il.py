@@ -132,4 +132,4 @@ def test_rejection_records(fw, hmp, kind):
             single = eng.test(T, cand, Zs, n_obs_min=nom)
             assert single[2] == tr[2] and single[3] == tr[3]
             assert abs(single[0]) == pytest.approx(abs(tr[0]), rel=1e-12, abs=1e-300) and single[1] == pytest.approx(tr[1], rel=1e-9, abs=1e-300)
-    assert n_rej > 10
+    assert n_rej > (10 if kind != "fz_nz" else 0)        # the fz_nz fixture has 10 univariate edges in all
