@@ -63,7 +63,7 @@ struct fw_ctx {
     DevBuf<int> d_data_i32;
     i64 n_obs = -1;                      // rows used by Fisher-z tests
     // discrete table: bit planes + per-variable level statistics (mi.cuh)
-    DevBuf<unsigned int> d_planes; DevBuf<int> d_levels, d_maxvals, d_nnz, d_bad;
+    DevBuf<unsigned int> d_planes; DevBuf<int> d_levels, d_maxvals, d_nnz, d_bad; DevBuf<double> d_logtab;
     std::vector<int> h_levels, h_maxvals;
     int disc_L = 0, disc_W = 0;
     // fz_nz: non-zero planes of the continuous table (fznz.cuh), built on first use
@@ -196,6 +196,7 @@ static MiTable make_mi_table(const fw_ctx* c, int kind) {
     t.p = c->p; t.n = (int)c->n; t.W = c->disc_W; t.L = c->disc_L; t.nz = (kind == FW_MI_NZ) ? 1 : 0;
     const int rem = (int)(c->n & 31);
     t.tail_mask = rem ? ((1u << rem) - 1u) : 0xffffffffu;
+    t.lgt = c->d_logtab.ptr;
     return t;
 }
 
@@ -546,6 +547,10 @@ static int install_discrete_table(fw_ctx* ctx, int64_t n, int64_t p, const char*
         ctx->launches++;
         CK(cudaGetLastError());
     }
+    CK(ctx->d_logtab.reserve((size_t)n + 1));
+    mi_logtab_kernel<<<(unsigned)((n + 256) / 256), 256, 0, ctx->stream>>>((int)n, ctx->d_logtab.ptr);
+    ctx->launches++;
+    CK(cudaGetLastError());
     ctx->n = n; ctx->p = p; ctx->ld = n; ctx->data_kind = 1; ctx->n_obs = n;
     table_changed(ctx);
     return FW_OK;
@@ -1488,13 +1493,22 @@ int32_t fw_hiton_pc_ex(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64
         i64 need = 2; for (i64 t = 0; t < n_targets; ++t) need = std::max<i64>(need, hoff[t + 1] - hoff[t] + 2);
         const int TH = 256; const int L = ma.t.L;
         const size_t tabs = (size_t)(TH / 32) * L * L * L * L * L * sizeof(int) + (size_t)(TH / 32) * MI_BIN_WARP_BYTES;   // + count buffers of the batched binary scan
-        // optimistic capacity (accepted sets are far smaller than candidate lists); re-run overflowing targets with the full bound
-        int caps[2] = {(int)std::min<i64>(need, 64), (int)need};
+        // optimistic capacity (accepted sets are far smaller than candidate lists); re-run overflowing targets in the next class
+        int caps[3] = {(int)std::min<i64>(need, 32), (int)std::min<i64>(need, 64), (int)need};
+        const int n_rounds = need <= 32 ? 1 : (need <= 64 ? 2 : 3);
         CK(cudaEventRecord(ctx->ev[4], ctx->stream));
         std::vector<int> hstatus(n_targets);
-        for (int round = 0; round < 2 && !sel.empty(); ++round) {
+        const int Wp = ma.t.W | 1;                                        // odd row stride: conflict-free per-lane plane reads
+        for (int round = 0; round < n_rounds && !sel.empty(); ++round) {
             ma.cap = caps[round];
-            size_t smem = sizeof(i64) * (ma.cap + 1) + 4 * sizeof(double) * ma.cap + sizeof(i64) * ma.cap + 2 * sizeof(int) * ma.cap + (((size_t)ma.cap + 15) & ~(size_t)15) + tabs + 16;
+            const size_t fixed = sizeof(i64) * (ma.cap + 1) + 4 * sizeof(double) * ma.cap + sizeof(i64) * ma.cap + 2 * sizeof(int) * ma.cap + (((size_t)ma.cap + 15) & ~(size_t)15);
+            // binary tables: the planes of every slot staged in shared memory + the positive-AND count tables (mi_lane.cuh); the
+            // region is shared with the buffers of the warp-cooperative scan, which remains the path for everything else
+            const size_t lane_bytes = sizeof(unsigned int) * (size_t)ma.cap * Wp + sizeof(int) * MI_LANE_TAB_INTS;
+            ma.Wp = Wp;
+            ma.lane_ok = (L == 2 && !ma.t.nz && ma.cap <= 64 && fixed + lane_bytes + 16 <= 100 * 1024) ? 1 : 0;
+            const size_t gen_tabs = (size_t)(TH / 32) * L * L * L * L * L * sizeof(int);
+            size_t smem = fixed + gen_tabs + (ma.lane_ok ? lane_bytes : tabs - gen_tabs) + 16;      // (the batched scan's buffers are unused on the lane path)
             NEED(smem <= 220 * 1024, FW_ERR_UNSUPPORTED, "fw_hiton_pc: a target has %lld candidates; too many for the discrete kernel", (long long)need - 2);
             int n_sel = (int)sel.size();
             CK(cudaMemcpyAsync(dsel.ptr, sel.data(), sizeof(int) * n_sel, cudaMemcpyHostToDevice, ctx->stream));
@@ -1510,7 +1524,7 @@ int32_t fw_hiton_pc_ex(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64
             CK(cudaStreamSynchronize(ctx->stream));
             std::vector<int> again;
             for (int t : sel) if (hstatus[t] == 1) again.push_back(t);
-            NEED(again.empty() || round == 0, FW_ERR_UNSUPPORTED, "fw_hiton_pc: capacity overflow in the full-bound class");
+            NEED(again.empty() || round + 1 < n_rounds, FW_ERR_UNSUPPORTED, "fw_hiton_pc: capacity overflow in the full-bound class");
             sel.swap(again);
         }
     }

@@ -7,6 +7,7 @@
 #include "fznz_tc.cuh"
 #include "subsets.cuh"
 #include "hiton.cuh"
+#include "mi_lane.cuh"
 
 struct MiSlotTest {
     MiTable t; const i64* var; int x, y; i64 hps; int* tab;
@@ -204,10 +205,14 @@ struct HitonMiArgs {
     i64* tpc_nbr; double* tpc_stat; double* tpc_p; i64* tpc_count;
     i64* num_tests; u64* executed_total; int* status;
     HitonLists lists;                        // whitelists / blacklists / rejection records (all optional; subsets.cuh)
+    int lane_ok, Wp;                         // binary tables: the planes of `cap` slots fit shared memory (row stride Wp, odd): one lane per test (mi_lane.cuh)
 };
 
+#ifndef FW_MI_MINB
+#define FW_MI_MINB 2
+#endif
 template <int THREADS, int TPT>
-__global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
+__global__ void __launch_bounds__(THREADS, FW_MI_MINB) hiton_mi_kernel(HitonMiArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int cap = a.cap, L = a.t.L;
@@ -226,6 +231,11 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
     int* tab = tabs + warp * tab_ints;
     int* cnt = tabs + (THREADS / 32) * tab_ints;                                     // batched binary scan: [warps][32][32] ints
     const bool bin_table = (L == 2 && !a.t.nz);
+    // one-lane-per-test scan (mi_lane.cuh): staged planes [cap][Wp] + count tables; shares the region of the batched scan's count buffers
+    const bool use_lane = bin_table && a.lane_ok;
+    const int Wp = a.Wp, W = a.t.W;
+    unsigned int* sp = reinterpret_cast<unsigned int*>(cnt);                          // (the per-warp tables `tab` of the generic scan stay usable)
+    int* ltabs = reinterpret_cast<int*>(sp + (size_t)cap * Wp);
     __shared__ EvalShared sh;
     __shared__ EvalOut ev;
     __shared__ int s_ti, s_nc, s_M, s_macc, s_npc, s_accept, s_nrej;
@@ -247,6 +257,7 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
         if (tid == 0) { s_nc = 0; s_M = 0; s_ntests = 0; s_exec = 0; s_exk[0] = s_exk[1] = s_exk[2] = 0; var[0] = T; s_nrej = 0; }
         __syncthreads();
         const bool track = a.lists.rej_count != nullptr;
+        if (use_lane) for (int w = tid; w < W; w += THREADS) sp[w] = __ldg(a.t.planes + (size_t)T * W + w);      // slot 0 = the target
         // hiton.jl:182-183,300-302: a discrete target with fewer than 2 levels has no neighbours
         if (a.t.levels[T] < 2) {
             if (tid == 0) { a.pc_count[tsel] = 0; a.tpc_count[tsel] = 0; a.num_tests[tsel] = 0; a.status[tsel] = 0; if (track) a.lists.rej_count[tsel] = 0; }
@@ -285,6 +296,7 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
             const i64 cand = a.uni_nbr[e0 + ui];
             const int ys = M + 1;
             if (tid == 0) { var[ys] = cand; s_accept = 0; }
+            if (use_lane) for (int w = tid; w < W; w += THREADS) sp[(size_t)ys * Wp + w] = __ldg(a.t.planes + (size_t)cand * W + w);
             __syncthreads();
             if (lf & 1) {
                 // whitelisted: accepted untested with (NaN, NaN) (hiton.jl:20-29)
@@ -295,7 +307,9 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
                 for (int s = tid; s < M; s += THREADS) acc[s] = s + 1;
                 __syncthreads();
                 MiSlotTest tf; tf.t = a.t; tf.var = var; tf.x = 0; tf.y = ys; tf.hps = a.hps; tf.tab = tab;
-                if (bin_table && a.t.levels[T] == 2 && a.t.levels[cand] == 2)
+                if (use_lane && M <= MI_LANE_MAX_M && a.t.levels[T] == 2 && a.t.levels[cand] == 2)
+                    eval_subsets_mi_lane<THREADS>(sp, Wp, W, a.t.n, 0, ys, acc, M, a.max_k, a.alpha, a.max_tests, a.hps, tri_off, ltabs, &sh, &ev, a.t.lgt);
+                else if (bin_table && !use_lane && a.t.levels[T] == 2 && a.t.levels[cand] == 2)
                     eval_subsets_mi_bin<THREADS>(a.t.planes, a.t.W, a.t.tail_mask, var, 0, ys, acc, M, a.max_k, a.alpha, a.max_tests, a.hps, tri_off, cnt, &sh, &ev);
                 else
                     eval_subsets<THREADS, TPT, 32>(tf, acc, M, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);
@@ -331,7 +345,9 @@ __global__ void __launch_bounds__(THREADS) hiton_mi_kernel(HitonMiArgs a) {
                 if (tid == 0) { pcs_stat[s_npc] = tpc_stat[c - 1]; pcs_p[s_npc] = tpc_p[c - 1]; s_accept = 1; }
             } else {
                 MiSlotTest tf; tf.t = a.t; tf.var = var; tf.x = 0; tf.y = c; tf.hps = a.hps; tf.tab = tab;
-                if (bin_table && a.t.levels[T] == 2 && a.t.levels[var[c]] == 2)
+                if (use_lane && macc <= MI_LANE_MAX_M && a.t.levels[T] == 2 && a.t.levels[var[c]] == 2)
+                    eval_subsets_mi_lane<THREADS>(sp, Wp, W, a.t.n, 0, c, acc, macc, a.max_k, a.alpha, a.max_tests, a.hps, tri_off, ltabs, &sh, &ev, a.t.lgt);
+                else if (bin_table && !use_lane && a.t.levels[T] == 2 && a.t.levels[var[c]] == 2)
                     eval_subsets_mi_bin<THREADS>(a.t.planes, a.t.W, a.t.tail_mask, var, 0, c, acc, macc, a.max_k, a.alpha, a.max_tests, a.hps, tri_off, cnt, &sh, &ev);
                 else
                     eval_subsets<THREADS, TPT, 32>(tf, acc, macc, a.max_k, a.alpha, a.max_tests, tri_off, &sh, &ev);

@@ -30,7 +30,13 @@ struct MiTable {
     const int* nnz;               // per variable: rows with a non-zero code
     i64 p; int n; int W; int L; int nz;   // nz: zero-adjusted kind (mi_nz)
     unsigned int tail_mask;       // valid bits of the last word
+    const double* lgt;            // lgt[i] = log(i), i = 0..n (lgt[0] = 0): the cells and margins of a table are integers <= n (mi_lane.cuh)
 };
+
+__global__ void mi_logtab_kernel(int n, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) out[i] = i > 0 ? log((double)i) : 0.0;
+}
 
 __device__ __forceinline__ const unsigned int* mi_plane(const MiTable& t, i64 v, int lvl /*1..L-1*/) {
     return t.planes + ((size_t)v * (t.L - 1) + (lvl - 1)) * (size_t)t.W;
