@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "fw_pairwise", "fw_pairwise_copy", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_ex", "fw_hiton_pc_capacity",
     "fw_normalize_f32", "fw_get_data_f32", "fw_get_data_i32", "fw_set_data_csc_f32", "fw_set_data_csc_i32",
     "fw_host_register", "fw_host_unregister",
-    "fw_cor_gather", "fw_pairwise_prefetch",
+    "fw_cor_gather", "fw_pairwise_prefetch", "fw_set_meta_mask", "fw_get_meta_mask",
     "fw_comm_handle_bytes", "fw_comm_export", "fw_comm_attach", "fw_comm_detach", "fw_multi_set_data_f32", "fw_multi_cor",
     "fw_build_info",
 ]
@@ -123,6 +123,8 @@ def load_library():
         "fw_get_data_f32": (i32, [vp, vp, i64]),
         "fw_get_data_i32": (i32, [vp, vp, i64]),
         "fw_cor_gather": (i32, [vp, vp, i64, vp]),
+        "fw_set_meta_mask": (i32, [vp, vp, i64]),
+        "fw_get_meta_mask": (i32, [vp, vp, i64]),
         "fw_pairwise_prefetch": (i32, [vp, dbl, i64]),
         "fw_comm_handle_bytes": (i32, []),
         "fw_comm_export": (i32, [vp, i32, i32, i64, i64, vp]),
@@ -315,6 +317,7 @@ class Engine:
             table = out if out is not None else self.get_data()
             comb, mmask, mnames = _meta.combine_with_meta(table, res["obs_filter_mask"], meta_data, meta_header, mode, make_onehot)
             self.set_data(comb, self.kind)
+            self.set_meta_mask(mmask)
             res.update(data=comb if want_host else None, meta_mask=mmask, meta_names=mnames)
         return res
 
@@ -352,6 +355,15 @@ class Engine:
         self.kind, self.n, self.p = kind, n, p
         self._cor_valid = False
         return self
+
+    def set_meta_mask(self, mask):
+        m = np.ascontiguousarray(np.asarray(mask, dtype=bool).astype(np.uint8))
+        self._ck(self.L.fw_set_meta_mask(self.h, _p(m), len(m)))
+
+    def meta_mask(self):
+        m = np.zeros(self.p, np.uint8)
+        self._ck(self.L.fw_get_meta_mask(self.h, _p(m), self.p))
+        return m.astype(bool)
 
     def levels(self):
         """get_levels / get_max_vals (misc.jl:64-97) of the resident discrete table"""

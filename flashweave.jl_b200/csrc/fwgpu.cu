@@ -69,6 +69,7 @@ struct fw_ctx {
     // fz_nz: non-zero planes of the continuous table (fznz.cuh), built on first use
     DevBuf<unsigned int> d_nzmask; DevBuf<int> d_nnz_f; bool nz_ready = false;
 
+    std::vector<uint8_t> meta_mask;     // meta_variable_mask of the resident table (carried to the host side's edgelist; no device use)
     // cor_mat: the full symmetric matrix (d_cor), or - in a multi-GPU group - this rank's row shard (grp, CorView)
     DevBuf<float> d_cor; i64 cor_p = 0;
     bool cor_sharded = false;
@@ -117,6 +118,7 @@ static int fail(fw_ctx* c, int code, const char* fmt, ...) {
 // non-zero planes and the univariate neighbour lists (fw_hiton_pc / fw_pairwise_copy then fail with FW_ERR_STATE instead of
 // silently running against the lists of another table)
 static void table_changed(fw_ctx* c) {
+    c->meta_mask.clear();
     c->nz_ready = false; c->tcp.valid = false; c->cor_p = 0; c->cor_sharded = false; c->col.valid = false;
     c->uni_entries = -1; c->h_uni_off.clear();
 }
@@ -576,6 +578,20 @@ int32_t fw_set_data_csc_i32(fw_ctx* ctx, const int64_t* colptr, const int64_t* r
     int st_ = set_data_csc<int>(ctx, colptr, rowval, nzval, n, p, ctx->d_data_i32, "fw_set_data_csc_i32");
     if (st_ != FW_OK) return st_;
     return install_discrete_table(ctx, n, p, "fw_set_data_csc_i32");
+}
+// meta_variable_mask (src/preprocessing.jl:418-446, written by src/io.jl:338-346): which variables are meta variables.  The tests treat
+// meta variables like any other variable (they differ in preprocessing only), so the mask is carried for the writers, not used on the device.
+int32_t fw_set_meta_mask(fw_ctx* ctx, const uint8_t* mask, int64_t p) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(p >= 0 && (p == 0 || mask) && (ctx->p == 0 || p == ctx->p), FW_ERR_INVALID, "fw_set_meta_mask: %lld entries for %lld variables", (long long)p, (long long)ctx->p);
+    ctx->meta_mask.assign(mask, mask + p);
+    return FW_OK;
+}
+int32_t fw_get_meta_mask(fw_ctx* ctx, uint8_t* mask_out, int64_t p) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(mask_out && p == ctx->p, FW_ERR_INVALID, "fw_get_meta_mask: %lld entries for %lld variables", (long long)p, (long long)ctx->p);
+    for (i64 i = 0; i < p; ++i) mask_out[i] = i < (i64)ctx->meta_mask.size() ? ctx->meta_mask[i] : 0;
+    return FW_OK;
 }
 int32_t fw_set_n_obs(fw_ctx* ctx, int64_t n) { if (!ctx) return FW_ERR_INVALID; NEED(n >= 0, FW_ERR_INVALID, "n_obs < 0"); ctx->n_obs = n; return FW_OK; }
 

@@ -85,6 +85,11 @@ int32_t fw_set_data_csc_i32(fw_ctx* ctx, const int64_t* colptr, const int64_t* r
 /* same, device-resident inputs owned by the caller (e.g. a tensor that was NCCL-broadcast);
  * the pointer must stay valid until the next fw_set_data / fw_adopt_data / fw_destroy */
 int32_t fw_adopt_data_f32_device(fw_ctx* ctx, const float* dev, int64_t n, int64_t p, int64_t ld);
+/* meta_variable_mask of the resident table (src/preprocessing.jl:418-446; `# meta mask` line of src/io.jl:338-346).  Meta variables
+ * are ordinary variables for every test; the mask is stored with the table (cleared when a new table is installed) and handed back to
+ * the host side that writes the network. */
+int32_t fw_set_meta_mask(fw_ctx* ctx, const uint8_t* mask, int64_t p);
+int32_t fw_get_meta_mask(fw_ctx* ctx, uint8_t* mask_out, int64_t p);
 /* number of observations used by Fisher-z tests when only a cor_mat is installed
  * (size(data,1) in src/tests.jl:150,256) */
 int32_t fw_set_n_obs(fw_ctx* ctx, int64_t n);

@@ -165,4 +165,10 @@ def test_meta_variables(fw, golden_dir):
         # resident table = returned table; the hot path runs on it
         assert eng.p == data.shape[1] and eng.n == data.shape[0]
         assert (eng.get_data() == data).all()
-        eng.LGL(max_k=0)
+        assert (eng.meta_mask() == mm).all()                  # fw_set_meta_mask: carried with the resident table ...
+        r = eng.LGL(max_k=0)
+        out = os.path.join(os.environ.get("TMPDIR", "/tmp"), "fw_meta_%s.edgelist" % tn)
+        fw.write_edgelist(out, r["edges"], header=["v%d" % i for i in range(eng.p)], meta_mask=eng.meta_mask())
+        assert open(out).read().split("\n")[1] == "# meta mask\t" + ",".join("true" if m else "false" for m in mm)   # ... to the `# meta mask` line (io.jl:338-346)
+        eng.set_data(data[:, :5], tn)
+        assert not eng.meta_mask().any()                      # a new table clears it
