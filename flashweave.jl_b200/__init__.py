@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "fw_pairwise", "fw_pairwise_copy", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_ex", "fw_hiton_pc_capacity",
     "fw_normalize_f32", "fw_get_data_f32", "fw_get_data_i32", "fw_set_data_csc_f32", "fw_set_data_csc_i32",
     "fw_host_register", "fw_host_unregister",
-    "fw_cor_gather", "fw_pairwise_prefetch", "fw_set_meta_mask", "fw_get_meta_mask",
+    "fw_cor_gather", "fw_pairwise_prefetch", "fw_set_meta_mask", "fw_get_meta_mask", "fw_set_semantics",
     "fw_comm_handle_bytes", "fw_comm_export", "fw_comm_attach", "fw_comm_detach", "fw_multi_set_data_f32", "fw_multi_cor",
     "fw_build_info",
 ]
@@ -123,6 +123,7 @@ def load_library():
         "fw_get_data_f32": (i32, [vp, vp, i64]),
         "fw_get_data_i32": (i32, [vp, vp, i64]),
         "fw_cor_gather": (i32, [vp, vp, i64, vp]),
+        "fw_set_semantics": (i32, [vp, i32]),
         "fw_set_meta_mask": (i32, [vp, vp, i64]),
         "fw_get_meta_mask": (i32, [vp, vp, i64]),
         "fw_pairwise_prefetch": (i32, [vp, dbl, i64]),
@@ -355,6 +356,10 @@ class Engine:
         self.kind, self.n, self.p = kind, n, p
         self._cor_valid = False
         return self
+
+    def set_semantics(self, sparse):
+        """mi_nz: follow the reference's sparse-input code path (contingency.jl:182-258, 300-480) instead of the dense one"""
+        self._ck(self.L.fw_set_semantics(self.h, 1 if sparse else 0))
 
     def set_meta_mask(self, mask):
         m = np.ascontiguousarray(np.asarray(mask, dtype=bool).astype(np.uint8))

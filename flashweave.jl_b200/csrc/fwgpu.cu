@@ -66,6 +66,7 @@ struct fw_ctx {
     DevBuf<unsigned int> d_planes; DevBuf<int> d_levels, d_maxvals, d_nnz, d_bad; DevBuf<double> d_logtab;
     std::vector<int> h_levels, h_maxvals;
     int disc_L = 0, disc_W = 0;
+    int sparse_sem = 0;                  // fw_set_semantics
     // fz_nz: non-zero planes of the continuous table (fznz.cuh), built on first use
     DevBuf<unsigned int> d_nzmask; DevBuf<int> d_nnz_f; bool nz_ready = false;
 
@@ -199,6 +200,7 @@ static MiTable make_mi_table(const fw_ctx* c, int kind) {
     const int rem = (int)(c->n & 31);
     t.tail_mask = rem ? ((1u << rem) - 1u) : 0xffffffffu;
     t.lgt = c->d_logtab.ptr;
+    t.sparse_sem = (c->sparse_sem && kind == FW_MI_NZ) ? 1 : 0;
     return t;
 }
 
@@ -591,6 +593,12 @@ int32_t fw_get_meta_mask(fw_ctx* ctx, uint8_t* mask_out, int64_t p) {
     if (!ctx) return FW_ERR_INVALID;
     NEED(mask_out && p == ctx->p, FW_ERR_INVALID, "fw_get_meta_mask: %lld entries for %lld variables", (long long)p, (long long)ctx->p);
     for (i64 i = 0; i < p; ++i) mask_out[i] = i < (i64)ctx->meta_mask.size() ? ctx->meta_mask[i] : 0;
+    return FW_OK;
+}
+int32_t fw_set_semantics(fw_ctx* ctx, int32_t semantics) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(semantics == FW_SEMANTICS_DENSE || semantics == FW_SEMANTICS_SPARSE, FW_ERR_INVALID, "fw_set_semantics: unknown value %d", semantics);
+    ctx->sparse_sem = semantics;
     return FW_OK;
 }
 int32_t fw_set_n_obs(fw_ctx* ctx, int64_t n) { if (!ctx) return FW_ERR_INVALID; NEED(n >= 0, FW_ERR_INVALID, "n_obs < 0"); ctx->n_obs = n; return FW_OK; }

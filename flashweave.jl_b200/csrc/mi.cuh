@@ -31,6 +31,7 @@ struct MiTable {
     i64 p; int n; int W; int L; int nz;   // nz: zero-adjusted kind (mi_nz)
     unsigned int tail_mask;       // valid bits of the last word
     const double* lgt;            // lgt[i] = log(i), i = 0..n (lgt[0] = 0): the cells and margins of a table are integers <= n (mi_lane.cuh)
+    int sparse_sem;               // mi_nz: semantics of the reference's SPARSE-input code path (contingency.jl:182-258, 300-480), see mi_epilogue_warp
 };
 
 __global__ void mi_logtab_kernel(int n, double* __restrict__ out) {
@@ -86,8 +87,13 @@ struct MiResult { double stat; double pval; i64 df; bool suff; };
 // ---- warp-cooperative epilogue: MI, df, p from a dense count table in (per-warp) shared memory ---------
 // tab[s*L*L + b*L + a] = N(X=a, Y=b, stratum s), S strata (S = 1: univariate).  All 32 lanes call this.
 // Follows tests.jl:48-68 (univariate) / :200-221 (conditional) after the table has been built.
+// sparse_k > 0: a conditional test with |Zs| = sparse_k under the reference's sparse-input semantics (its default tables for
+// sensitive=false, learning.jl:470).  The table itself equals the dense one on the rows the test uses; what differs is levels_z in
+// the power rule (tests.jl:210): the k = 1 specialisation indexes slices by the raw z value and reports max(z) + 1
+// (contingency.jl:171-173, 229); the generic merge back-fills the rows it never visited (all-zero rows and, under Nz, the rows
+// where X or Y is zero) into the stratum of the all-zero key, creating that stratum if no visited row had it (contingency.jl:461-477).
 __device__ MiResult mi_epilogue_warp(const int* tab, int L, int S, int lvx, int lvy, int mvx, int mvy, int nz, bool conditional,
-                                     i64 hps, i64 n_obs_min) {
+                                     i64 hps, i64 n_obs_min, int sparse_k = 0, i64 n_total = 0) {
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     int ox = 0, oy = 0, lx = lvx, ly = lvy, sx = L, sy = L;
@@ -100,7 +106,25 @@ __device__ MiResult mi_epilogue_warp(const int* tab, int L, int S, int lvx, int 
         for (int b = 0; b < L; ++b) for (int a = 0; a < L; ++a) { int c = t[b * L + a]; tot += c; if (a >= ox && b >= oy) sub += c; }
         lz_loc += tot > 0; nobs_loc += sub;
     }
-    const int levels_z = conditional ? __reduce_add_sync(full, lz_loc) : 1;
+    int levels_z = conditional ? __reduce_add_sync(full, lz_loc) : 1;
+    if (conditional && sparse_k > 0 && nz && (ox || oy)) {
+        int hi = -1; i64 cnt = 0;
+        for (int s = lane; s < S; s += 32) {
+            const int* t = tab + s * L * L;
+            int tot = 0;
+            for (int e = 0; e < L * L; ++e) tot += t[e];
+            if (tot > 0) hi = s;
+            cnt += tot;
+        }
+        hi = __reduce_max_sync(full, hi);
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(full, cnt, o);
+        if (sparse_k == 1) levels_z = hi + 1 > 1 ? hi + 1 : 1;
+        else {
+            int tot0 = 0;
+            for (int e = 0; e < L * L; ++e) tot0 += tab[e];
+            if (tot0 == 0 && n_total - cnt > 0) levels_z += 1;
+        }
+    }
     i64 n_obs = nobs_loc;
     for (int o = 16; o > 0; o >>= 1) n_obs += __shfl_xor_sync(full, n_obs, o);
     MiResult r;
@@ -308,10 +332,14 @@ __device__ MiResult mi_test_warp(const MiTable& t, i64 X, i64 Y, const i64* Z, i
         mi_count_warp(t, X, Y, Z, 0, trim_x, false, tab);
         return mi_epilogue_warp(tab, t.L, 1, lvx, lvy, t.max_vals[X], t.max_vals[Y], t.nz, false, hps, n_obs_min);
     }
-    const bool trim_y = mi_needs_nz_view(t, Y);
-    mi_count_warp(t, X, Y, Z, k, trim_x, trim_y, tab);
+    // rows of the test: the dense path trims the view for a variable with more than 2 levels (misc.jl:103-107, hiton.jl:41-50,85),
+    // the sparse path skips the zero rows of a variable with max_val > 1 (contingency.jl:243-248)
+    const bool sp = t.sparse_sem && t.nz;
+    const bool tx = sp ? t.max_vals[X] > 1 : trim_x;
+    const bool trim_y = sp ? t.max_vals[Y] > 1 : mi_needs_nz_view(t, Y);
+    mi_count_warp(t, X, Y, Z, k, tx, trim_y, tab);
     int S = 1; for (int j = 0; j < k; ++j) S *= t.L;
-    return mi_epilogue_warp(tab, t.L, S, lvx, lvy, t.max_vals[X], t.max_vals[Y], t.nz, true, hps, n_obs_min);
+    return mi_epilogue_warp(tab, t.L, S, lvx, lvy, t.max_vals[X], t.max_vals[Y], t.nz, true, hps, n_obs_min, sp ? k : 0, (i64)t.n);
 }
 
 // ---- table preparation ---------------------------------------------------------------------------------

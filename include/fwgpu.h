@@ -82,6 +82,14 @@ int32_t fw_set_data_i32(fw_ctx* ctx, const int32_t* host, int64_t n, int64_t p, 
  * on the device and then behaves exactly like the dense one (the dense test semantics are the canonical ones). */
 int32_t fw_set_data_csc_f32(fw_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const float* nzval, int64_t n, int64_t p);
 int32_t fw_set_data_csc_i32(fw_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const int32_t* nzval, int64_t n, int64_t p);
+/* Which of the reference's two code paths the discrete zero-ignoring kind (mi_nz) follows.  FW_SEMANTICS_DENSE (default): the
+ * Matrix{Int32} path (src/contingency.jl:7-56 + level_map!), the canonical semantics.  FW_SEMANTICS_SPARSE: the SparseMatrixCSC path
+ * the reference takes by default for sensitive=false (make_sparse, src/learning.jl:470): identical tables, but levels_z of the power
+ * rule (src/tests.jl:210) is max(z)+1 in the max_k = 1 specialisation (src/contingency.jl:171-173, 229) and may count the back-fill
+ * stratum of the generic merge (src/contingency.jl:461-477); rows are skipped per max_val > 1 instead of trimmed per levels > 2.
+ * Applies to the table however it was uploaded (dense or fw_set_data_csc_i32); mi / fz / fz_nz are unaffected. */
+enum fw_semantics { FW_SEMANTICS_DENSE = 0, FW_SEMANTICS_SPARSE = 1 };
+int32_t fw_set_semantics(fw_ctx* ctx, int32_t semantics);
 /* same, device-resident inputs owned by the caller (e.g. a tensor that was NCCL-broadcast);
  * the pointer must stay valid until the next fw_set_data / fw_adopt_data / fw_destroy */
 int32_t fw_adopt_data_f32_device(fw_ctx* ctx, const float* dev, int64_t n, int64_t p, int64_t ld);

@@ -213,9 +213,14 @@ static Rows trim_rows(const Data& D, const Rows& in, i64 V) {
     return r;
 }
 
+// SparseMatrixCSC image of the discrete table (0-based), built when the sparse semantics are switched on
+struct Csc { std::vector<i64> colptr; std::vector<i32> rowval, nzval; };
+
 struct Ctx {
     int kind;
     Data D;
+    bool sparse_sem = false;             // discrete kinds: follow the reference's sparse-input code path (contingency.jl:80-480)
+    Csc csc;
     std::vector<i32> levels, max_vals;   // misc.jl:64-97 (discrete only)
     i64 max_level;                       // types.jl:88-91,110: maximum(max_vals)+1
     CorMat C;                            // precomputed cor_mat (fz) or scratch (fz_nz)
@@ -227,6 +232,9 @@ struct Ctx {
 static bool needs_nz_view(const Ctx& c, i64 X) {
     bool nz = is_nz(c.kind);
     bool is_nz_var = !is_discrete(c.kind) || c.levels[X] > 2;
+    // misc.jl:103-107: `!issparse(data) || isa(test_obj, FzTestCond)` - a sparse discrete table is never row-trimmed, the sparse
+    // contingency functions skip the zero rows of X / Y themselves
+    if (is_discrete(c.kind) && c.sparse_sem) return false;
     return nz && is_nz_var;
 }
 
@@ -438,8 +446,103 @@ static fwo_result test_mi_uni(const Ctx& c, DiscScratch& s, i64 X, i64 Y, const 
 }
 
 // tests.jl:184-229 conditional discrete test; contingency.jl:42-56 + misc.jl:162-184
+// ---- sparse 3-way tables (the reference's default input for sensitive=false, learning.jl:470) -----------------------------
+// contingency.jl:182-237: the max_k = 1 / heterogeneous specialisation.  Slices are indexed by the RAW z value and
+// levels_z = largest z value seen + 1 (:171-173, :229) - not the number of distinct values the dense path reports.
+static i64 sparse_ctab_k1(const Ctx& c, i64 X, i64 Y, i64 Z, bool X_nz, bool Y_nz, i64* tab) {
+    const Csc& A = c.csc; const i64 L = c.max_level, n = c.D.n;
+    i64 levels_z = 1;
+    i64 pX = A.colptr[X], pY = A.colptr[Y], pZ = A.colptr[Z];
+    const i64 eX = A.colptr[X + 1], eY = A.colptr[Y + 1], eZ = A.colptr[Z + 1];
+    i64 vX = 0, vY = 0, vZ = 0;                                       // 0-based values (the reference's val - 1)
+    i64 rZ = pZ < eZ ? A.rowval[pZ] : n;                              // n = "beyond the last row"
+    auto zupd = [&](i64 row) {                                        // make_Zupd_expression, :144-161
+        while (pZ < eZ - 1 && rZ < row) { ++pZ; rZ = A.rowval[pZ]; }
+        if (rZ == row) { vZ = A.nzval[pZ]; if (vZ + 1 > levels_z) levels_z = vZ + 1; } else vZ = 0;
+    };
+    while (pX < eX && pY < eY) {                                      // :203-218
+        const i64 rX = A.rowval[pX], rY = A.rowval[pY];
+        if (rX == rY) { vX = A.nzval[pX]; vY = A.nzval[pY]; zupd(rX); tab[vX + vY * L + vZ * L * L] += 1; ++pX; ++pY; }
+        else if (rX < rY) { if (!Y_nz) { vX = A.nzval[pX]; vY = 0; zupd(rX); tab[vX + vY * L + vZ * L * L] += 1; } ++pX; }
+        else { if (!X_nz) { vY = A.nzval[pY]; vX = 0; zupd(rY); tab[vX + vY * L + vZ * L * L] += 1; } ++pY; }
+    }
+    if (!Y_nz) { vY = 0; while (pX < eX) { vX = A.nzval[pX]; zupd(A.rowval[pX]); tab[vX + vY * L + vZ * L * L] += 1; ++pX; } }   // :125-141
+    if (!X_nz) { vX = 0; while (pY < eY) { vY = A.nzval[pY]; zupd(A.rowval[pY]); tab[vX + vY * L + vZ * L * L] += 1; ++pY; } }
+    return levels_z;
+}
+
+// contingency.jl:300-480 sparse_ctab_backend! for cols = (X, Y, Zs...): merge over the rows with at least one non-zero among the
+// columns; under Nz a row where an adjusted X / Y is zero is skipped; z keys are mapped first-seen (:262-284); the rows never
+// visited (all-zero or skipped) are back-filled into ctab[1, 1, slice of the all-zero key], which may ADD a stratum (:461-477).
+static i64 sparse_ctab_backend(const Ctx& c, DiscScratch& s, const i64* cols, int N, bool nz_type, bool X_nz, bool Y_nz, i64* tab) {
+    const Csc& A = c.csc; const i64 L = c.max_level, n = c.D.n;
+    std::fill(s.z_map.begin(), s.z_map.end(), -1);
+    i64 levels_total = 0, n_oob = 0, min_ind = n - 1, counted = 0;   // rows 0-based: the reference's n_rows <-> n - 1, n_rows + 1 <-> n
+    bool break_loop = false;
+    i64 ptr[5], bound[5], rowind[5], val[5];
+    for (int i = 0; i < N; ++i) {
+        ptr[i] = A.colptr[cols[i]]; bound[i] = A.colptr[cols[i] + 1];
+        if (ptr[i] < bound[i]) { rowind[i] = A.rowval[ptr[i]]; if (rowind[i] < min_ind) min_ind = rowind[i]; }
+        else { if (nz_type && i < 2 && (i == 0 ? X_nz : Y_nz)) break_loop = true; rowind[i] = n; ++n_oob; }
+    }
+    while (true) {
+        bool skip_row = false;
+        i64 next_min = n - 1;
+        for (int i = 0; i < N; ++i) {
+            if (nz_type && i >= 2 && skip_row) {                      // :395-410: catch up without reading a value
+                while (rowind[i] < next_min) { ++ptr[i]; if (ptr[i] >= bound[i]) { ++n_oob; rowind[i] = n; } else rowind[i] = A.rowval[ptr[i]]; }
+            } else {
+                if (rowind[i] == min_ind) {
+                    val[i] = A.nzval[ptr[i]]; ++ptr[i];
+                    if (ptr[i] >= bound[i]) { if (nz_type && i < 2 && (i == 0 ? X_nz : Y_nz)) break_loop = true; ++n_oob; rowind[i] = n; }
+                    else rowind[i] = A.rowval[ptr[i]];
+                } else {
+                    val[i] = 0;
+                    if (nz_type && i < 2 && (i == 0 ? X_nz : Y_nz)) skip_row = true;
+                }
+            }
+            if (rowind[i] < next_min) next_min = rowind[i];
+        }
+        if (!skip_row) {
+            i64 key = 0; for (int i = 2; i < N; ++i) key += val[i] * s.cum_levels[i - 2];
+            i32 zv = s.z_map[(size_t)key];
+            if (zv == -1) { zv = (i32)levels_total; s.z_map[(size_t)key] = zv; ++levels_total; }
+            tab[val[0] + val[1] * L + (i64)zv * L * L] += 1; ++counted;
+        }
+        if (nz_type && break_loop) break;
+        if (n_oob >= N) break;
+        min_ind = next_min;
+    }
+    const i64 all_zero_obs = n - counted;                             // :461-477
+    if (all_zero_obs > 0) {
+        i64 idx;
+        if (s.z_map[0] != -1) idx = s.z_map[0]; else { idx = levels_total; ++levels_total; }
+        tab[idx * L * L] += all_zero_obs;
+    }
+    return levels_total;
+}
+
+static fwo_result mi_cond_from_table(const Ctx& c, DiscScratch& s, i64 X, i64 Y, i64 levels_z, i64 hps);
+
+// tests.jl:184-229 on a sparse table: contingency.jl:240-258 picks the specialisation
+static fwo_result test_mi_cond_sparse(const Ctx& c, DiscScratch& s, i64 X, i64 Y, const i64* Zs, int k, i64 hps,
+                                      i64* out_levels_z = nullptr, i64* out_ctab = nullptr) {
+    const i64 L = c.max_level, S = s.nz_slices;
+    i64* tab = s.ctab.data();
+    for (i64 t = 0; t < L * L * S; ++t) tab[t] = 0;
+    const bool nzk = is_nz(c.kind);
+    const bool X_nz = nzk && c.max_vals[X] > 1, Y_nz = nzk && c.max_vals[Y] > 1;
+    i64 levels_z;
+    if (k == 1 && (X_nz || Y_nz)) levels_z = sparse_ctab_k1(c, X, Y, Zs[0], X_nz, Y_nz, tab);
+    else { i64 cols[5] = {X, Y, 0, 0, 0}; for (int j = 0; j < k; ++j) cols[2 + j] = Zs[j]; levels_z = sparse_ctab_backend(c, s, cols, 2 + k, nzk, X_nz, Y_nz, tab); }
+    if (out_levels_z) *out_levels_z = levels_z;
+    if (out_ctab) memcpy(out_ctab, tab, sizeof(i64) * (size_t)(L * L * S));
+    return mi_cond_from_table(c, s, X, Y, levels_z, hps);
+}
+
 static fwo_result test_mi_cond(const Ctx& c, DiscScratch& s, i64 X, i64 Y, const i64* Zs, int k, const Rows& R, i64 hps,
                                i64* out_levels_z = nullptr, i64* out_ctab = nullptr) {
+    if (c.sparse_sem) return test_mi_cond_sparse(c, s, X, Y, Zs, k, hps, out_levels_z, out_ctab);   // (R is the untrimmed table: needs_nz_view)
     i64 L = c.max_level, S = s.nz_slices, rows = R.size();
     i64* tab = s.ctab.data();
     for (i64 t = 0; t < L * L * S; ++t) tab[t] = 0;
@@ -457,6 +560,13 @@ static fwo_result test_mi_cond(const Ctx& c, DiscScratch& s, i64 X, i64 Y, const
     for (i64 i = 0; i < rows; ++i) { i64 r = R[i]; tab[cx[r] + cy[r] * L + (i64)s.z[(size_t)i] * L * L] += 1; }
     if (out_levels_z) *out_levels_z = levels_z;
     if (out_ctab) memcpy(out_ctab, tab, sizeof(i64) * (size_t)(L * L * S));
+    return mi_cond_from_table(c, s, X, Y, levels_z, hps);
+}
+
+// second half of tests.jl:184-229: nz adjustment, power rule, MI, df, p from the table in s.ctab
+static fwo_result mi_cond_from_table(const Ctx& c, DiscScratch& s, i64 X, i64 Y, i64 levels_z, i64 hps) {
+    const i64 L = c.max_level, S = s.nz_slices;
+    i64* tab = s.ctab.data();
     i64 lx = c.levels[X], ly = c.levels[Y], ox = 0, oy = 0, sx = L, sy = L;
     if (is_nz(c.kind)) {
         ox = c.max_vals[X] > 1 ? 1 : 0; oy = c.max_vals[Y] > 1 ? 1 : 0;
@@ -852,6 +962,18 @@ fwo_ctx* fwo_create(int kind, i64 n, i64 p, const double* data_f64, const i32* d
     return h;
 }
 void fwo_destroy(fwo_ctx* h) { delete h; }
+// discrete kinds: follow the reference's sparse-input code path (SparseMatrixCSC tables, the default for sensitive=false)
+void fwo_set_sparse_semantics(fwo_ctx* h, int on) {
+    Ctx& c = h->c;
+    c.sparse_sem = on != 0 && is_discrete(c.kind);
+    if (c.sparse_sem && c.csc.colptr.empty()) {
+        c.csc.colptr.assign((size_t)c.D.p + 1, 0);
+        for (i64 v = 0; v < c.D.p; ++v) {
+            for (i64 i = 0; i < c.D.n; ++i) { i32 x = c.D.disc[i + v * c.D.n]; if (x != 0) { c.csc.rowval.push_back((i32)i); c.csc.nzval.push_back(x); } }
+            c.csc.colptr[(size_t)v + 1] = (i64)c.csc.rowval.size();
+        }
+    }
+}
 void fwo_get_levels(fwo_ctx* h, i32* levels, i32* max_vals) {
     for (i64 i = 0; i < h->c.D.p; ++i) { levels[i] = h->c.levels[(size_t)i]; max_vals[i] = h->c.max_vals[(size_t)i]; }
 }

@@ -44,6 +44,7 @@ def lib():
         L.fwo_create.argtypes = [C.c_int, i64, i64, p, p, C.c_int]
         L.fwo_destroy.argtypes = [p]
         L.fwo_get_levels.argtypes = [p, p, p]
+        L.fwo_set_sparse_semantics.argtypes = [p, C.c_int]
         L.fwo_compute_cor.argtypes = [p]
         L.fwo_set_cor.argtypes = [p, p]
         L.fwo_get_cor.argtypes = [p, p]
@@ -108,6 +109,10 @@ class Oracle:
             self.L.fwo_destroy(self.h)
         except Exception:
             pass
+
+    def set_sparse_semantics(self, on=True):
+        """discrete kinds: the reference's sparse-input code path (contingency.jl:80-480), its default for sensitive=false"""
+        self.L.fwo_set_sparse_semantics(self.h, int(on))
 
     # -- precompute ---------------------------------------------------------------
     def levels(self):

@@ -210,3 +210,48 @@ def test_discrete_hiton_pc_and_graph(fw, synth, hmp, golden_dir, kind):
             want3 = {(a_, b_) for a_, b_, _ in graphs[f"exp_{kind}_maxk3"]}
             got3 = {(a_, b_) for a_, b_, _ in r3["edges"]}
             assert len(got3 ^ want3) == (11 if kind == "mi" else 0)
+
+
+def test_sparse_input_semantics_mi_nz(fw, hmp):
+    """FW_SEMANTICS_SPARSE (the reference's SparseMatrixCSC code path, its default for sensitive=false): single tests, the subset
+    search and the whole network against the oracle's restatement of contingency.jl:182-258, 300-480; and the reference's own
+    dense-vs-sparse check (test/learning.jl:369-383) replayed on the GPU."""
+    A = np.array(hmp["mi_nz"], dtype=np.int32)
+    A[:, -6:] = (A[:, -6:] == 0)                       # "make some variables binary to test Nz behaviour"
+    x = np.ascontiguousarray(A.T)
+    n, p = A.shape
+    ora = fwo.Oracle(A, "mi_nz"); ora.set_sparse_semantics(True)
+    ora_d = fwo.Oracle(A, "mi_nz")
+    # uploaded as the CSC triple a Julia host would pass (index base 0 here)
+    colptr = np.zeros(p + 1, np.int64); rv, nz = [], []
+    for v in range(p):
+        r = np.nonzero(x[v])[0]
+        rv.append(r); nz.append(x[v][r]); colptr[v + 1] = colptr[v] + len(r)
+    eng = fw.Engine(0)
+    eng.set_data_csc(colptr, np.concatenate(rv), np.concatenate(nz), n, p, "mi_nz")
+    eng.set_semantics(sparse=True)
+    rng = np.random.default_rng(12)
+    X, Y, Zs = [], [], []
+    for _ in range(1500):
+        k = int(rng.integers(1, 4))
+        v = rng.choice(p, size=2 + k, replace=False)
+        X.append(int(v[0])); Y.append(int(v[1])); Zs.append(tuple(int(z) for z in v[2:]))
+    got = eng.test_batch(X, Y, Zs, hps=5)
+    n_div = 0
+    for x_, y_, z_, g in zip(X, Y, Zs, got):
+        w = ora.test_cond(x_, y_, list(z_), hps=5)
+        assert _same(g, w) or (g[2] == w[2] and g[3] == w[3] and _close(abs(g[0]), abs(w[0]), 1e-12) and _sign_is_a_tie(x, x_, y_, z_)), (x_, y_, z_, g, w)
+        n_div += ora_d.test_cond(x_, y_, list(z_), hps=5)[3] != w[3]
+    assert n_div > 0                                   # the two code paths do differ in power on this table
+    # networks: sparse semantics == oracle (sparse); and sparse ~ dense at max_k 0 / 1 as the reference asserts
+    for max_k in (0, 1, 3):
+        eng.set_semantics(sparse=True)
+        r = eng.LGL(max_k=max_k)
+        w = ora.lgl(max_k=max_k, mode="single")
+        assert [(a, b) for a, b, _ in r["edges"]] == [(a, b) for a, b, _ in w["edges"]] and r["cond_tests"] == w["cond_tests"]
+        assert np.allclose([e[2] for e in r["edges"]], [e[2] for e in w["edges"]], rtol=1e-12, atol=0)
+        if max_k <= 1:
+            eng.set_semantics(sparse=False)
+            rd = eng.LGL(max_k=max_k)
+            assert [(a, b) for a, b, _ in r["edges"]] == [(a, b) for a, b, _ in rd["edges"]]
+            assert np.allclose([e[2] for e in r["edges"]], [e[2] for e in rd["edges"]], rtol=1e-8, atol=0)

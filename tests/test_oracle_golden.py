@@ -197,3 +197,75 @@ def test_round5_shortcut():
     L.fwo_round5_shortcut_mismatches.restype = ctypes.c_longlong
     L.fwo_round5_shortcut_mismatches.argtypes = [ctypes.c_longlong]
     assert L.fwo_round5_shortcut_mismatches(400000) == 0
+
+
+# ---- sparse-input code path of the discrete kinds (contingency.jl:80-480) ------------------------------------------------
+def _slices_equal_up_to_permutation(got, want):
+    """test/contingency.jl:28-53 compare_cond_ctabs: every expected z-slice occurs among the computed ones"""
+    g = [got[:2, :2, i] for i in range(got.shape[2])]
+    used = set()
+    for j in range(want.shape[2]):
+        hit = next((i for i in range(len(g)) if i not in used and (g[i] == want[:, :, j]).all()), None)
+        if hit is None:
+            return False
+        used.add(hit)
+    return True
+
+
+def test_sparse_contingency_known_answers():
+    """test/contingency.jl:55-69 in its "sparse" mode: the CSC merge back-end gives the dense tables up to the order of the z slices"""
+    v1 = [0, 0, 0, 0, 1, 1, 1, 1, 0, 1, 0, 1]
+    v2 = [0, 0, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1]
+    v3 = [0, 0, 1, 1, 1, 1, 0, 0, 0, 1, 0, 2]
+    v4 = [0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1]
+    data = np.array([v1, v2, v3, v4]).T
+    want3 = np.zeros((2, 2, 3), int)
+    want3[0, 0, 0], want3[1, 0, 0], want3[0, 1, 1], want3[1, 1, 1], want3[1, 1, 2] = 4, 2, 2, 3, 1
+    want34 = np.zeros((2, 2, 5), int)
+    want34[0, 0, 0], want34[0, 1, 1], want34[1, 1, 1], want34[0, 0, 2], want34[1, 0, 2], want34[1, 1, 3], want34[1, 1, 4] = 2, 2, 2, 2, 2, 1, 1
+    for sparse in (False, True):
+        o = fwo.Oracle(data, "mi")
+        o.set_sparse_semantics(sparse)
+        _, lz, ctab = o.test_cond(0, 1, [2], max_k=1, want_ctab=True)
+        assert lz == 3 and _slices_equal_up_to_permutation(ctab, want3)
+        _, lz, ctab = o.test_cond(0, 1, [2, 3], max_k=2, want_ctab=True)
+        assert lz == 5 and _slices_equal_up_to_permutation(ctab, want34)
+    # test/contingency.jl:71-83: an all-zero Y under Nz must terminate
+    v = np.concatenate([np.ones(25, int), np.full(25, 2)])
+    A = np.stack([v, np.zeros(50, int), v], axis=1)
+    o = fwo.Oracle(A, "mi_nz")
+    o.set_sparse_semantics(True)
+    for X, Y, Z in [(0, 1, [2]), (1, 0, [2]), (0, 2, [1]), (0, 2, [1, 1])]:
+        r = o.test_cond(X, Y, Z, max_k=2)
+        assert r[3] in (True, False)
+
+
+def test_sparse_vs_dense_semantics(inputs):
+    """test/learning.jl:369-383 ("sparse special optim (max_k 0 / 1, mi_nz)"): the mi_nz table with its last six variables made
+    binary, learnt from the dense and from the sparse representation, gives the same network weights; and, test by test, the two code
+    paths build the same sub-table - only levels_z of the power rule may differ (contingency.jl:171-173, 229, 461-477)."""
+    A = np.array(inputs["mi_nz"], dtype=np.int32)
+    A[:, -6:] = (A[:, -6:] == 0)
+    for max_k in (0, 1):
+        nets = []
+        for sparse in (False, True):
+            o = fwo.Oracle(A, "mi_nz")
+            o.set_sparse_semantics(sparse)
+            nets.append(o.lgl(max_k=max_k, mode="single"))
+        ea, eb = {(a, b): w for a, b, w in nets[0]["edges"]}, {(a, b): w for a, b, w in nets[1]["edges"]}
+        assert set(ea) == set(eb) and all(ea[e] == pytest.approx(eb[e], rel=1e-8) for e in ea)
+    rng = np.random.default_rng(8)
+    od, os_ = fwo.Oracle(A, "mi_nz"), fwo.Oracle(A, "mi_nz")
+    os_.set_sparse_semantics(True)
+    n_div = 0
+    for _ in range(600):
+        k = int(rng.integers(1, 4))
+        v = [int(x) for x in rng.choice(A.shape[1], size=2 + k, replace=False)]
+        (rd, lzd), (rs, lzs) = od.test_cond(v[0], v[1], v[2:], want_ctab=True)[:2], os_.test_cond(v[0], v[1], v[2:], want_ctab=True)[:2]
+        assert lzs >= lzd                                  # the sparse path never reports fewer strata
+        n_div += lzs != lzd
+        if rd[3] and rs[3]:
+            assert rd[0] == pytest.approx(rs[0], rel=1e-12, abs=1e-300) and rd[2] == rs[2] and rd[1] == pytest.approx(rs[1], rel=1e-10)
+        else:
+            assert rd[3] or not rs[3]                      # more strata can only lose power
+    assert n_div > 10
