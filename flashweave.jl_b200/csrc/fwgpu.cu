@@ -1038,7 +1038,7 @@ int32_t fw_multi_cor(fw_ctx* ctx) {
         const int staged = n * (i64)sizeof(float) <= 200 * 1024 ? 1 : 0;
         const size_t smem = staged ? (size_t)n * sizeof(float) : 0;
         CK(cudaFuncSetAttribute(fwcomm::standardize_split_peer_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-        fwcomm::standardize_split_peer_kernel<256><<<(unsigned)p_pad, 256, smem, ctx->stream>>>(ps, G.world, n, p, kp, zhi, zlo, staged);
+        fwcomm::standardize_split_peer_kernel<256><<<(unsigned)p_pad, 256, smem, ctx->stream>>>(ps, G.world, n, p, kp, zhi, zlo, staged, G.col0((G.rank + 1) % G.world));
         ctx->launches++;
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->evx[0], ctx->stream));
