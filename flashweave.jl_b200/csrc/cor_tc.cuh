@@ -546,11 +546,15 @@ static cudaError_t prepare(Scratch& S, Prepared& P, const float* d_data, i64 n, 
     return cudaSuccess;
 }
 
-// upper-triangular tiles of tile rows [bi0, bi1)
-static bool use_cluster_kernel() {
-    static const int v = [] { const char* e = getenv("FWGPU_COR_CLUSTER"); return e ? atoi(e) : 1; }();
-    return v != 0;
+// upper-triangular tiles of tile rows [bi0, bi1).  FWGPU_COR_CLUSTER: 0 = cor_tc_kernel (one CTA per 128 x 128 tile), 1 = cor_tc2_kernel
+// (CTA pair sharing A by multicast), 2 = cor_tc3_kernel (cta_group::2, 256 x 256 super-tile per CTA pair; cor_tc3.cuh, the default)
+static int cluster_kernel_mode() {
+    static const int v = [] { const char* e = getenv("FWGPU_COR_CLUSTER"); return e ? atoi(e) : 2; }();
+    return v;
 }
+static bool use_cluster_kernel() { return cluster_kernel_mode() != 0; }
+static cudaError_t launch_tc3(const Prepared& P, float* d_cor, i64 p, int bi0, int bi1, bool mirror, int bjlo, int bjhi, cudaStream_t st, int* n_launch,
+                              std::string* msg, const PwEmit& em, int sh_world, int sh_h);
 // clusters of cor_tc2_kernel for tile rows [bi0, bi1) x columns [bjlo, bjhi): see the tile-order comment in the kernel
 static long long grouped_clusters(int bi0, int bi1, int bjlo, int bjhi) {
     long long c = 0;
@@ -565,6 +569,7 @@ static cudaError_t run_rows(const Prepared& P, float* d_cor, i64 p, int bi0, int
                             const PwEmit& em = PwEmit{nullptr, nullptr, 0, 2.0f, 0}, int sh_world = 1, int sh_h = 1) {
     if (bi1 > P.nb) bi1 = P.nb;
     if (bi0 >= bi1) return cudaSuccess;
+    if (cluster_kernel_mode() == 2) return launch_tc3(P, d_cor, p, bi0, bi1, mirror, 0, P.nb, st, n_launch, msg, em, sh_world, sh_h);
     if (use_cluster_kernel()) {
         const long long clusters = grouped_clusters(bi0, bi1, 0, P.nb);
         cudaError_t e = cudaFuncSetAttribute(cor_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -628,10 +633,15 @@ static cudaError_t run_overlapped(Scratch& S, const float* host, float* d_data, 
         const i64 s1 = (c == chunks - 1) ? p_pad : (i64)t1 * BM;          // the last chunk also zero-fills the padding rows
         standardize_split_kernel<256><<<(unsigned)(s1 - c0), 256, 0, st>>>(d_data, n, n, p, kp, zhi, zlo, c0);
         (*n_launch)++;
-        const long long clusters = grouped_clusters(0, t1, t0, t1);
-        cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(kp / BK), nb, 0, t1, 1, t0, t1, em, 1, 1);
-        (*n_launch)++;
-        e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "cor_tc2_kernel (band)"; return e; }
+        if (cluster_kernel_mode() == 2) {
+            P.kp = kp; P.p_pad = p_pad; P.nb = nb;
+            e = launch_tc3(P, d_cor, p, 0, t1, true, t0, t1, st, n_launch, msg, em, 1, 1); if (e != cudaSuccess) return e;
+        } else {
+            const long long clusters = grouped_clusters(0, t1, t0, t1);
+            cor_tc2_kernel<<<(unsigned)(2 * clusters), NTHREADS, SMEM_BYTES, st>>>(P.tm_hi, P.tm_lo, d_cor, p, (int)(kp / BK), nb, 0, t1, 1, t0, t1, em, 1, 1);
+            (*n_launch)++;
+            e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "cor_tc2_kernel (band)"; return e; }
+        }
         t0 = t1;
     }
     return cudaSuccess;

@@ -18,6 +18,7 @@
 #include "hiton.cuh"
 #include "pairwise.cuh"
 #include "cor_tc.cuh"
+#include "cor_tc3.cuh"
 #include "comm.cuh"
 #include "mi.cuh"
 #include "hiton_mi.cuh"
@@ -1595,6 +1596,7 @@ int32_t fw_hiton_pc_ex(fw_ctx* ctx, int32_t kind, int64_t n_targets, const int64
             size_t smem = hiton_smem_bytes(a.cap, true, nzw, cache);
             NEED(smem <= 220 * 1024, FW_ERR_UNSUPPORTED, "fw_hiton_pc: target does not fit shared memory (n = %lld rows, %d slots)", (long long)ctx->n, a.cap);
             if (nzk) { CK(grid_for(hiton_fz_kernel<256, 2, true, false, false>, 256, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<256, 2, true, false, false><<<grid, 256, smem, ctx->stream>>>(a); }
+            else if (cache && !lists.wl_off && !lists.bl_off) { CK(grid_for(hiton_fz_kernel<128, 4, false, false, true, false>, 128, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<128, 4, false, false, true, false><<<grid, 128, smem, ctx->stream>>>(a); }
             else if (cache) { CK(grid_for(hiton_fz_kernel<128, 4, false, false, true>, 128, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<128, 4, false, false, true><<<grid, 128, smem, ctx->stream>>>(a); }
             else if (c <= 1) { CK(grid_for(hiton_fz_kernel<128, 2, false, false, false>, 128, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<128, 2, false, false, false><<<grid, 128, smem, ctx->stream>>>(a); }
             else { CK(grid_for(hiton_fz_kernel<256, 2, false, false, false>, 256, smem, ctx->sm_count, n_sel, &grid)); hiton_fz_kernel<256, 2, false, false, false><<<grid, 256, smem, ctx->stream>>>(a); }

@@ -359,7 +359,8 @@ __device__ void eval_subsets_fz_cached(const CorSlots r, const FzTab tab, int xs
 
 // GS: R lives in global scratch (the unbounded capacity class); otherwise it is a plain shared-memory array, which lets
 // the compiler emit LDS instead of generic loads in the test arithmetic.
-template <int THREADS, int TPT, bool NZ, bool GS, bool CACHE>
+// LISTS = false compiles the whitelist / blacklist / rejection-record handling out (no lists passed: the default call).
+template <int THREADS, int TPT, bool NZ, bool GS, bool CACHE, bool LISTS = true>
 #ifndef FW_HITON_MINB
 #define FW_HITON_MINB 5
 #endif
@@ -428,14 +429,14 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
                     double pj = a.uni_p[e0 + j];
                     if (pj < a.alpha && (pj < pi || (pj == pi && j < i))) ++rank;
                 }
-                order[rank] = i | (hiton_list_flags(a.lists, tsel, a.uni_nbr[e0 + i]) << 28);
+                order[rank] = LISTS ? (i | (hiton_list_flags(a.lists, tsel, a.uni_nbr[e0 + i]) << 28)) : i;
                 atomicAdd(&s_nc, 1);
             }
         }
         __syncthreads();
         const int n_c = s_nc;
         bool overflow = false;
-        const bool track = a.lists.rej_count != nullptr;
+        const bool track = LISTS && a.lists.rej_count != nullptr;
         // rejection record of the candidate just scanned (thread 0; hiton.jl:72-74).  pos -> variable through the accepted list
         auto reject = [&](i64 cand, const AccView& av) {
             const i64 r = o0 + s_nrej;
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
         for (int ci = 0; ci < n_c; ++ci) {
             const int M = s_M;                         // accepted so far; acc[0..M) = slots 1..M (kept by thread 0)
             if (M + 2 > cap) { overflow = true; break; }
-            const int ui = order[ci] & HITON_ORDER_MASK, lf = order[ci] >> 28;
+            const int ui = LISTS ? (order[ci] & HITON_ORDER_MASK) : order[ci], lf = LISTS ? (order[ci] >> 28) : 0;
             if (lf == 2) continue;                     // blacklisted (and not whitelisted): skipped untested (hiton.jl:31-34)
             const i64 cand = a.uni_nbr[e0 + ui];
             const int ys = M + 1;
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
                     }
                 }
             }
-            if (tid == 0 && accept) { member[M] = cand; acc[M] = M + 1; sflag[M + 1] = (unsigned char)lf; s_M = M + 1; }
+            if (tid == 0 && accept) { member[M] = cand; acc[M] = M + 1; if (LISTS) sflag[M + 1] = (unsigned char)lf; s_M = M + 1; }
             __syncthreads();
         }
         if (overflow) {
@@ -516,11 +517,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 128 && !NZ) ? (CACHE ? FW
         if (tid == 0) s_npc = 0;
         __syncthreads();
         for (int c = 1; c <= M; ++c) {
-            const int npc0 = s_npc, npre = s_npre;
+            const int npc0 = s_npc, npre = LISTS ? s_npre : 0;
             const int macc = npre + (M - c) + npc0;
             AccView av; av.n_head = M - c; av.head_base = c + 1; av.tail = pc_slot; av.n_pre = npre; av.pre = wl_slot;
             bool accept = false;                       // thread 0 only
-            if (sflag[c] & 1) {
+            if (LISTS && (sflag[c] & 1)) {
                 // whitelisted: (NaN, NaN), pushed onto `accepted` again while its original entry stays (hiton.jl:20-29, 124-131)
                 __syncthreads();
                 if (tid == 0) { pcs_stat[npc0] = __longlong_as_double(0x7ff8000000000000LL); pcs_p[npc0] = pcs_stat[npc0]; wl_slot[npre] = c; s_npre = npre + 1; accept = true; }
