@@ -6,10 +6,9 @@
 // (128 of the 256 columns), the hardware feeds both SMs from the two halves, so the shared-memory reads per flop halve (A 4 KB +
 // B-half 4 KB per 128 cycles) and the L2 -> SM fill drops from 48 KB to 32 KB per 128 x 128 x 64 block of MMAs.
 //
-// Accuracy scheme as in cor_tc.cuh (z = hi + lo in bf16; hi*hi drained every CHUNK k-blocks because the tensor core truncates when
-// it adds a K = 16 partial product into the fp32 accumulator; the 2^-8 smaller cross terms hi*lo + lo*hi in their own accumulator),
-// but 512 TMEM columns only hold ONE main (256) + ONE cross (256) accumulator: the main accumulator is single-buffered and its drain
-// hides behind the cross-term MMAs of the next k-block, which the issuing thread queues before it waits for the drain.
+// Accuracy scheme: z = hi + lo in bf16 and hi*hi + hi*lo + lo*hi as in cor_tc.cuh; because the tensor core truncates when it adds a
+// K = 16 partial product into the fp32 accumulator, a TMEM accumulator only ever holds the partial sum of CHUNK3 k-blocks, which the
+// epilogue warps drain into fp32 registers.  512 TMEM columns = two 256-column accumulators used alternately (see CHUNK3 below).
 //
 // Roles per CTA (320 threads): warp 0 = TMA producer (own A rows, own half of B; the transaction bytes of BOTH CTAs are counted on the
 // leader's `full` barrier, cp.async.bulk.tensor ... .cta_group::2), warp 1 = TMEM allocation + (leader CTA only) the MMA-issuing
@@ -20,9 +19,20 @@
 
 namespace cortc {
 
+#ifndef FW_COR3_SLEEP_NS
+#define FW_COR3_SLEEP_NS 0
+#endif
 constexpr int NTHREADS3 = 320;
 constexpr int COR_GROUP3 = 8;                              // super-rows (of 256 matrix rows) per rasterisation group
 constexpr int STG_LD = 129;                                // staging row stride in floats (conflict-free both ways)
+
+#ifdef FW_COR3_DEBUG
+// experiment builds only (scripts/cor3_trace.py): per-cluster cycle stamps of the leader CTA, 8 x i64 per cluster
+__device__ long long* g_cor3_dbg = nullptr;
+#define COR3_DBG(slot, val) do { if (g_cor3_dbg) g_cor3_dbg[(size_t)(blockIdx.x >> 1) * 8 + (slot)] = (long long)(val); } while (0)
+#else
+#define COR3_DBG(slot, val) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t mapa_cta(uint32_t addr, uint32_t cta) {
     uint32_t r;
@@ -45,13 +55,16 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 // bounded spin (a protocol bug must trap, not hang the GPU): ~2^27 polls is seconds, far beyond any legitimate wait
+// SLEEP_NS > 0: back off between polls (the epilogue warps and the producer wait for microseconds; the kernel is power-limited and
+// eight warps polling at full issue rate are not free)
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     unsigned int spins = 0;
     do {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (!ok && ++spins > (1u << 27)) __trap();
+        if (!ok) { if (++spins > (1u << 27)) __trap(); if (SLEEP_NS > 0) __nanosleep(SLEEP_NS); }
     } while (!ok);
 }
 __device__ __forceinline__ void mbar_wait_cluster_b(uint32_t bar, uint32_t parity) {
@@ -63,6 +76,63 @@ __device__ __forceinline__ void mbar_wait_cluster_b(uint32_t bar, uint32_t parit
         if (!ok && ++spins > (1u << 27)) __trap();
     } while (!ok);
 }
+
+// raw candidates of one 32-column chunk of the staged tile (emit_chunk of cor_tc.cuh with the values read back from shared memory)
+__device__ __forceinline__ void emit_chunk_stg(const PwEmit& em, const float* stg_row, int c0, unsigned int hitmask, i64 row, i64 col0, int lane) {
+    const unsigned int n_hit = __popc(hitmask);
+    unsigned int incl = n_hit;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (!total) return;                                  // warp-uniform
+    u64 base = 0;
+    if (lane == 31) base = atomicAdd(&em.counters[0], (u64)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    u64 pos = base + incl - n_hit;
+    while (hitmask) {
+        const int j = __ffs(hitmask) - 1; hitmask &= hitmask - 1;
+        if ((i64)pos < em.cap) { PwRec rec; rec.x = (int)row; rec.y = (int)(col0 + c0 + j); rec.r = stg_row[c0 + j]; em.list[pos] = rec; }
+        ++pos;
+    }
+}
+
+// Mirrored tile + raw candidates of one 128 x 128 tile staged in S (row stride STG_LD): warp q writes the matrix rows col0 + q*32 .. +31
+// (= tile columns), 128 consecutive entries each (= the tile rows, read down a column of S: conflict-free with the odd stride).
+// DIAG: diagonal tile, only col >= row is written / tested.  EMIT: collect the raw candidates of the univariate stage for the warp's
+// 128 x 32 block (lane = row within a 32-row group k, bit = column).  Everything row- or column-uniform is hoisted: the loop body is
+// one shared-memory load and one predicated store per element.
+template <bool DIAG, bool EMIT>
+__device__ __forceinline__ void mirror_block(const float* S, float* Cw, i64 p, i64 trow0, i64 col0, int q, int lane, bool do_mirror, const PwEmit& em) {
+    const int nrow = (int)((p - trow0) < 128 ? (p - trow0) : 128), ncol = (int)((p - col0) < 128 ? (p - col0) : 128);
+    unsigned int hm[4] = {0u, 0u, 0u, 0u}, n_nan = 0;
+    float* mp = Cw + (col0 + q * 32) * p + trow0 + lane;
+    const float* sp = S + lane * STG_LD + q * 32;
+    const int cend = ncol - q * 32 < 32 ? ncol - q * 32 : 32;
+    for (int cc = 0; cc < cend; ++cc, mp += p, ++sp) {
+        const int c = q * 32 + cc;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = k * 32 + lane;
+            const float x = sp[k * 32 * STG_LD];
+            const bool ok = r < nrow && (!DIAG || c >= r);
+            if (ok && do_mirror) mp[k * 32] = x;
+            if (EMIT) { if (ok && (!DIAG || c > r)) { if (x != x) ++n_nan; else if (fabsf(x) >= em.r_lo) hm[k] |= 1u << cc; } }
+        }
+    }
+    if (EMIT) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) emit_chunk_stg(em, S + (k * 32 + lane) * STG_LD, q * 32, hm[k], trow0 + k * 32 + lane, col0, lane);
+        n_nan = __reduce_add_sync(0xffffffffu, n_nan);
+        if (lane == 0 && n_nan) atomicAdd(&em.counters[1], (u64)n_nan);
+    }
+}
+
+// Accumulation: all three split terms of a chunk of CHUNK3 k-blocks (256 samples) go to ONE TMEM accumulator, the two accumulators
+// (256 columns each = all 512) alternate by chunk, and the epilogue warps drain the finished one into fp32 registers (round-to-nearest
+// adds) while the MMAs of the next chunk run.  The truncation bias of the tensor core's accumulate is proportional to
+// (#accumulations per chunk) x (magnitude of the partial sum): 48 x |r| 256/n here against 64 x |r| 1024/n of cor_tc2_kernel's
+// main accumulator, i.e. ~5x smaller, which is why the cross terms no longer need an accumulator of their own.
+constexpr int CHUNK3 = 4;
 
 // Tile order.  Tile rows [bi0, bi1) (units of 128 matrix rows) are taken two at a time = one super-row per cluster (CTA r of the pair
 // owns tile row R0 + r); a cluster covers the tile columns (lo + 2j, lo + 2j + 1).  Super-rows are grouped COR_GROUP3 at a time, the
@@ -76,13 +146,16 @@ cor_tc3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - raw);
-    // barriers: full[STAGES], empty[STAGES], cfull, cempty; then the TMEM base-address slot
+    // barriers: full[STAGES], empty[STAGES], cfull[2], cempty[2]; then the TMEM base-address slot
     const uint32_t bar0 = base + STAGES * STAGE_BYTES;
-    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * STAGES, bar_cfull = bar0 + 16 * STAGES, bar_cempty = bar0 + 16 * STAGES + 8;
+    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * STAGES, bar_cfull = bar0 + 16 * STAGES, bar_cempty = bar0 + 16 * STAGES + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t crank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+#ifdef FW_COR3_DEBUG
+    const long long t_entry = clock64();
+#endif
 
     int R0, cp0;                                           // first tile row of the super-row, first tile column of the pair
     {
@@ -101,12 +174,11 @@ cor_tc3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     }
     if (cp0 + 1 < R0 || cp0 >= bjhi || R0 >= bi1) return;  // nothing of this cluster is on or above the diagonal (both CTAs agree)
     const int bi = R0 + (int)crank;                        // this CTA's tile row (A operand, TMEM lanes)
-    const int n_chunks = (num_kb + CHUNK - 1) / CHUNK;
+    const int n_chunks = (num_kb + CHUNK3 - 1) / CHUNK3;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_cfull, 1);
-        mbar_init(bar_cempty, 16);                         // 8 epilogue warps of each CTA arrive on the LEADER's barrier
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_cfull + 8 * b, 1); mbar_init(bar_cempty + 8 * b, 16); }   // 8 epilogue warps of each CTA arrive on the LEADER's cempty
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
@@ -120,7 +192,6 @@ cor_tc3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     cluster_sync_all();                                    // the peer's barriers exist before anything can arrive on them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t t_main = tmem_base, t_cross = tmem_base + 256;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -129,7 +200,7 @@ cor_tc3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (uint32_t)((kb / STAGES) & 1);
-                mbar_wait_b(bar_empty + 8 * s, ph ^ 1u);
+                mbar_wait_b<FW_COR3_SLEEP_NS / 4>(bar_empty + 8 * s, ph ^ 1u);
                 const uint32_t full_leader = mapa_cta(bar_full + 8 * s, 0);
                 if (crank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * STAGE_BYTES);       // both CTAs' four tiles
                 const uint32_t st = base + s * STAGE_BYTES;
@@ -144,34 +215,50 @@ cor_tc3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         if (lane == 0 && crank == 0) {
             // ===== MMA issuer (leader CTA): M = 256 (128 per CTA), N = 256 (128 B rows from each CTA), K = 16 =====
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+#ifdef FW_COR3_DEBUG
+            long long w_full = 0, w_drain = 0, t_first = 0;
+            COR3_DBG(0, t_entry);
+#endif
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (uint32_t)((kb / STAGES) & 1);
-                const int c = kb / CHUNK;
-                const bool first = (kb % CHUNK) == 0;
+                const int c = kb / CHUNK3, b = c & 1, u = c >> 1;
+                const bool first = (kb % CHUNK3) == 0;
+                if (first && c >= 2) {                                            // the epilogue warps of both CTAs have drained chunk c - 2
+#ifdef FW_COR3_DEBUG
+                    const long long td0 = clock64();
+#endif
+                    mbar_wait_cluster_b(bar_cempty + 8 * b, (uint32_t)((u - 1) & 1));
+#ifdef FW_COR3_DEBUG
+                    w_drain += clock64() - td0;
+#endif
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+#ifdef FW_COR3_DEBUG
+                const long long tw0 = clock64();
+#endif
                 mbar_wait_b(bar_full + 8 * s, ph);
+#ifdef FW_COR3_DEBUG
+                if (kb == 0) t_first = clock64(); else w_full += clock64() - tw0;
+#endif
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t t_acc = tmem_base + 256u * (uint32_t)b;
                 const uint32_t st = base + s * STAGE_BYTES;
                 const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + TILE_BYTES);
                 const uint64_t b_hi = make_desc(st + 2 * TILE_BYTES), b_lo = make_desc(st + 3 * TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
-                    umma_bf16_cg2(t_cross, a_hi + adv, b_lo + adv, idesc, (kb == 0 && k == 0) ? 0u : 1u);
-                    umma_bf16_cg2(t_cross, a_lo + adv, b_hi + adv, idesc, 1u);
-                }
-                if (first && c >= 1) {                                            // the epilogue warps of both CTAs have drained chunk c - 1
-                    mbar_wait_cluster_b(bar_cempty, (uint32_t)((c - 1) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-#pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
-                    umma_bf16_cg2(t_main, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                    umma_bf16_cg2(t_acc, a_hi + adv, b_hi + adv, idesc, (first && k == 0) ? 0u : 1u);
+                    umma_bf16_cg2(t_acc, a_hi + adv, b_lo + adv, idesc, 1u);
+                    umma_bf16_cg2(t_acc, a_lo + adv, b_hi + adv, idesc, 1u);
                 }
                 umma_commit_cg2(bar_empty + 8 * s, (uint16_t)3);                  // frees the stage in both CTAs
-                if ((kb % CHUNK) == CHUNK - 1 || kb == num_kb - 1) umma_commit_cg2(bar_cfull, (uint16_t)3);
+                if ((kb % CHUNK3) == CHUNK3 - 1 || kb == num_kb - 1) umma_commit_cg2(bar_cfull + 8 * b, (uint16_t)3);
             }
+#ifdef FW_COR3_DEBUG
+            COR3_DBG(1, t_first); COR3_DBG(2, clock64()); (void)w_full; (void)w_drain;
+#endif
         }
         __syncwarp();
     } else {
@@ -179,72 +266,84 @@ cor_tc3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         const int q = warp & 3, hh = (warp - 2) >> 2;                             // TMEM lane quarter, column half
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t col_base = (uint32_t)(hh * 128);
-        const uint32_t cempty_leader = mapa_cta(bar_cempty, 0);
         float acc[128];
 #pragma unroll
         for (int j = 0; j < 128; ++j) acc[j] = 0.0f;
         for (int c = 0; c < n_chunks; ++c) {
-            mbar_wait_b(bar_cfull, (uint32_t)(c & 1));
+            const int b = c & 1, u = c >> 1;
+            mbar_wait_b<FW_COR3_SLEEP_NS>(bar_cfull + 8 * b, (uint32_t)(u & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int c0 = 0; c0 < 128; c0 += 32) {
                 uint32_t v[32];
-                tmem_ld32(t_main + lane_base + col_base + (uint32_t)c0, v);
+                tmem_ld32(tmem_base + lane_base + 256u * (uint32_t)b + col_base + (uint32_t)c0, v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0 && c + 1 < n_chunks) mbar_arrive_cluster(cempty_leader);
+            if (lane == 0 && c + 2 < n_chunks) mbar_arrive_cluster(mapa_cta(bar_cempty + 8 * b, 0));
         }
-        // the last commit covers every earlier MMA, including the cross accumulator; the pipeline buffers are idle from here on
+        // every MMA has retired: the pipeline buffers are idle from here on and serve as the staging area of the tile
+#ifdef FW_COR3_DEBUG
+        if (warp == 2 && lane == 0 && crank == 0) COR3_DBG(5, clock64());
+#endif
         const int bj = cp0 + hh;                                                  // tile column of this warp's 128 columns
         const bool live = bi < bi1 && bj >= bi && bj < bjhi;
         const bool diag = (bi == bj);
-        const i64 row0 = (i64)bi * BM + q * 32, row = row0 + lane;
-        // row-sharded mode (several GPUs): tile row t is stored at its local position in this rank's shard (common.cuh, CorView)
-        float* Cw = C;
-        if (sh_world > 1) { const int g = bi / sh_h; Cw = C + ((i64)((g < sh_world ? 0 : sh_h) + (bi - g * sh_h)) * 128 - (i64)bi * 128) * p; }
-        float* stg = reinterpret_cast<float*>(gen) + (size_t)(warp - 2) * 32 * STG_LD;
-        unsigned int n_nan = 0;
+        const i64 trow0 = (i64)bi * BM, col0 = (i64)bj * BN;                      // first matrix row / column of the 128 x 128 tile
+        // staged tile of this column half: S[r][c], r = row in the tile (all four lane quarters), c = column in the tile
+        float* S = reinterpret_cast<float*>(gen) + (size_t)hh * 128 * STG_LD;
+        float* stg_row = S + (q * 32 + lane) * STG_LD;
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(t_cross + lane_base + col_base + (uint32_t)c0, v);
-            unsigned int hitmask = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const i64 col = (i64)bj * BN + c0 + j;
-                float x = acc[c0 + j] + __uint_as_float(v[j]);
-                x = x > 1.0f ? 1.0f : (x < -1.0f ? -1.0f : x);        // clampcor (NaN passes through)
-                if (row == col) x = 1.0f;                              // cov2cor!: unit diagonal
-                const bool ok = live && row < p && col < p && (!diag || col >= row);
-                stg[lane * STG_LD + c0 + j] = x;
-                if (ok && (mirror || diag)) Cw[col * p + row] = x;     // mirror (coalesced across the warp: consecutive rows)
-                v[j] = __float_as_uint(x);
-                if (em.on && ok && col > row) { if (x != x) ++n_nan; else if (fabsf(x) >= em.r_lo) hitmask |= 1u << j; }
-            }
-            if (em.on) emit_chunk(em, v, hitmask, row, (i64)bj * BN + c0, lane);
+        for (int j = 0; j < 128; ++j) {
+            float x = acc[j];
+            x = x > 1.0f ? 1.0f : (x < -1.0f ? -1.0f : x);            // clampcor (NaN passes through)
+            stg_row[j] = x;
         }
-        if (em.on) { n_nan = __reduce_add_sync(0xffffffffu, n_nan); if (lane == 0 && n_nan) atomicAdd(&em.counters[1], (u64)n_nan); }
-        __syncwarp();
+        if (diag) stg_row[q * 32 + lane] = 1.0f;                       // cov2cor!: unit diagonal (row == col)
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + hh) : "memory");    // the four warps of this column half
+#ifdef FW_COR3_DEBUG
+        long long t_s1 = clock64(), t_s2 = 0;
+#endif
         if (live) {
-            // direct tile: one 128-byte row segment per store instruction
+            // row-sharded mode (several GPUs): tile row t is stored at its local position in this rank's shard (common.cuh, CorView)
+            float* Cw = C;
+            if (sh_world > 1) { const int g = bi / sh_h; Cw = C + ((i64)((g < sh_world ? 0 : sh_h) + (bi - g * sh_h)) * 128 - (i64)bi * 128) * p; }
+            // mirrored tile (+ raw candidates of the univariate stage), then the direct tile: 32 matrix rows of 512 bytes per warp each
+            const bool do_mirror = (mirror != 0) || diag;
+            if (do_mirror || em.on) {
+                if (diag) { if (em.on) mirror_block<true, true>(S, Cw, p, trow0, col0, q, lane, do_mirror, em); else mirror_block<true, false>(S, Cw, p, trow0, col0, q, lane, do_mirror, em); }
+                else      { if (em.on) mirror_block<false, true>(S, Cw, p, trow0, col0, q, lane, do_mirror, em); else mirror_block<false, false>(S, Cw, p, trow0, col0, q, lane, do_mirror, em); }
+            }
+#ifdef FW_COR3_DEBUG
+            t_s2 = clock64();
+#endif
+            // direct tile: warp q writes the tile rows q*32 .. +31, one 128-byte row segment per store instruction
+            const int ncol = (int)((p - col0) < 128 ? (p - col0) : 128);              // valid columns of this tile
             for (int rr = 0; rr < 32; ++rr) {
-                const i64 r_ = row0 + rr;
+                const i64 r_ = trow0 + q * 32 + rr;
                 if (r_ >= p) break;
-                float* dst = Cw + r_ * p + (i64)bj * BN;
+                float* dst = Cw + r_ * p + col0;
+                const float* src = S + (q * 32 + rr) * STG_LD;
+                const int cmin = diag ? q * 32 + rr : 0;                              // diagonal tile: upper triangle only
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const i64 col = (i64)bj * BN + k * 32 + lane;
-                    if (col < p && (!diag || col >= r_)) dst[k * 32 + lane] = stg[rr * STG_LD + k * 32 + lane];
+                    const int c = k * 32 + lane;
+                    if (c < ncol && c >= cmin) dst[c] = src[c];
                 }
             }
         }
+#ifdef FW_COR3_DEBUG
+        if (warp == 2 && lane == 0 && crank == 0) { COR3_DBG(6, clock64()); COR3_DBG(3, t_s1); COR3_DBG(4, t_s2); }
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     cluster_sync_all();                                    // no CTA leaves while its peer can still arrive on its barriers / read its smem
+#ifdef FW_COR3_DEBUG
+    if (warp == 2 && lane == 0 && crank == 0) COR3_DBG(7, clock64());
+#endif
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
@@ -276,3 +375,9 @@ static cudaError_t launch_tc3(const Prepared& P, float* d_cor, i64 p, int bi0, i
 }
 
 }  // namespace cortc
+
+#ifdef FW_COR3_DEBUG
+extern "C" int fw_debug_cor3_trace(long long* dev_buf) {
+    return (int)cudaMemcpyToSymbol(cortc::g_cor3_dbg, &dev_buf, sizeof(dev_buf));
+}
+#endif
