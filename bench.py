@@ -17,7 +17,8 @@ interleaved.jl hands targets to workers): scaling = "strong".  No collective in 
           fz, N = 1: column chunks of the upload hidden behind the GEMM (fw_upload_cor_f32).  fz, N > 1: the library's group path (include/fwgpu.h "multi-GPU"): every rank uploads 1/N of
           the columns, the standardising kernel reads the peers' slices over NVLink, cor_mat stays row-sharded and is read
           through peer mappings; no NCCL call in the data path (torch.distributed only sets the group up and reduces the
-          timings).  Other kinds, N > 1: table and pairwise stage replicated, targets sharded.
+          timings).  Other kinds, N > 1: table replicated (every rank uploads it over its own PCIe link), pairwise stage split by X with one
+          NCCL all-gather of the raw-significant records for the global BH step, targets sharded.
   parity_sample : the oracle re-runs a sample of the targets on the engine's own inputs and must reproduce the engine's PC sets,
           statistics and test counts; a mismatch fails the run.
 
@@ -349,7 +350,12 @@ def main_ours(a, rank, world, local_rank):
         else:
             eng.set_data_ptr(host_x.data_ptr(), n, p, kind)
         t1 = time.perf_counter()
-        eng.pw_univar_neighbors(alpha=a.alpha, n_obs_min=nom, want_host=False, kind=kind)
+        if dist is not None and kind != "fz":
+            # table-based kinds: every rank holds the table, the X variables of the pairwise stage are dealt to the ranks, one all-gather
+            # of the raw-significant records (NCCL) for the global Benjamini-Hochberg step (fw_pairwise_partial / fw_pairwise_merge)
+            par.sharded_pairwise(dist, eng, kind, alpha=a.alpha, n_obs_min=nom, device=torch.device("cuda", local_rank))
+        else:
+            eng.pw_univar_neighbors(alpha=a.alpha, n_obs_min=nom, want_host=False, kind=kind)
         off = np.zeros(p + 1, np.int64)
         eng._ck(eng.L.fw_pairwise_copy(eng.h, off.ctypes.data_as(fw.C.c_void_p), None, None, None))
         order = np.argsort(np.diff(off), kind="stable").astype(np.int64)      # learning.jl:97-98
@@ -507,7 +513,7 @@ def main_ours(a, rank, world, local_rank):
                 "phases_wall_ms_rank0": {k: float(np.mean(v)) for k, v in phase_wall.items() if v},
                 "pairwise_tests_per_s": p * (p - 1) / 2 / (float(np.mean(phase_wall["pairwise_ms"])) * 1e-3),
                 "multi_gpu_path": ("library group (CUDA IPC peer mappings over NVLink, row-sharded cor_mat, no NCCL in the data path)" if group else
-                                   ("replicated table + pairwise stage, sharded targets" if world > 1 else "single GPU"))},
+                                   ("replicated table, pairwise stage split by X (one NCCL all-gather of the raw-significant records), sharded targets" if world > 1 else "single GPU"))},
         "gpu_launches": int(sm[4].item()),
         "roofline": roofline,
         "clocks": clocks,

@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "fw_hiton_exec_by_k",
     "fw_set_data_f32", "fw_set_data_i32", "fw_adopt_data_f32_device", "fw_set_n_obs", "fw_levels", "fw_cor_matrix",
     "fw_set_cor_f32", "fw_adopt_cor_device", "fw_cor_device_ptr", "fw_adopt_cor_device_rows", "fw_cor_prepare", "fw_cor_rows", "fw_cor_symmetrize", "fw_upload_cor_f32", "fw_test_batch", "fw_test_subsets", "fw_test_subsets_batch",
-    "fw_pairwise", "fw_pairwise_copy", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_ex", "fw_hiton_pc_capacity",
+    "fw_pairwise", "fw_pairwise_copy", "fw_pairwise_partial", "fw_pairwise_partial_copy", "fw_pairwise_merge", "fw_set_univar_nbrs", "fw_pairwise_stats", "fw_hiton_pc", "fw_hiton_pc_ex", "fw_hiton_pc_capacity",
     "fw_normalize_f32", "fw_get_data_f32", "fw_get_data_i32", "fw_set_data_csc_f32", "fw_set_data_csc_i32",
     "fw_host_register", "fw_host_unregister",
     "fw_cor_gather", "fw_pairwise_prefetch", "fw_set_meta_mask", "fw_get_meta_mask", "fw_set_semantics",
@@ -127,6 +127,9 @@ def load_library():
         "fw_set_meta_mask": (i32, [vp, vp, i64]),
         "fw_get_meta_mask": (i32, [vp, vp, i64]),
         "fw_pairwise_prefetch": (i32, [vp, dbl, i64]),
+        "fw_pairwise_partial": (i32, [vp, i32, dbl, i64, i64, i32, i32, i32, vp, vp]),
+        "fw_pairwise_partial_copy": (i32, [vp, vp, vp, vp, vp]),
+        "fw_pairwise_merge": (i32, [vp, i32, dbl, i32, i64, vp, vp, vp, vp, i64, vp]),
         "fw_comm_handle_bytes": (i32, []),
         "fw_comm_export": (i32, [vp, i32, i32, i64, i64, vp]),
         "fw_comm_attach": (i32, [vp, vp]),
@@ -534,6 +537,29 @@ class Engine:
         if not want_host:
             return None
         return self.univar_nbrs()
+
+    def pairwise_partial(self, rank, world, alpha=0.01, hps=5, n_obs_min=0, correct_reliable_only=True, kind=None):
+        """This rank's share of pw_univar_neighbors for the table-based kinds (fw_pairwise_partial): the raw-significant records
+        {"x", "y", "p", "stat"} of the pairs whose X is dealt to `rank`, and the number of its tests that enter the correction."""
+        nr, nrel = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.fw_pairwise_partial(self.h, KINDS[kind or self.kind], alpha, hps, n_obs_min, int(correct_reliable_only), rank, world,
+                                            C.byref(nr), C.byref(nrel)))
+        n = int(nr.value)
+        rec = {"x": np.zeros(n, np.int32), "y": np.zeros(n, np.int32), "p": np.zeros(n), "stat": np.zeros(n), "n_reliable": int(nrel.value)}
+        self._ck(self.L.fw_pairwise_partial_copy(self.h, _p(rec["x"]), _p(rec["y"]), _p(rec["p"]), _p(rec["stat"])))
+        return rec
+
+    def pairwise_merge(self, records, alpha=0.01, FDR=True, correct_reliable_only=True, kind=None, want_host=True):
+        """BH + neighbour lists from the records of ALL ranks (fw_pairwise_merge); `records` = the dicts of pairwise_partial."""
+        x = np.ascontiguousarray(np.concatenate([r["x"] for r in records]), dtype=np.int32)
+        y = np.ascontiguousarray(np.concatenate([r["y"] for r in records]), dtype=np.int32)
+        pv = np.ascontiguousarray(np.concatenate([r["p"] for r in records]), dtype=np.float64)
+        st = np.ascontiguousarray(np.concatenate([r["stat"] for r in records]), dtype=np.float64)
+        m = sum(int(r["n_reliable"]) for r in records) if correct_reliable_only else self.p * (self.p - 1) // 2
+        ne = C.c_int64(0)
+        self._ck(self.L.fw_pairwise_merge(self.h, KINDS[kind or self.kind], alpha, int(FDR), len(x), _p(x), _p(y), _p(pv), _p(st), m, C.byref(ne)))
+        self.uni_entries = int(ne.value)
+        return self.univar_nbrs() if want_host else None
 
     def univar_nbrs(self):
         ne = self.uni_entries

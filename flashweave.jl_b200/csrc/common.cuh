@@ -49,6 +49,16 @@ struct CorView {
     __host__ __device__ __forceinline__ i64 local_row_of_tile_row(int tr) const { const int g = tr / h; return (i64)((g < world ? 0 : h) + (tr - g * h)) * 128; }
 };
 
+// ---- pairwise stage of the table-based kinds (mi, mi_nz, fz_nz) split over the GPUs of a group ------------------------------------
+// The X variables (first member of a pair X < Y) are dealt in groups of PW_X_GROUP = 1024 (8 tile rows of the tensor-core pre-filter)
+// in a snake 0..N-1, N-1..0: row X has p - X - 1 partners, so pairing an early with a late group balances the ranks.
+constexpr int PW_X_GROUP = 1024;
+__host__ __device__ __forceinline__ bool pw_owns_group(i64 g, int rank, int world) {
+    if (world <= 1) return true;
+    const int c = (int)(g % (2 * world));
+    return (c < world ? c : 2 * world - 1 - c) == rank;
+}
+
 // ---- raw candidates of the univariate Fisher-z stage ---------------------------------------------------------------------------
 // A pair whose |r| reaches the (conservatively lowered) significance threshold, as the cor_mat GEMM epilogue (cor_tc.cuh) or the
 // one-pass scan of the resident matrix (pairwise.cuh) appends it: unordered, 12 bytes.  counters[0] = records appended (it keeps

@@ -87,6 +87,7 @@ struct fw_ctx {
     DevBuf<i64> d_uni_off, d_uni_nbr; DevBuf<double> d_uni_stat, d_uni_p;
     std::vector<i64> h_uni_off; i64 uni_entries = -1;
     i64 pw_tests = 0, pw_reliable = 0, pw_raw_sig = 0;
+    PwCollected part; int part_kind = -1;   // fw_pairwise_partial: this rank's raw-significant records (device, scratch slots 7-10)
     i64 exec_by_k[3] = {0, 0, 0};     // tests executed by the last fw_hiton_pc with |Zs| = 1, 2, 3
 
     // per-phase device timing (CUDA events on `stream`), see fw_last_timing
@@ -1261,6 +1262,22 @@ int32_t fw_test_subsets(fw_ctx* ctx, int32_t kind, int64_t X, int64_t Y, const i
 }
 
 // ---- pairwise stage -------------------------------------------------------------------------
+// the resident neighbour lists <- the CSR a pairwise stage produced (device copies + host offsets)
+static int adopt_pairwise(fw_ctx* ctx, const PairwiseOut& po, i64 p) {
+    CK(ctx->d_uni_off.reserve(p + 1)); CK(ctx->d_uni_nbr.reserve(po.n_entries)); CK(ctx->d_uni_stat.reserve(po.n_entries)); CK(ctx->d_uni_p.reserve(po.n_entries));
+    CK(cudaMemcpyAsync(ctx->d_uni_off.ptr, po.d_off, sizeof(i64) * (p + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (po.n_entries) {
+        CK(cudaMemcpyAsync(ctx->d_uni_nbr.ptr, po.d_nbr, sizeof(i64) * po.n_entries, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_uni_stat.ptr, po.d_stat, sizeof(double) * po.n_entries, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_uni_p.ptr, po.d_adjp, sizeof(double) * po.n_entries, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    ctx->h_uni_off.resize(p + 1);
+    CK(cudaMemcpyAsync(ctx->h_uni_off.data(), po.d_off, sizeof(i64) * (p + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->uni_entries = po.n_entries; ctx->pw_tests = po.n_tests; ctx->pw_reliable = po.n_reliable; ctx->pw_raw_sig = po.n_raw_sig;
+    return FW_OK;
+}
+
 int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_t n_obs_min,
                     int32_t fdr, int32_t correct_reliable_only, int64_t* n_entries) {
     if (!ctx) return FW_ERR_INVALID;
@@ -1295,18 +1312,81 @@ int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_
     if (e != cudaSuccess && msg.find("unsupported size") != std::string::npos) return fail(ctx, FW_ERR_UNSUPPORTED, "fw_pairwise: %s", msg.c_str());
     if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_pairwise: %s: %s", msg.c_str(), cudaGetErrorString(e));
     CK(cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->ev_valid[1] = true;
-    // adopt the CSR
-    CK(ctx->d_uni_off.reserve(p + 1)); CK(ctx->d_uni_nbr.reserve(po.n_entries)); CK(ctx->d_uni_stat.reserve(po.n_entries)); CK(ctx->d_uni_p.reserve(po.n_entries));
-    CK(cudaMemcpyAsync(ctx->d_uni_off.ptr, po.d_off, sizeof(i64) * (p + 1), cudaMemcpyDeviceToDevice, ctx->stream));
-    if (po.n_entries) {
-        CK(cudaMemcpyAsync(ctx->d_uni_nbr.ptr, po.d_nbr, sizeof(i64) * po.n_entries, cudaMemcpyDeviceToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_uni_stat.ptr, po.d_stat, sizeof(double) * po.n_entries, cudaMemcpyDeviceToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_uni_p.ptr, po.d_adjp, sizeof(double) * po.n_entries, cudaMemcpyDeviceToDevice, ctx->stream));
+    { int st_ = adopt_pairwise(ctx, po, p); if (st_ != FW_OK) return st_; }
+    if (n_entries) *n_entries = po.n_entries;
+    return FW_OK;
+}
+
+// ---- pairwise stage of the table-based kinds split over the ranks of a job (include/fwgpu.h "multi-GPU, table-based kinds") -------
+int32_t fw_pairwise_partial(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_t n_obs_min, int32_t correct_reliable_only,
+                            int32_t rank, int32_t world, int64_t* n_raw, int64_t* n_reliable) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(kind == FW_MI || kind == FW_MI_NZ || kind == FW_FZ_NZ, FW_ERR_UNSUPPORTED, "fw_pairwise_partial: kind %d (FW_FZ shares the work through the group path, fw_multi_cor + fw_pairwise)", kind);
+    NEED(world >= 1 && world <= FW_MAX_RANKS && rank >= 0 && rank < world, FW_ERR_INVALID, "fw_pairwise_partial: rank %d of %d", rank, world);
+    const bool disc = kind != FW_FZ_NZ;
+    NzTable nzt;
+    if (!disc) { int st_ = ensure_nz_table(ctx, &nzt); if (st_ != FW_OK) return st_; }
+    else NEED(ctx->data_kind == 1, FW_ERR_STATE, "fw_pairwise_partial: no discrete table resident (fw_set_data_i32)");
+    CK(cudaSetDevice(ctx->device));
+    std::string msg; int nl = 0;
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    cudaError_t e;
+    ctx->part = PwCollected(); ctx->part_kind = -1;
+    if (disc) { MiTable t = make_mi_table(ctx, kind); e = pairwise_mi_collect(ctx->pw, t, hps, n_obs_min, alpha, correct_reliable_only != 0, rank, world, ctx->stream, &ctx->part, &nl, &msg); }
+    else e = pairwise_fznz_collect(ctx->pw, ctx->nzplanes, nzt, n_obs_min, alpha, correct_reliable_only != 0, rank, world, ctx->stream, &ctx->part, &nl, &msg);
+    ctx->launches += nl;
+    if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_pairwise_partial: %s: %s", msg.c_str(), cudaGetErrorString(e));
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->ev_valid[1] = true;
+    ctx->part_kind = kind;
+    if (n_raw) *n_raw = ctx->part.nf;
+    if (n_reliable) *n_reliable = ctx->part.n_rel;
+    return FW_OK;
+}
+
+int32_t fw_pairwise_partial_copy(fw_ctx* ctx, int32_t* x, int32_t* y, double* pval, double* stat) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(ctx->part_kind >= 0, FW_ERR_STATE, "fw_pairwise_partial_copy: no partial pairwise result (fw_pairwise_partial)");
+    NEED(ctx->part.nf == 0 || (x && y && pval && stat), FW_ERR_INVALID, "fw_pairwise_partial_copy: NULL output");
+    CK(cudaSetDevice(ctx->device));
+    const i64 nf = ctx->part.nf;
+    if (nf) {
+        CK(cudaMemcpyAsync(x, ctx->part.c_x, sizeof(int) * nf, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(y, ctx->part.c_y, sizeof(int) * nf, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(pval, ctx->part.c_p, sizeof(double) * nf, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(stat, ctx->part.c_stat, sizeof(double) * nf, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
     }
-    ctx->h_uni_off.resize(p + 1);
-    CK(cudaMemcpyAsync(ctx->h_uni_off.data(), po.d_off, sizeof(i64) * (p + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->uni_entries = po.n_entries; ctx->pw_tests = po.n_tests; ctx->pw_reliable = po.n_reliable; ctx->pw_raw_sig = po.n_raw_sig;
+    return FW_OK;
+}
+
+int32_t fw_pairwise_merge(fw_ctx* ctx, int32_t kind, double alpha, int32_t fdr, int64_t n_raw_total, const int32_t* x, const int32_t* y,
+                          const double* pval, const double* stat, int64_t m_tests, int64_t* n_entries) {
+    if (!ctx) return FW_ERR_INVALID;
+    NEED(kind == FW_MI || kind == FW_MI_NZ || kind == FW_FZ_NZ, FW_ERR_UNSUPPORTED, "fw_pairwise_merge: kind %d", kind);
+    NEED(ctx->data_kind != 0 && ctx->p > 0, FW_ERR_STATE, "fw_pairwise_merge: no table resident");
+    NEED(n_raw_total >= 0 && (n_raw_total == 0 || (x && y && pval && stat)), FW_ERR_INVALID, "fw_pairwise_merge: NULL records");
+    NEED(n_raw_total < ((i64)1 << 31) - 1, FW_ERR_UNSUPPORTED, "fw_pairwise_merge: more than 2^31 raw-significant pairs");
+    CK(cudaSetDevice(ctx->device));
+    const i64 p = ctx->p, nf = n_raw_total;
+    for (i64 i = 0; i < nf; ++i) NEED(x[i] >= 0 && x[i] < y[i] && y[i] < p, FW_ERR_INVALID, "fw_pairwise_merge: record %lld is not a pair x < y < p", (long long)i);
+    int *d_x, *d_y; double *d_p, *d_s;
+    const i64 cap = std::max<i64>(nf, 16);
+    CK(ctx->pw.get(7, sizeof(int) * cap, (void**)&d_x)); CK(ctx->pw.get(8, sizeof(int) * cap, (void**)&d_y));
+    CK(ctx->pw.get(9, sizeof(double) * cap, (void**)&d_p)); CK(ctx->pw.get(10, sizeof(double) * cap, (void**)&d_s));
+    ctx->part = PwCollected(); ctx->part_kind = -1;                   // the slots of the partial result are overwritten
+    if (nf) {
+        CK(cudaMemcpyAsync(d_x, x, sizeof(int) * nf, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_y, y, sizeof(int) * nf, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_p, pval, sizeof(double) * nf, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_s, stat, sizeof(double) * nf, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PairwiseOut po; std::string msg; int nl = 0;
+    po.n_tests = p * (p - 1) / 2; po.n_raw_sig = nf; po.n_reliable = m_tests;
+    cudaError_t e = pairwise_order_finish(ctx->pw, d_x, d_y, d_p, d_s, nf, m_tests, p, alpha, fdr != 0, ctx->stream, &po, &nl, &msg);
+    ctx->launches += nl;
+    if (e != cudaSuccess && msg.find("unsupported size") != std::string::npos) return fail(ctx, FW_ERR_UNSUPPORTED, "fw_pairwise_merge: %s", msg.c_str());
+    if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "fw_pairwise_merge: %s: %s", msg.c_str(), cudaGetErrorString(e));
+    { int st_ = adopt_pairwise(ctx, po, p); if (st_ != FW_OK) return st_; }
     if (n_entries) *n_entries = po.n_entries;
     return FW_OK;
 }

@@ -341,9 +341,10 @@ __device__ int fznz_subcor_block(const NzTable& t, const i64* var, int nv, int x
 // ---- pairwise stage: one warp per pair, unordered emission (tests.jl:410-433, :391-407) -----------------------
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) pw_fznz_rows_kernel(NzTable t, i64 n_obs_min, double alpha, int reliable_only,
-                                                                  u64* counters, i64 cap, int* c_x, int* c_y, double* c_p, double* c_stat) {
+                                                                  u64* counters, i64 cap, int* c_x, int* c_y, double* c_p, double* c_stat, int sh_rank, int sh_world) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const i64 X = blockIdx.x;
+    if (!pw_owns_group(X / PW_X_GROUP, sh_rank, sh_world)) return;
     i64 n_rel = 0;
     for (i64 Y = X + 1 + warp; Y < t.p; Y += WARPS) {
         NzUni r = fznz_uni_warp(t, X, Y, n_obs_min);

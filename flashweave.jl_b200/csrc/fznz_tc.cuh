@@ -99,6 +99,7 @@ struct PrefilterArgs {
     float trunc_rel;                            // T: bound of the accumulated truncation of the fp32 TMEM accumulators, relative to sum |terms|
     u64* counters;                              // [0] candidates appended, [1] pairs counted reliable here (non-candidates)
     i64 cand_cap; int* cand_x; int* cand_y;
+    int sh_rank, sh_world;                      // X groups of this rank (pw_owns_group, common.cuh)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) fznz_prefilter_kernel(const __grid_constant__ CUtensorMap tm_m, const __grid_constant__ CUtensorMap tm_x,
@@ -122,8 +123,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fznz_prefilter_kernel(const __gri
         int r0 = 0, rows = 1;
         for (;; r0 += TC_GROUP) {
             rows = a.nb_a - r0 < TC_GROUP ? a.nb_a - r0 : TC_GROUP;
-            const long long cnt = (long long)(a.nb_b - 2 * r0) * rows;
-            if (q < cnt || r0 + TC_GROUP >= a.nb_a) break;
+            const long long cnt = pw_owns_group(r0 / TC_GROUP, a.sh_rank, a.sh_world) ? (long long)(a.nb_b - 2 * r0) * rows : 0;
+            if (q < cnt) break;
+            if (r0 + TC_GROUP >= a.nb_a) return;
             q -= cnt;
         }
         I = r0 + (int)(q % rows);
@@ -323,7 +325,8 @@ static double z_of_alpha(double alpha) {
 
 // planes + pre-filter launch; on return counters[0] = #candidates (possibly > cand_cap: caller re-runs), counters[1] = #reliable counted
 static cudaError_t run_prefilter(Planes& P, const NzTable& t, i64 n_obs_min, double alpha, bool reliable_only, u64* counters,
-                                 i64 cand_cap, int* cand_x, int* cand_y, bool planes_ready, cudaStream_t st, int* n_launch, std::string* msg) {
+                                 i64 cand_cap, int* cand_x, int* cand_y, bool planes_ready, cudaStream_t st, int* n_launch, std::string* msg,
+                                 int sh_rank = 0, int sh_world = 1) {
     const i64 p = t.p, n = t.n;
     const i64 kp = (n + BK - 1) / BK * BK;
     const i64 p_pad = (p + BM - 1) / BM * BM;
@@ -347,8 +350,12 @@ static cudaError_t run_prefilter(Planes& P, const NzTable& t, i64 n_obs_min, dou
     a.z_alpha = (float)(z_of_alpha(alpha) * (1.0 - 1e-6));
     a.trunc_rel = (float)(2.0 * (double)(kp / 16) / 8388608.0);       // one truncation (< 2^-23 relative) per K = 16 accumulation, x2 margin
     a.counters = counters; a.cand_cap = cand_cap; a.cand_x = cand_x; a.cand_y = cand_y;
+    a.sh_rank = sh_rank; a.sh_world = sh_world;
+    static_assert(TC_GROUP * BM == PW_X_GROUP, "the X groups of the sharded pairwise stage are the rasterisation groups of the pre-filter");
     long long tiles = 0;
-    for (int r0 = 0; r0 < a.nb_a; r0 += TC_GROUP) tiles += (long long)(a.nb_b - 2 * r0) * std::min(TC_GROUP, a.nb_a - r0);
+    for (int r0 = 0; r0 < a.nb_a; r0 += TC_GROUP)
+        if (pw_owns_group(r0 / TC_GROUP, sh_rank, sh_world)) tiles += (long long)(a.nb_b - 2 * r0) * std::min(TC_GROUP, a.nb_a - r0);
+    if (tiles == 0) return cudaSuccess;
     fznz_prefilter_kernel<<<(unsigned)tiles, NTHREADS, SMEM_BYTES, st>>>(tm_m, tm_x, tm_x2, a);
     (*n_launch)++;
     e = cudaGetLastError(); if (e != cudaSuccess) { *msg = "fznz_prefilter_kernel"; return e; }

@@ -461,11 +461,12 @@ __device__ MiResult mi_pair_bin_thread(int n, int nx, int ny, int nxy, i64 hps, 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) pw_mi_rows_kernel(MiTable t, i64 hps, i64 n_obs_min, double alpha, int reliable_only,
                                                                 u64* counters /* [0] emitted, [1] reliable */, i64 cap,
-                                                                int* c_x, int* c_y, double* c_p, double* c_stat) {
+                                                                int* c_x, int* c_y, double* c_p, double* c_stat, int sh_rank, int sh_world) {
     extern __shared__ int smem_tab[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* tab = smem_tab + warp * (t.L * t.L);
     const i64 X = blockIdx.x;
+    if (!pw_owns_group(X / PW_X_GROUP, sh_rank, sh_world)) return;
     i64 n_rel = 0;
     if (t.L == 2 && !t.nz && t.levels[X] == 2) {
         // binary table: one LANE per pair.  N(X=1,Y=1) = popc(X & Y) over the words is the only count that is not a per-variable
@@ -524,24 +525,27 @@ __global__ void __launch_bounds__(WARPS * 32) pw_mi_rows_kernel(MiTable t, i64 h
     if (lane == 0 && n_rel) atomicAdd(&counters[1], (u64)n_rel);
 }
 
-// pw_univar_neighbors for mi / mi_nz (tests.jl:436-532): all pairs -> raw-significant list -> condensed order -> BH + CSR
-static cudaError_t pairwise_mi_run(PairwiseScratch& S, const MiTable& t, i64 hps, i64 n_obs_min, double alpha, bool fdr, bool reliable_only,
-                                   cudaStream_t st, PairwiseOut* out, int* n_launch, std::string* msg) {
-    const int T = 256, WARPS = 8;
+// ---- pw_univar_neighbors for the table-based kinds (tests.jl:436-532) in two halves ------------------------------------------------
+//   collect:      all pairs (X, Y > X) with X in this rank's X groups -> unordered raw-significant records + the number of reliable tests
+//   order_finish: records (of ALL ranks) -> condensed-index order (x, then y ascending) -> BH with the global m -> neighbour CSR
+// One GPU: both halves back to back (pairwise_*_run).  Several GPUs: fw_pairwise_partial / host all-gather / fw_pairwise_merge.
+struct PwCollected { int* c_x = nullptr; int* c_y = nullptr; double* c_p = nullptr; double* c_stat = nullptr; i64 nf = 0, n_rel = 0; };
+
+static cudaError_t pairwise_mi_collect(PairwiseScratch& S, const MiTable& t, i64 hps, i64 n_obs_min, double alpha, bool reliable_only, int sh_rank, int sh_world,
+                                       cudaStream_t st, PwCollected* pc, int* n_launch, std::string* msg) {
+    const int WARPS = 8;
     const i64 p = t.p, n_pairs = p * (p - 1) / 2;
-    out->n_tests = n_pairs;
     u64* counters; PWCK(S.get(0, sizeof(u64) * 4, (void**)&counters), "alloc");
     i64 cap = std::max<i64>((i64)1 << 16, std::min<i64>(n_pairs, n_pairs / 8 + 1024));
-    int *c_x, *c_y; double *c_p, *c_stat;
     u64 h_cnt[2] = {0, 0};
     for (int attempt = 0; attempt < 2; ++attempt) {
-        PWCK(S.get(7, sizeof(int) * cap, (void**)&c_x), "alloc");
-        PWCK(S.get(8, sizeof(int) * cap, (void**)&c_y), "alloc");
-        PWCK(S.get(9, sizeof(double) * cap, (void**)&c_p), "alloc");
-        PWCK(S.get(10, sizeof(double) * cap, (void**)&c_stat), "alloc");
+        PWCK(S.get(7, sizeof(int) * cap, (void**)&pc->c_x), "alloc");
+        PWCK(S.get(8, sizeof(int) * cap, (void**)&pc->c_y), "alloc");
+        PWCK(S.get(9, sizeof(double) * cap, (void**)&pc->c_p), "alloc");
+        PWCK(S.get(10, sizeof(double) * cap, (void**)&pc->c_stat), "alloc");
         PWCK(cudaMemsetAsync(counters, 0, sizeof(u64) * 4, st), "memset");
         pw_mi_rows_kernel<WARPS><<<(unsigned)p, WARPS * 32, WARPS * t.L * t.L * sizeof(int), st>>>(t, hps, n_obs_min, alpha, reliable_only ? 1 : 0, counters, cap,
-                                                                                             c_x, c_y, c_p, c_stat);
+                                                                                             pc->c_x, pc->c_y, pc->c_p, pc->c_stat, sh_rank, sh_world);
         (*n_launch)++;
         PWCK(cudaGetLastError(), "pw_mi_rows_kernel");
         PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 2, cudaMemcpyDeviceToHost, st), "d2h");
@@ -549,10 +553,76 @@ static cudaError_t pairwise_mi_run(PairwiseScratch& S, const MiTable& t, i64 hps
         if ((i64)h_cnt[0] <= cap) break;
         cap = (i64)h_cnt[0];
     }
-    const i64 nf = (i64)h_cnt[0];
-    out->n_raw_sig = nf;
-    out->n_reliable = reliable_only ? (i64)h_cnt[1] : n_pairs;
-    const i64 m = reliable_only ? (i64)h_cnt[1] : n_pairs;             // tests.jl:521-526
+    pc->nf = (i64)h_cnt[0]; pc->n_rel = (i64)h_cnt[1];
+    return cudaSuccess;
+}
+
+// fz_nz: per-pair correlations on the co-non-zero rows.  Default: tensor-core pre-filter (fznz_tc.cuh) + exact fp64 test of the
+// candidate pairs; FWGPU_FZNZ_TC=0 runs the exact test on every pair instead - same neighbour lists, used by the tests to check the pre-filter.
+static bool fznz_use_tc() {
+    const char* e = getenv("FWGPU_FZNZ_TC");       // read on every call: the tests switch between the two paths
+    return e ? atoi(e) != 0 : true;
+}
+static cudaError_t pairwise_fznz_collect(PairwiseScratch& S, fznztc::Planes& planes, const NzTable& t, i64 n_obs_min, double alpha, bool reliable_only,
+                                         int sh_rank, int sh_world, cudaStream_t st, PwCollected* pc, int* n_launch, std::string* msg) {
+    const int WARPS = 8;
+    const i64 p = t.p, n_pairs = p * (p - 1) / 2;
+    u64* counters; PWCK(S.get(0, sizeof(u64) * 4, (void**)&counters), "alloc");
+    u64 h_cnt[3] = {0, 0, 0};
+    if (fznz_use_tc() && t.n >= 64 && p >= 2) {
+        i64 ccap = std::max<i64>((i64)1 << 16, std::min<i64>(n_pairs, n_pairs / 16 + 1024));
+        int *k_x, *k_y;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            PWCK(S.get(16, sizeof(int) * ccap, (void**)&k_x), "alloc");
+            PWCK(S.get(17, sizeof(int) * ccap, (void**)&k_y), "alloc");
+            PWCK(cudaMemsetAsync(counters, 0, sizeof(u64) * 4, st), "memset");
+            { cudaError_t e_ = fznztc::run_prefilter(planes, t, n_obs_min, alpha, reliable_only, counters, ccap, k_x, k_y, attempt > 0, st, n_launch, msg, sh_rank, sh_world); if (e_ != cudaSuccess) return e_; }
+            PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 3, cudaMemcpyDeviceToHost, st), "d2h");
+            PWCK(cudaStreamSynchronize(st), "sync (fznz_prefilter_kernel)");
+            if ((i64)h_cnt[0] <= ccap) break;
+            ccap = (i64)h_cnt[0];
+        }
+        const i64 n_cand = (i64)h_cnt[0];
+        const i64 cap = std::max<i64>(n_cand, 16);
+        PWCK(S.get(7, sizeof(int) * cap, (void**)&pc->c_x), "alloc");
+        PWCK(S.get(8, sizeof(int) * cap, (void**)&pc->c_y), "alloc");
+        PWCK(S.get(9, sizeof(double) * cap, (void**)&pc->c_p), "alloc");
+        PWCK(S.get(10, sizeof(double) * cap, (void**)&pc->c_stat), "alloc");
+        if (n_cand > 0) {
+            const i64 blocks = std::min<i64>((n_cand + WARPS - 1) / WARPS, (i64)148 * 32);
+            fznztc::fznz_candidates_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, 0, st>>>(t, n_cand, k_x, k_y, n_obs_min, alpha, reliable_only ? 1 : 0,
+                                                                                       counters, cap, pc->c_x, pc->c_y, pc->c_p, pc->c_stat);
+            (*n_launch)++;
+            PWCK(cudaGetLastError(), "fznz_candidates_kernel");
+        }
+        PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 3, cudaMemcpyDeviceToHost, st), "d2h");
+        PWCK(cudaStreamSynchronize(st), "sync (fznz_candidates_kernel)");
+        h_cnt[0] = h_cnt[2];                                             // raw-significant pairs
+    } else {
+        i64 cap = std::max<i64>((i64)1 << 16, std::min<i64>(n_pairs, n_pairs / 8 + 1024));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            PWCK(S.get(7, sizeof(int) * cap, (void**)&pc->c_x), "alloc");
+            PWCK(S.get(8, sizeof(int) * cap, (void**)&pc->c_y), "alloc");
+            PWCK(S.get(9, sizeof(double) * cap, (void**)&pc->c_p), "alloc");
+            PWCK(S.get(10, sizeof(double) * cap, (void**)&pc->c_stat), "alloc");
+            PWCK(cudaMemsetAsync(counters, 0, sizeof(u64) * 4, st), "memset");
+            pw_fznz_rows_kernel<WARPS><<<(unsigned)p, WARPS * 32, 0, st>>>(t, n_obs_min, alpha, reliable_only ? 1 : 0, counters, cap, pc->c_x, pc->c_y, pc->c_p, pc->c_stat, sh_rank, sh_world);
+            (*n_launch)++;
+            PWCK(cudaGetLastError(), "pw_fznz_rows_kernel");
+            PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 2, cudaMemcpyDeviceToHost, st), "d2h");
+            PWCK(cudaStreamSynchronize(st), "sync");
+            if ((i64)h_cnt[0] <= cap) break;
+            cap = (i64)h_cnt[0];
+        }
+    }
+    pc->nf = (i64)h_cnt[0]; pc->n_rel = (i64)h_cnt[1];
+    return cudaSuccess;
+}
+
+// records in any order -> condensed-index order (sort by x*p + y, gather) -> BH (m tests) + neighbour CSR
+static cudaError_t pairwise_order_finish(PairwiseScratch& S, const int* c_x, const int* c_y, const double* c_p, const double* c_stat, i64 nf, i64 m, i64 p,
+                                         double alpha, bool fdr, cudaStream_t st, PairwiseOut* out, int* n_launch, std::string* msg) {
+    const int T = 256;
     i64* d_off; PWCK(S.get(6, sizeof(i64) * (p + 1), (void**)&d_off), "alloc");
     out->d_off = d_off;
     if (nf == 0) {
@@ -560,7 +630,6 @@ static cudaError_t pairwise_mi_run(PairwiseScratch& S, const MiTable& t, i64 hps
         out->n_entries = 0; out->d_nbr = nullptr; out->d_stat = nullptr; out->d_adjp = nullptr;
         return cudaSuccess;
     }
-    // restore condensed-index order (x, then y ascending): sort by x*p + y, gather
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     unsigned char* arena; PWCK(S.get(11, 2 * al(sizeof(u64) * nf) + 2 * al(sizeof(unsigned int) * nf), (void**)&arena), "alloc");
     u64* keys = (u64*)arena; u64* keys2 = (u64*)(arena + al(sizeof(u64) * nf));
@@ -581,94 +650,26 @@ static cudaError_t pairwise_mi_run(PairwiseScratch& S, const MiTable& t, i64 hps
     return pairwise_finish(S, o_x, o_y, o_p, o_s, nf, m, p, alpha, fdr, st, out, n_launch, msg);
 }
 
-// pw_univar_neighbors for fz_nz (tests.jl:436-532): per-pair correlations on the co-non-zero rows.
-// Default: tensor-core pre-filter (fznz_tc.cuh) + exact fp64 test of the candidate pairs; FWGPU_FZNZ_TC=0 (or use_tc = false)
-// runs the exact test on every pair instead - same neighbour lists, used by the tests to check the pre-filter.
-static bool fznz_use_tc() {
-    const char* e = getenv("FWGPU_FZNZ_TC");       // read on every call: the tests switch between the two paths
-    return e ? atoi(e) != 0 : true;
+static cudaError_t pairwise_mi_run(PairwiseScratch& S, const MiTable& t, i64 hps, i64 n_obs_min, double alpha, bool fdr, bool reliable_only,
+                                   cudaStream_t st, PairwiseOut* out, int* n_launch, std::string* msg) {
+    const i64 p = t.p, n_pairs = p * (p - 1) / 2;
+    PwCollected pc;
+    cudaError_t e = pairwise_mi_collect(S, t, hps, n_obs_min, alpha, reliable_only, 0, 1, st, &pc, n_launch, msg);
+    if (e != cudaSuccess) return e;
+    out->n_tests = n_pairs; out->n_raw_sig = pc.nf;
+    out->n_reliable = reliable_only ? pc.n_rel : n_pairs;
+    const i64 m = reliable_only ? pc.n_rel : n_pairs;             // tests.jl:521-526
+    return pairwise_order_finish(S, pc.c_x, pc.c_y, pc.c_p, pc.c_stat, pc.nf, m, p, alpha, fdr, st, out, n_launch, msg);
 }
+
 static cudaError_t pairwise_fznz_run(PairwiseScratch& S, fznztc::Planes& planes, const NzTable& t, i64 n_obs_min, double alpha, bool fdr, bool reliable_only,
                                      cudaStream_t st, PairwiseOut* out, int* n_launch, std::string* msg) {
-    const int T = 256, WARPS = 8;
     const i64 p = t.p, n_pairs = p * (p - 1) / 2;
-    out->n_tests = n_pairs;
-    u64* counters; PWCK(S.get(0, sizeof(u64) * 4, (void**)&counters), "alloc");
-    int *c_x, *c_y; double *c_p, *c_stat;
-    u64 h_cnt[3] = {0, 0, 0};
-    if (fznz_use_tc() && t.n >= 64 && p >= 2) {
-        i64 ccap = std::max<i64>((i64)1 << 16, std::min<i64>(n_pairs, n_pairs / 16 + 1024));
-        int *k_x, *k_y;
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            PWCK(S.get(16, sizeof(int) * ccap, (void**)&k_x), "alloc");
-            PWCK(S.get(17, sizeof(int) * ccap, (void**)&k_y), "alloc");
-            PWCK(cudaMemsetAsync(counters, 0, sizeof(u64) * 4, st), "memset");
-            { cudaError_t e_ = fznztc::run_prefilter(planes, t, n_obs_min, alpha, reliable_only, counters, ccap, k_x, k_y, attempt > 0, st, n_launch, msg); if (e_ != cudaSuccess) return e_; }
-            PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 3, cudaMemcpyDeviceToHost, st), "d2h");
-            PWCK(cudaStreamSynchronize(st), "sync (fznz_prefilter_kernel)");
-            if ((i64)h_cnt[0] <= ccap) break;
-            ccap = (i64)h_cnt[0];
-        }
-        const i64 n_cand = (i64)h_cnt[0];
-        const i64 cap = std::max<i64>(n_cand, 16);
-        PWCK(S.get(7, sizeof(int) * cap, (void**)&c_x), "alloc");
-        PWCK(S.get(8, sizeof(int) * cap, (void**)&c_y), "alloc");
-        PWCK(S.get(9, sizeof(double) * cap, (void**)&c_p), "alloc");
-        PWCK(S.get(10, sizeof(double) * cap, (void**)&c_stat), "alloc");
-        if (n_cand > 0) {
-            const i64 blocks = std::min<i64>((n_cand + WARPS - 1) / WARPS, (i64)148 * 32);
-            fznztc::fznz_candidates_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, 0, st>>>(t, n_cand, k_x, k_y, n_obs_min, alpha, reliable_only ? 1 : 0,
-                                                                                       counters, cap, c_x, c_y, c_p, c_stat);
-            (*n_launch)++;
-            PWCK(cudaGetLastError(), "fznz_candidates_kernel");
-        }
-        PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 3, cudaMemcpyDeviceToHost, st), "d2h");
-        PWCK(cudaStreamSynchronize(st), "sync (fznz_candidates_kernel)");
-        h_cnt[0] = h_cnt[2];                                             // raw-significant pairs
-    } else {
-        i64 cap = std::max<i64>((i64)1 << 16, std::min<i64>(n_pairs, n_pairs / 8 + 1024));
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            PWCK(S.get(7, sizeof(int) * cap, (void**)&c_x), "alloc");
-            PWCK(S.get(8, sizeof(int) * cap, (void**)&c_y), "alloc");
-            PWCK(S.get(9, sizeof(double) * cap, (void**)&c_p), "alloc");
-            PWCK(S.get(10, sizeof(double) * cap, (void**)&c_stat), "alloc");
-            PWCK(cudaMemsetAsync(counters, 0, sizeof(u64) * 4, st), "memset");
-            pw_fznz_rows_kernel<WARPS><<<(unsigned)p, WARPS * 32, 0, st>>>(t, n_obs_min, alpha, reliable_only ? 1 : 0, counters, cap, c_x, c_y, c_p, c_stat);
-            (*n_launch)++;
-            PWCK(cudaGetLastError(), "pw_fznz_rows_kernel");
-            PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 2, cudaMemcpyDeviceToHost, st), "d2h");
-            PWCK(cudaStreamSynchronize(st), "sync");
-            if ((i64)h_cnt[0] <= cap) break;
-            cap = (i64)h_cnt[0];
-        }
-    }
-    const i64 nf = (i64)h_cnt[0];
-    out->n_raw_sig = nf;
-    out->n_reliable = reliable_only ? (i64)h_cnt[1] : n_pairs;
-    const i64 m = reliable_only ? (i64)h_cnt[1] : n_pairs;
-    i64* d_off; PWCK(S.get(6, sizeof(i64) * (p + 1), (void**)&d_off), "alloc");
-    out->d_off = d_off;
-    if (nf == 0) {
-        PWCK(cudaMemsetAsync(d_off, 0, sizeof(i64) * (p + 1), st), "memset");
-        out->n_entries = 0; out->d_nbr = nullptr; out->d_stat = nullptr; out->d_adjp = nullptr;
-        return cudaSuccess;
-    }
-    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    unsigned char* arena; PWCK(S.get(11, 2 * al(sizeof(u64) * nf) + 2 * al(sizeof(unsigned int) * nf), (void**)&arena), "alloc");
-    u64* keys = (u64*)arena; u64* keys2 = (u64*)(arena + al(sizeof(u64) * nf));
-    unsigned int* vals = (unsigned int*)(arena + 2 * al(sizeof(u64) * nf)); unsigned int* vals2 = (unsigned int*)(arena + 2 * al(sizeof(u64) * nf) + al(sizeof(unsigned int) * nf));
-    pw_pair_keys<<<pw_blocks(nf, T), T, 0, st>>>(c_x, c_y, p, keys, vals, nf); (*n_launch)++;
-    int end_bit = 1; while (((u64)1 << end_bit) < (u64)p * (u64)p && end_bit < 64) ++end_bit;
-    void* tmp = nullptr; size_t need = 0;
-    if (nf >= ((i64)1 << 31) - 1) { if (msg) *msg = "more than 2^31 raw-significant pairs are not supported (unsupported size)"; return cudaErrorInvalidValue; }
-    cub::DeviceRadixSort::SortPairs(nullptr, need, keys, keys2, vals, vals2, (int)nf, 0, end_bit, st);
-    PWCK(S.get(5, need, &tmp), "alloc");
-    PWCK(cub::DeviceRadixSort::SortPairs(tmp, need, keys, keys2, vals, vals2, (int)nf, 0, end_bit, st), "sort"); (*n_launch) += 8;
-    unsigned char* ord; PWCK(S.get(15, 2 * al(sizeof(int) * nf) + 2 * al(sizeof(double) * nf), (void**)&ord), "alloc");
-    int* o_x = (int*)ord; int* o_y = (int*)(ord + al(sizeof(int) * nf));
-    double* o_p = (double*)(ord + 2 * al(sizeof(int) * nf)); double* o_s = (double*)(ord + 2 * al(sizeof(int) * nf) + al(sizeof(double) * nf));
-    pw_gather_pairs<<<pw_blocks(nf, T), T, 0, st>>>(vals2, c_x, c_y, c_p, c_stat, o_x, o_y, o_p, o_s, nf); (*n_launch)++;
-    PWCK(cudaGetLastError(), "pw_gather_pairs");
-    PWCK(cudaStreamSynchronize(st), "sync");
-    return pairwise_finish(S, o_x, o_y, o_p, o_s, nf, m, p, alpha, fdr, st, out, n_launch, msg);
+    PwCollected pc;
+    cudaError_t e = pairwise_fznz_collect(S, planes, t, n_obs_min, alpha, reliable_only, 0, 1, st, &pc, n_launch, msg);
+    if (e != cudaSuccess) return e;
+    out->n_tests = n_pairs; out->n_raw_sig = pc.nf;
+    out->n_reliable = reliable_only ? pc.n_rel : n_pairs;
+    const i64 m = reliable_only ? pc.n_rel : n_pairs;
+    return pairwise_order_finish(S, pc.c_x, pc.c_y, pc.c_p, pc.c_stat, pc.nf, m, p, alpha, fdr, st, out, n_launch, msg);
 }

@@ -77,6 +77,42 @@ def table_slice(p, rank, world):
     return p * rank // world, p * (rank + 1) // world
 
 
+# ---- pairwise stage of the table-based kinds (mi, mi_nz, fz_nz) split over the ranks ---------------------------------------------
+def pack_records(rec):
+    """the raw-significant records of one rank as ONE float64 array [4, n] (x, y, p, stat; indices are exact in float64)"""
+    return np.stack([rec["x"].astype(np.float64), rec["y"].astype(np.float64), rec["p"], rec["stat"]])
+
+
+def unpack_records(arr, n_reliable):
+    return {"x": arr[0].astype(np.int32), "y": arr[1].astype(np.int32), "p": np.ascontiguousarray(arr[2]), "stat": np.ascontiguousarray(arr[3]),
+            "n_reliable": int(n_reliable)}
+
+
+def allgather_records(dist, rec, device=None):
+    """The one exchange step of the sharded pairwise stage (Benjamini-Hochberg needs every p-value, statfuns.jl:326-350): all ranks'
+    records on every rank.  Two collectives: the counts, then the records padded to the longest list (NCCL on `device`, gloo on CPU)."""
+    import torch
+    world = dist.get_world_size()
+    meta = torch.tensor([len(rec["x"]), rec["n_reliable"]], dtype=torch.int64, device=device)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    counts = [int(m[0]) for m in metas]
+    nmax = max(max(counts), 1)
+    mine = torch.zeros((4, nmax), dtype=torch.float64, device=device)
+    mine[:, :counts[dist.get_rank()]] = torch.from_numpy(pack_records(rec)).to(mine.device)
+    bucket = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(bucket, mine)
+    return [unpack_records(b[:, :c].cpu().numpy(), int(m[1])) for b, c, m in zip(bucket, counts, metas)]
+
+
+def sharded_pairwise(dist, eng, kind, alpha=0.01, hps=5, n_obs_min=0, FDR=True, correct_reliable_only=True, device=None, want_host=False):
+    """pw_univar_neighbors by all ranks together (every rank holds the table): partial -> all-gather -> merge; identical lists on every rank"""
+    rec = eng.pairwise_partial(dist.get_rank(), dist.get_world_size(), alpha=alpha, hps=hps, n_obs_min=n_obs_min,
+                               correct_reliable_only=correct_reliable_only, kind=kind)
+    recs = allgather_records(dist, rec, device=device)
+    return eng.pairwise_merge(recs, alpha=alpha, FDR=FDR, correct_reliable_only=correct_reliable_only, kind=kind, want_host=want_host)
+
+
 # ---- row-sharded correlation matrix with a host-side NCCL exchange (superseded by the group API above) -------------------------------------------------------------------------------------
 def cor_groups(n_tile_rows, world):
     """Split the tile rows of the upper-triangular cor_mat GEMM into 2*world equal contiguous groups; rank r owns group r

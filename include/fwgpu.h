@@ -213,6 +213,20 @@ int32_t fw_pairwise(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_
  * optimisation: with other parameters, or without the announcement, fw_pairwise scans the resident matrix once.  alpha <= 0 disarms. */
 int32_t fw_pairwise_prefetch(fw_ctx* ctx, double alpha, int64_t n_obs_min);
 int32_t fw_pairwise_copy(fw_ctx* ctx, int64_t* offsets /* p+1 */, int64_t* nbr, double* stat, double* adjp);
+/* Multi-GPU, table-based kinds (FW_MI, FW_MI_NZ, FW_FZ_NZ): pw_univar_neighbors split over `world` ranks that each hold the whole
+ * table (src/tests.jl:464, 494 hands the X rows of the pairwise loop to the workers with @distributed; here the X variables are dealt
+ * to the ranks in balanced groups).  fw_pairwise_partial evaluates every pair (X, Y > X) whose X belongs to `rank` and keeps the
+ * raw-significant records (p < alpha) on the device: n_raw of them, and n_reliable = the rank's tests that enter the FDR correction
+ * (meaningful with correct_reliable_only; otherwise m = p (p - 1) / 2).  fw_pairwise_partial_copy returns the records (opaque to
+ * the host, 0-based).  The host language concatenates the records of all ranks in any order (Distributed / torch.distributed
+ * all-gather: this is the one exchange step of the pairwise stage, statfuns.jl:326-350 needs every p-value) and every rank calls
+ * fw_pairwise_merge with the concatenation and m_tests = sum of n_reliable (or p (p - 1) / 2): condensed-index order,
+ * Benjamini-Hochberg and the neighbour lists exactly as fw_pairwise would produce them on one GPU. */
+int32_t fw_pairwise_partial(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_t n_obs_min, int32_t correct_reliable_only,
+                            int32_t rank, int32_t world, int64_t* n_raw, int64_t* n_reliable);
+int32_t fw_pairwise_partial_copy(fw_ctx* ctx, int32_t* x, int32_t* y, double* pval, double* stat);
+int32_t fw_pairwise_merge(fw_ctx* ctx, int32_t kind, double alpha, int32_t fdr, int64_t n_raw_total, const int32_t* x, const int32_t* y,
+                          const double* pval, const double* stat, int64_t m_tests, int64_t* n_entries);
 /* install caller-provided neighbour lists (the `all_univar_nbrs` argument of LGL, src/learning.jl:213,235-242) */
 int32_t fw_set_univar_nbrs(fw_ctx* ctx, const int64_t* offsets /* p+1 */, const int64_t* nbr,
                            const double* stat, const double* adjp);

@@ -91,3 +91,41 @@ def test_shard_targets_partition():
         parts = [par.shard_targets(order, r, world) for r in range(world)]
         assert sorted(np.concatenate(parts).tolist()) == list(range(1001))
         assert max(len(x) for x in parts) - min(len(x) for x in parts) <= 1
+
+
+def _records_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    par = fwload.load_sub("parallel")
+    rng = np.random.default_rng(100 + rank)
+    n = [5, 0, 17][rank]                                    # ragged, one rank with no records
+    rec = {"x": rng.integers(0, 2 ** 31 - 2, n).astype(np.int32), "y": rng.integers(0, 2 ** 31 - 2, n).astype(np.int32),
+           "p": rng.random(n) * 1e-300, "stat": rng.standard_normal(n), "n_reliable": 1000 + rank}
+    got = par.allgather_records(dist, rec)
+    q.put((rank, rec, got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allgather_records_ragged():
+    """the exchange step of the sharded pairwise stage (parallel.allgather_records): every rank ends up with every rank's records,
+    bit for bit (indices up to 2^31, denormal p-values), including an empty list"""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_records_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    sent = {r: rec for r, rec, _ in out}
+    for _, _, got in out:
+        assert len(got) == world
+        for r in range(world):
+            for k in ("x", "y", "p", "stat"):
+                assert got[r][k].dtype == sent[r][k].dtype and (got[r][k] == sent[r][k]).all()
+            assert got[r]["n_reliable"] == sent[r]["n_reliable"]
