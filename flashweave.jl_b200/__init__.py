@@ -549,6 +549,24 @@ class Engine:
         self._ck(self.L.fw_pairwise_partial_copy(self.h, _p(rec["x"]), _p(rec["y"]), _p(rec["p"]), _p(rec["stat"])))
         return rec
 
+    def pairwise_partial_run(self, rank, world, alpha=0.01, hps=5, n_obs_min=0, correct_reliable_only=True, kind=None):
+        """fw_pairwise_partial without fetching the records: (n_raw, n_reliable); the records stay on the device"""
+        nr, nrel = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.fw_pairwise_partial(self.h, KINDS[kind or self.kind], alpha, hps, n_obs_min, int(correct_reliable_only), rank, world,
+                                            C.byref(nr), C.byref(nrel)))
+        return int(nr.value), int(nrel.value)
+
+    def pairwise_partial_copy_ptrs(self, x_ptr, y_ptr, p_ptr, stat_ptr):
+        """this rank's records into caller-provided int32 / int32 / float64 / float64 buffers (host or device pointers)"""
+        self._ck(self.L.fw_pairwise_partial_copy(self.h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), C.c_void_p(p_ptr), C.c_void_p(stat_ptr)))
+
+    def pairwise_merge_ptrs(self, n_total, x_ptr, y_ptr, p_ptr, stat_ptr, m_tests, alpha=0.01, FDR=True, kind=None):
+        """fw_pairwise_merge on raw pointers (host or device memory)"""
+        ne = C.c_int64(0)
+        self._ck(self.L.fw_pairwise_merge(self.h, KINDS[kind or self.kind], alpha, int(FDR), n_total, C.c_void_p(x_ptr), C.c_void_p(y_ptr),
+                                          C.c_void_p(p_ptr), C.c_void_p(stat_ptr), m_tests, C.byref(ne)))
+        self.uni_entries = int(ne.value)
+
     def pairwise_merge(self, records, alpha=0.01, FDR=True, correct_reliable_only=True, kind=None, want_host=True):
         """BH + neighbour lists from the records of ALL ranks (fw_pairwise_merge); `records` = the dicts of pairwise_partial."""
         x = np.ascontiguousarray(np.concatenate([r["x"] for r in records]), dtype=np.int32)

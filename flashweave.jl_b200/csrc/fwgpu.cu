@@ -1350,10 +1350,10 @@ int32_t fw_pairwise_partial_copy(fw_ctx* ctx, int32_t* x, int32_t* y, double* pv
     CK(cudaSetDevice(ctx->device));
     const i64 nf = ctx->part.nf;
     if (nf) {
-        CK(cudaMemcpyAsync(x, ctx->part.c_x, sizeof(int) * nf, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(y, ctx->part.c_y, sizeof(int) * nf, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(pval, ctx->part.c_p, sizeof(double) * nf, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(stat, ctx->part.c_stat, sizeof(double) * nf, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(x, ctx->part.c_x, sizeof(int) * nf, cudaMemcpyDefault, ctx->stream));
+        CK(cudaMemcpyAsync(y, ctx->part.c_y, sizeof(int) * nf, cudaMemcpyDefault, ctx->stream));
+        CK(cudaMemcpyAsync(pval, ctx->part.c_p, sizeof(double) * nf, cudaMemcpyDefault, ctx->stream));
+        CK(cudaMemcpyAsync(stat, ctx->part.c_stat, sizeof(double) * nf, cudaMemcpyDefault, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     return FW_OK;
@@ -1363,22 +1363,25 @@ int32_t fw_pairwise_merge(fw_ctx* ctx, int32_t kind, double alpha, int32_t fdr, 
                           const double* pval, const double* stat, int64_t m_tests, int64_t* n_entries) {
     if (!ctx) return FW_ERR_INVALID;
     NEED(kind == FW_MI || kind == FW_MI_NZ || kind == FW_FZ_NZ, FW_ERR_UNSUPPORTED, "fw_pairwise_merge: kind %d", kind);
-    NEED(ctx->data_kind != 0 && ctx->p > 0, FW_ERR_STATE, "fw_pairwise_merge: no table resident");
+    NEED(ctx->data_kind == (kind == FW_FZ_NZ ? 0 : 1) && ctx->p > 0, FW_ERR_STATE, "fw_pairwise_merge: no table of this kind resident");
     NEED(n_raw_total >= 0 && (n_raw_total == 0 || (x && y && pval && stat)), FW_ERR_INVALID, "fw_pairwise_merge: NULL records");
     NEED(n_raw_total < ((i64)1 << 31) - 1, FW_ERR_UNSUPPORTED, "fw_pairwise_merge: more than 2^31 raw-significant pairs");
     CK(cudaSetDevice(ctx->device));
     const i64 p = ctx->p, nf = n_raw_total;
-    for (i64 i = 0; i < nf; ++i) NEED(x[i] >= 0 && x[i] < y[i] && y[i] < p, FW_ERR_INVALID, "fw_pairwise_merge: record %lld is not a pair x < y < p", (long long)i);
+    bool on_device = false;                                           // records may live in host or device memory (unified addressing)
+    if (nf) { cudaPointerAttributes at; if (cudaPointerGetAttributes(&at, x) == cudaSuccess) on_device = at.type == cudaMemoryTypeDevice; else cudaGetLastError(); }
+    if (!on_device) for (i64 i = 0; i < nf; ++i) NEED(x[i] >= 0 && x[i] < y[i] && y[i] < p, FW_ERR_INVALID, "fw_pairwise_merge: record %lld is not a pair x < y < p", (long long)i);
     int *d_x, *d_y; double *d_p, *d_s;
     const i64 cap = std::max<i64>(nf, 16);
     CK(ctx->pw.get(7, sizeof(int) * cap, (void**)&d_x)); CK(ctx->pw.get(8, sizeof(int) * cap, (void**)&d_y));
     CK(ctx->pw.get(9, sizeof(double) * cap, (void**)&d_p)); CK(ctx->pw.get(10, sizeof(double) * cap, (void**)&d_s));
     ctx->part = PwCollected(); ctx->part_kind = -1;                   // the slots of the partial result are overwritten
     if (nf) {
-        CK(cudaMemcpyAsync(d_x, x, sizeof(int) * nf, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(d_y, y, sizeof(int) * nf, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(d_p, pval, sizeof(double) * nf, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(d_s, stat, sizeof(double) * nf, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_x, x, sizeof(int) * nf, cudaMemcpyDefault, ctx->stream));
+        CK(cudaMemcpyAsync(d_y, y, sizeof(int) * nf, cudaMemcpyDefault, ctx->stream));
+        CK(cudaMemcpyAsync(d_p, pval, sizeof(double) * nf, cudaMemcpyDefault, ctx->stream));
+        CK(cudaMemcpyAsync(d_s, stat, sizeof(double) * nf, cudaMemcpyDefault, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));                       // borrowed pointers: valid for the duration of the call only
     }
     PairwiseOut po; std::string msg; int nl = 0;
     po.n_tests = p * (p - 1) / 2; po.n_raw_sig = nf; po.n_reliable = m_tests;

@@ -106,11 +106,38 @@ def allgather_records(dist, rec, device=None):
 
 
 def sharded_pairwise(dist, eng, kind, alpha=0.01, hps=5, n_obs_min=0, FDR=True, correct_reliable_only=True, device=None, want_host=False):
-    """pw_univar_neighbors by all ranks together (every rank holds the table): partial -> all-gather -> merge; identical lists on every rank"""
-    rec = eng.pairwise_partial(dist.get_rank(), dist.get_world_size(), alpha=alpha, hps=hps, n_obs_min=n_obs_min,
-                               correct_reliable_only=correct_reliable_only, kind=kind)
-    recs = allgather_records(dist, rec, device=device)
-    return eng.pairwise_merge(recs, alpha=alpha, FDR=FDR, correct_reliable_only=correct_reliable_only, kind=kind, want_host=want_host)
+    """pw_univar_neighbors by all ranks together (every rank holds the table): partial -> all-gather -> merge; identical lists on every
+    rank.  With a CUDA `device` the records never leave the GPUs: they are copied device-to-device into torch buffers, all-gathered by
+    NCCL over NVLink and handed to fw_pairwise_merge as device pointers."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if device is None or torch.device(device).type != "cuda":
+        rec = eng.pairwise_partial(rank, world, alpha=alpha, hps=hps, n_obs_min=n_obs_min, correct_reliable_only=correct_reliable_only, kind=kind)
+        recs = allgather_records(dist, rec, device=device)
+        return eng.pairwise_merge(recs, alpha=alpha, FDR=FDR, correct_reliable_only=correct_reliable_only, kind=kind, want_host=want_host)
+    n_raw, n_rel = eng.pairwise_partial_run(rank, world, alpha=alpha, hps=hps, n_obs_min=n_obs_min, correct_reliable_only=correct_reliable_only, kind=kind)
+    meta = torch.tensor([n_raw, n_rel], dtype=torch.int64, device=device)
+    metas = torch.zeros((world, 2), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(metas, meta)
+    metas = metas.cpu().numpy()
+    counts = [int(c) for c in metas[:, 0]]
+    nmax = max(max(counts), 1)
+    mine_i = torch.zeros((2, nmax), dtype=torch.int32, device=device)
+    mine_f = torch.zeros((2, nmax), dtype=torch.float64, device=device)
+    torch.cuda.synchronize(device)                   # the buffers exist (torch's stream) before the library's stream writes them
+    eng.pairwise_partial_copy_ptrs(mine_i[0].data_ptr(), mine_i[1].data_ptr(), mine_f[0].data_ptr(), mine_f[1].data_ptr())
+    all_i = torch.empty((world, 2, nmax), dtype=torch.int32, device=device)
+    all_f = torch.empty((world, 2, nmax), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(all_i, mine_i)
+    dist.all_gather_into_tensor(all_f, mine_f)
+    xs = torch.cat([all_i[r, 0, :counts[r]] for r in range(world)]).contiguous()
+    ys = torch.cat([all_i[r, 1, :counts[r]] for r in range(world)]).contiguous()
+    ps = torch.cat([all_f[r, 0, :counts[r]] for r in range(world)]).contiguous()
+    ss = torch.cat([all_f[r, 1, :counts[r]] for r in range(world)]).contiguous()
+    torch.cuda.synchronize(device)
+    m = int(metas[:, 1].sum()) if correct_reliable_only else eng.p * (eng.p - 1) // 2
+    eng.pairwise_merge_ptrs(int(sum(counts)), xs.data_ptr(), ys.data_ptr(), ps.data_ptr(), ss.data_ptr(), m, alpha=alpha, FDR=FDR, kind=kind)
+    return eng.univar_nbrs() if want_host else None
 
 
 # ---- row-sharded correlation matrix with a host-side NCCL exchange (superseded by the group API above) -------------------------------------------------------------------------------------

@@ -221,7 +221,9 @@ int32_t fw_pairwise_copy(fw_ctx* ctx, int64_t* offsets /* p+1 */, int64_t* nbr, 
  * the host, 0-based).  The host language concatenates the records of all ranks in any order (Distributed / torch.distributed
  * all-gather: this is the one exchange step of the pairwise stage, statfuns.jl:326-350 needs every p-value) and every rank calls
  * fw_pairwise_merge with the concatenation and m_tests = sum of n_reliable (or p (p - 1) / 2): condensed-index order,
- * Benjamini-Hochberg and the neighbour lists exactly as fw_pairwise would produce them on one GPU. */
+ * Benjamini-Hochberg and the neighbour lists exactly as fw_pairwise would produce them on one GPU.  The record arrays of
+ * fw_pairwise_partial_copy / fw_pairwise_merge may be host or device memory (unified addressing): with NCCL the records never
+ * leave the GPUs. */
 int32_t fw_pairwise_partial(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_t n_obs_min, int32_t correct_reliable_only,
                             int32_t rank, int32_t world, int64_t* n_raw, int64_t* n_reliable);
 int32_t fw_pairwise_partial_copy(fw_ctx* ctx, int32_t* x, int32_t* y, double* pval, double* stat);

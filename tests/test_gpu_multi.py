@@ -140,3 +140,58 @@ def test_group_one_process_two_contexts():
     assert fw.assemble_graph(merged, uni1, "fz") == edges1
     for e in engs:
         e.comm_detach()
+
+
+def _worker_nz(rank, world, port, q):
+    """table-based kinds: every rank holds the table, the pairwise stage is split by X (NCCL all-gather of the records on the
+    device), targets are sharded"""
+    import torch
+    import torch.distributed as dist
+    import fwload
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    fw = fwload.load(); par = fwload.load_sub("parallel"); synth = fwload.load_sub("synth")
+    ok = True
+    for kind in ("fz_nz", "mi"):
+        x = synth.hetero(2600, 500, B=12, seed=21)[0] if kind == "fz_nz" else synth.binarize(synth.clique(2600, 400, B=10, seed=22))
+        nom = 20 if kind == "fz_nz" else fw.auto_n_obs_min("mi", 3, 5, max_level=2)
+        eng = fw.Engine(rank)
+        eng.set_data_colmajor(x, kind)
+        uni = par.sharded_pairwise(dist, eng, kind, alpha=0.01, n_obs_min=nom, device=torch.device("cuda", rank), want_host=True)
+        order = fw.target_order(uni)
+        res = eng.si_HITON_PC(par.shard_targets(order, rank, world), max_k=3, alpha=0.01, n_obs_min=nom, want_tpc=False, kind=kind)
+        bucket = par.gather_results(dist, par.pack_result(res), dst=0)
+        if rank == 0:
+            merged = par.MergedResult(bucket)
+            edges = fw.assemble_graph(merged, uni, kind)
+            e1 = fw.Engine(0)
+            e1.set_data_colmajor(x, kind)
+            uni1 = e1.pw_univar_neighbors(alpha=0.01, n_obs_min=nom)
+            res1 = e1.si_HITON_PC(fw.target_order(uni1), max_k=3, alpha=0.01, n_obs_min=nom, want_tpc=False)
+            ok &= bool((uni.offsets == uni1.offsets).all()) and bool((uni.nbr == uni1.nbr).all()) and bool((uni.stat == uni1.stat).all()) and bool((uni.pval == uni1.pval).all())
+            ok &= edges == fw.assemble_graph(res1, uni1, kind) and int(merged.num_tests.sum()) == int(res1.num_tests.sum()) and len(edges) > 100
+    if rank == 0:
+        q.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_pairwise_two_processes_nccl():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_nz, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    ok = q.get(timeout=300)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert ok, "sharded pairwise stage + sharded targets differ from the single-GPU result"
