@@ -61,9 +61,12 @@ __device__ __forceinline__ double fznz_r_from_moments(double gaa, double gbb, do
     return rr;
 }
 // One pass over the rows where X != 0 and Y != 0.  Lane (c = lane & 7, j = lane >> 3) accumulates class c (row mod 8) of one
-// moment: j = 0: Sx (and Sy in a second register), 1: Sxx, 2: Syy, 3: Sxy.  Per 32-row word every lane loads its own row
-// (coalesced) and the four rows of a class reach their lane by shuffles, in increasing row order.
-__device__ NzUni fznz_uni_warp(const NzTable& t, i64 X, i64 Y, i64 n_obs_min) {
+// moment: j = 0: Sx (and Sy in a second register), 1: Sxx, 2: Syy, 3: Sxy, over the view rows of its class in increasing row
+// order (the canonical summation order shared with the oracle).  Every lane walks the SET bits of its class with its own cursor
+// (the four moment lanes of a class move together): the view holds 10-30 % of the rows in FlashWeaveHE tables, and a loop over all
+// 32 rows of every mask word spent most of its fp64 issue slots on rows outside the view.  wm: W words of per-warp scratch (shared
+// memory) for the combined mask, or nullptr (the two masks are then re-read from global memory).
+__device__ NzUni fznz_uni_warp(const NzTable& t, i64 X, i64 Y, i64 n_obs_min, unsigned int* wm) {
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     NzUni r;
@@ -72,36 +75,51 @@ __device__ NzUni fznz_uni_warp(const NzTable& t, i64 X, i64 Y, i64 n_obs_min) {
     const float* x = t.data + X * t.ld; const float* y = t.data + Y * t.ld;
     const unsigned int* mx = t.nzmask + X * t.W; const unsigned int* my = t.nzmask + Y * t.W;
     int cnt = 0, first = 0x7fffffff;
+    if (wm) __syncwarp();                                                // the previous pair's cursors are done with wm
     for (int w = lane; w < t.W; w += 32) {
         const unsigned int m = mx[w] & my[w];
+        if (wm) wm[w] = m;
         cnt += __popc(m);
         if (m && first == 0x7fffffff) first = w * 32 + __ffs(m) - 1;
     }
+    if (wm) __syncwarp();                                                // wm is complete and visible to every lane
     const i64 n_obs = __reduce_add_sync(full, cnt);
     first = __reduce_min_sync(full, first);
     double p_stat = 0.0;
     if (n_obs > 0 && n_obs >= n_obs_min) {
         const double cx = (double)x[first], cy = (double)y[first];
         const int c = lane & 7, j = lane >> 3;
+        const unsigned int cls_bits = 0x01010101u << c;                  // rows c, c + 8, c + 16, c + 24 of a word
         double acc = 0.0, acc2 = 0.0;
-        for (int w = 0; w < t.W; ++w) {
-            const unsigned int m = mx[w] & my[w];                        // warp-uniform
-            if (!m) continue;
-            const int row = w * 32 + lane;
-            const float a = row < t.n ? x[row] : 0.0f, b = row < t.n ? y[row] : 0.0f;
+        int w = 0;
+        unsigned int cm = (wm ? wm[0] : (mx[0] & my[0])) & cls_bits;
+        // U rows per trip: the row indices come from the mask alone, so the 2U loads of a trip are independent and in flight together
+        // (the columns of all resident warps do not fit L1: a load is an L2 round trip); the moments are still accumulated row by row
+        constexpr int U = 4;
+        for (;;) {
+            int rows[U]; int nr = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int src = c + 8 * q;
-                const float aq = __shfl_sync(full, a, src), bq = __shfl_sync(full, b, src);
-                if ((m >> src) & 1u) {
-                    const double da = __dsub_rn((double)aq, cx), db = __dsub_rn((double)bq, cy);
-                    const double u = (j == 2) ? db : da;
-                    const double v = (j == 0) ? 1.0 : ((j == 1) ? da : db);
-                    acc = fma(u, v, acc);
+            for (int u = 0; u < U; ++u) {
+                while (cm == 0u && ++w < t.W) cm = (wm ? wm[w] : (mx[w] & my[w])) & cls_bits;
+                if (w < t.W) { rows[u] = w * 32 + __ffs(cm) - 1; cm &= cm - 1u; nr = u + 1; } else rows[u] = first;
+            }
+            if (nr == 0) break;
+            float xa[U], ya[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { xa[u] = x[rows[u]]; ya[u] = y[rows[u]]; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u < nr) {
+                    const double da = __dsub_rn((double)xa[u], cx), db = __dsub_rn((double)ya[u], cy);
+                    const double uu = (j == 2) ? db : da;
+                    const double vv = (j == 0) ? 1.0 : ((j == 1) ? da : db);
+                    acc = fma(uu, vv, acc);
                     acc2 = fma(db, 1.0, acc2);
                 }
             }
+            if (nr < U) break;
         }
+        __syncwarp();
         double tot = 0.0, tot2 = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) { tot += __shfl_sync(full, acc, (lane & 24) + k); tot2 += __shfl_sync(full, acc2, (lane & 24) + k); }
@@ -338,16 +356,21 @@ __device__ int fznz_subcor_block(const NzTable& t, const i64* var, int nv, int x
     return rows;
 }
 
+// per-warp mask scratch of the pairwise kernels: WARPS x W words of dynamic shared memory when that fits (0 = re-read the masks)
+static inline size_t fznz_warp_scratch_bytes(int warps, int W) { const size_t b = (size_t)warps * W * sizeof(unsigned int); return b <= 96 * 1024 ? b : 0; }
+
 // ---- pairwise stage: one warp per pair, unordered emission (tests.jl:410-433, :391-407) -----------------------
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) pw_fznz_rows_kernel(NzTable t, i64 n_obs_min, double alpha, int reliable_only,
-                                                                  u64* counters, i64 cap, int* c_x, int* c_y, double* c_p, double* c_stat, int sh_rank, int sh_world) {
+                                                                  u64* counters, i64 cap, int* c_x, int* c_y, double* c_p, double* c_stat, int sh_rank, int sh_world, int use_wm) {
+    extern __shared__ unsigned int pw_wm[];                             // WARPS x W words (or nothing: see fznz_warp_scratch_bytes)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const i64 X = blockIdx.x;
     if (!pw_owns_group(X / PW_X_GROUP, sh_rank, sh_world)) return;
+    unsigned int* wm = use_wm ? pw_wm + (size_t)warp * t.W : nullptr;
     i64 n_rel = 0;
     for (i64 Y = X + 1 + warp; Y < t.p; Y += WARPS) {
-        NzUni r = fznz_uni_warp(t, X, Y, n_obs_min);
+        NzUni r = fznz_uni_warp(t, X, Y, n_obs_min, wm);
         const bool rel = (r.suff || !reliable_only) && !isnan(r.pval);
         n_rel += rel;
         if (rel && r.pval < alpha && lane == 0) {
@@ -374,7 +397,7 @@ __global__ void __launch_bounds__(THREADS) fznz_test_batch_kernel(NzTable t, i64
         const int kk = k[tix];
         if (kk == 0) {
             if (threadIdx.x < 32) {
-                NzUni r = fznz_uni_warp(t, X[tix], Y[tix], n_obs_min);
+                NzUni r = fznz_uni_warp(t, X[tix], Y[tix], n_obs_min, mask);
                 if (threadIdx.x == 0) out[tix] = make_result(r.stat, r.pval, 0, r.suff);
             }
             continue;

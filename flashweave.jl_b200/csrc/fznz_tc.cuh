@@ -263,16 +263,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) fznz_prefilter_kernel(const __gri
     }
 }
 
+// Candidate order.  The exact test streams both columns of a pair through L1 (2 x 4n bytes, an L2 round trip per sector); the 8 warps of
+// a CTA take 8 consecutive candidates, so the list is sorted by (X tile, Y tile, X, Y): the warps of a CTA then share X (its sectors hit
+// L1 after the first warp) and the CTAs that run together stay inside a few pre-filter tiles (L2).  key = tileX:20 | tileY:20 | x&127:7 | y&63:6.
+__global__ void fznz_cand_keys_kernel(const int* __restrict__ cand_x, const int* __restrict__ cand_y, i64 n, u64* __restrict__ keys) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 x = (u64)cand_x[i], y = (u64)cand_y[i];
+    keys[i] = ((x >> 7) << 33) | ((y >> 6) << 13) | ((x & 127u) << 6) | (y & 63u);
+}
+
 // exact fp64 test of the candidate pairs, one warp each; same outputs as pw_fznz_rows_kernel
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) fznz_candidates_kernel(NzTable t, i64 n_cand, const int* __restrict__ cand_x, const int* __restrict__ cand_y,
+__global__ void __launch_bounds__(WARPS * 32) fznz_candidates_kernel(NzTable t, i64 n_cand, const u64* __restrict__ keys,
                                                                      i64 n_obs_min, double alpha, int reliable_only,
-                                                                     u64* counters, i64 cap, int* c_x, int* c_y, double* c_p, double* c_stat) {
+                                                                     u64* counters, i64 cap, int* c_x, int* c_y, double* c_p, double* c_stat, int use_wm) {
+    extern __shared__ unsigned int cand_wm[];                           // WARPS x W words (fznz_warp_scratch_bytes)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned int* wm = use_wm ? cand_wm + (size_t)warp * t.W : nullptr;
     i64 n_rel = 0;
     for (i64 i = (i64)blockIdx.x * WARPS + warp; i < n_cand; i += (i64)gridDim.x * WARPS) {
-        const i64 X = cand_x[i], Y = cand_y[i];
-        NzUni r = fznz_uni_warp(t, X, Y, n_obs_min);
+        const u64 k = keys[i];
+        const i64 X = (i64)(((k >> 33) << 7) | ((k >> 6) & 127u)), Y = (i64)((((k >> 13) & 0xFFFFFu) << 6) | (k & 63u));
+        NzUni r = fznz_uni_warp(t, X, Y, n_obs_min, wm);
         const bool rel = (r.suff || !reliable_only) && !isnan(r.pval);
         n_rel += rel;
         if (rel && r.pval < alpha && lane == 0) {

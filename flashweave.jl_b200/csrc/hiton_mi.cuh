@@ -583,15 +583,29 @@ static cudaError_t pairwise_fznz_collect(PairwiseScratch& S, fznztc::Planes& pla
             ccap = (i64)h_cnt[0];
         }
         const i64 n_cand = (i64)h_cnt[0];
+        if (getenv("FWGPU_VERBOSE")) fprintf(stderr, "[fwgpu] fz_nz pairwise: %lld candidates of %lld pairs after the tensor-core pre-filter (rank %d of %d)\n", (long long)n_cand, (long long)n_pairs, sh_rank, sh_world);
         const i64 cap = std::max<i64>(n_cand, 16);
         PWCK(S.get(7, sizeof(int) * cap, (void**)&pc->c_x), "alloc");
         PWCK(S.get(8, sizeof(int) * cap, (void**)&pc->c_y), "alloc");
         PWCK(S.get(9, sizeof(double) * cap, (void**)&pc->c_p), "alloc");
         PWCK(S.get(10, sizeof(double) * cap, (void**)&pc->c_stat), "alloc");
         if (n_cand > 0) {
+            if (n_cand >= ((i64)1 << 31) - 1) { if (msg) *msg = "more than 2^31 candidate pairs are not supported (unsupported size)"; return cudaErrorInvalidValue; }
+            // sort the candidates by (X tile, Y tile, X, Y): see fznz_cand_keys_kernel
+            auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+            unsigned char* karena; PWCK(S.get(18, 2 * al(sizeof(u64) * n_cand), (void**)&karena), "alloc");
+            u64* keys = (u64*)karena; u64* keys2 = (u64*)(karena + al(sizeof(u64) * n_cand));
+            fznztc::fznz_cand_keys_kernel<<<pw_blocks(n_cand, 256), 256, 0, st>>>(k_x, k_y, n_cand, keys); (*n_launch)++;
+            int tb = 1; while (((u64)1 << tb) <= (u64)((p + 127) >> 7) && tb < 20) ++tb;
+            void* tmp = nullptr; size_t need = 0;
+            cub::DeviceRadixSort::SortKeys(nullptr, need, keys, keys2, (int)n_cand, 0, 33 + tb, st);
+            PWCK(S.get(5, need, &tmp), "alloc");
+            PWCK(cub::DeviceRadixSort::SortKeys(tmp, need, keys, keys2, (int)n_cand, 0, 33 + tb, st), "sort (candidates)"); (*n_launch) += 7;
             const i64 blocks = std::min<i64>((n_cand + WARPS - 1) / WARPS, (i64)148 * 32);
-            fznztc::fznz_candidates_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, 0, st>>>(t, n_cand, k_x, k_y, n_obs_min, alpha, reliable_only ? 1 : 0,
-                                                                                       counters, cap, pc->c_x, pc->c_y, pc->c_p, pc->c_stat);
+            const size_t wmb = fznz_warp_scratch_bytes(WARPS, t.W);
+            if (wmb > 48 * 1024) PWCK(cudaFuncSetAttribute(fznztc::fznz_candidates_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wmb), "cudaFuncSetAttribute(fznz_candidates_kernel)");
+            fznztc::fznz_candidates_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, wmb, st>>>(t, n_cand, keys2, n_obs_min, alpha, reliable_only ? 1 : 0,
+                                                                                         counters, cap, pc->c_x, pc->c_y, pc->c_p, pc->c_stat, wmb ? 1 : 0);
             (*n_launch)++;
             PWCK(cudaGetLastError(), "fznz_candidates_kernel");
         }
@@ -606,7 +620,9 @@ static cudaError_t pairwise_fznz_collect(PairwiseScratch& S, fznztc::Planes& pla
             PWCK(S.get(9, sizeof(double) * cap, (void**)&pc->c_p), "alloc");
             PWCK(S.get(10, sizeof(double) * cap, (void**)&pc->c_stat), "alloc");
             PWCK(cudaMemsetAsync(counters, 0, sizeof(u64) * 4, st), "memset");
-            pw_fznz_rows_kernel<WARPS><<<(unsigned)p, WARPS * 32, 0, st>>>(t, n_obs_min, alpha, reliable_only ? 1 : 0, counters, cap, pc->c_x, pc->c_y, pc->c_p, pc->c_stat, sh_rank, sh_world);
+            const size_t wmb = fznz_warp_scratch_bytes(WARPS, t.W);
+            if (wmb > 48 * 1024) PWCK(cudaFuncSetAttribute(pw_fznz_rows_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wmb), "cudaFuncSetAttribute(pw_fznz_rows_kernel)");
+            pw_fznz_rows_kernel<WARPS><<<(unsigned)p, WARPS * 32, wmb, st>>>(t, n_obs_min, alpha, reliable_only ? 1 : 0, counters, cap, pc->c_x, pc->c_y, pc->c_p, pc->c_stat, sh_rank, sh_world, wmb ? 1 : 0);
             (*n_launch)++;
             PWCK(cudaGetLastError(), "pw_fznz_rows_kernel");
             PWCK(cudaMemcpyAsync(h_cnt, counters, sizeof(u64) * 2, cudaMemcpyDeviceToHost, st), "d2h");
