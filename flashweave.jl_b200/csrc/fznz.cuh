@@ -62,7 +62,7 @@ __device__ __forceinline__ double fznz_r_from_moments(double gaa, double gbb, do
 }
 // One pass over the rows where X != 0 and Y != 0.  Lane (c = lane & 7, j = lane >> 3) accumulates class c (row mod 8) of one
 // moment: j = 0: Sx (and Sy in a second register), 1: Sxx, 2: Syy, 3: Sxy, over the view rows of its class in increasing row
-// order (the canonical summation order shared with the oracle).  Every lane walks the SET bits of its class with its own cursor
+// order (the canonical summation order shared with the oracle).  Every lane walks the SET bits of its class only
 // (the four moment lanes of a class move together): the view holds 10-30 % of the rows in FlashWeaveHE tables, and a loop over all
 // 32 rows of every mask word spent most of its fp64 issue slots on rows outside the view.  wm: W words of per-warp scratch (shared
 // memory) for the combined mask, or nullptr (the two masks are then re-read from global memory).
@@ -89,35 +89,41 @@ __device__ NzUni fznz_uni_warp(const NzTable& t, i64 X, i64 Y, i64 n_obs_min, un
     if (n_obs > 0 && n_obs >= n_obs_min) {
         const double cx = (double)x[first], cy = (double)y[first];
         const int c = lane & 7, j = lane >> 3;
-        const unsigned int cls_bits = 0x01010101u << c;                  // rows c, c + 8, c + 16, c + 24 of a word
         double acc = 0.0, acc2 = 0.0;
-        int w = 0;
-        unsigned int cm = (wm ? wm[0] : (mx[0] & my[0])) & cls_bits;
-        // U rows per trip: the row indices come from the mask alone, so the 2U loads of a trip are independent and in flight together
-        // (the columns of all resident warps do not fit L1: a load is an L2 round trip); the moments are still accumulated row by row
+        // Class words: the membership bits of class c (rows c, c + 8, c + 16, ...) of 8 consecutive mask words gathered into one
+        // 32-bit word, bit b <-> row 256 k + 8 b + c (increasing b = increasing row).  Built with uniform control flow (4 spaced bits
+        // of a word -> one nibble by a multiply); the only divergent loop left is the walk over the set bits of a class word, whose
+        // trip count differs between the 8 classes by their popcounts.  U rows per trip: the row indices come from the mask alone,
+        // so the 2U loads of a trip are independent and in flight together; the moments are still accumulated row by row.
         constexpr int U = 4;
-        for (;;) {
-            int rows[U]; int nr = 0;
+        for (int k = 0; k * 8 < t.W; ++k) {
+            unsigned int cw = 0u;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                while (cm == 0u && ++w < t.W) cm = (wm ? wm[w] : (mx[w] & my[w])) & cls_bits;
-                if (w < t.W) { rows[u] = w * 32 + __ffs(cm) - 1; cm &= cm - 1u; nr = u + 1; } else rows[u] = first;
+            for (int i = 0; i < 8; ++i) {
+                const int w = 8 * k + i;
+                const unsigned int m = w < t.W ? (wm ? wm[w] : (mx[w] & my[w])) : 0u;
+                cw |= ((((m >> c) & 0x01010101u) * 0x10204080u) >> 28) << (4 * i);
             }
-            if (nr == 0) break;
-            float xa[U], ya[U];
+            while (cw) {
+                int rows[U]; int nr = 0;
 #pragma unroll
-            for (int u = 0; u < U; ++u) { xa[u] = x[rows[u]]; ya[u] = y[rows[u]]; }
+                for (int u = 0; u < U; ++u) {
+                    if (cw) { rows[u] = k * 256 + 8 * (__ffs(cw) - 1) + c; cw &= cw - 1u; nr = u + 1; } else rows[u] = first;
+                }
+                float xa[U], ya[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (u < nr) {
-                    const double da = __dsub_rn((double)xa[u], cx), db = __dsub_rn((double)ya[u], cy);
-                    const double uu = (j == 2) ? db : da;
-                    const double vv = (j == 0) ? 1.0 : ((j == 1) ? da : db);
-                    acc = fma(uu, vv, acc);
-                    acc2 = fma(db, 1.0, acc2);
+                for (int u = 0; u < U; ++u) { xa[u] = x[rows[u]]; ya[u] = y[rows[u]]; }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (u < nr) {
+                        const double da = __dsub_rn((double)xa[u], cx), db = __dsub_rn((double)ya[u], cy);
+                        const double uu = (j == 2) ? db : da;
+                        const double vv = (j == 0) ? 1.0 : ((j == 1) ? da : db);
+                        acc = fma(uu, vv, acc);
+                        acc2 = fma(db, 1.0, acc2);
+                    }
                 }
             }
-            if (nr < U) break;
         }
         __syncwarp();
         double tot = 0.0, tot2 = 0.0;
@@ -126,6 +132,82 @@ __device__ NzUni fznz_uni_warp(const NzTable& t, i64 X, i64 Y, i64 n_obs_min, un
         const double sx = __shfl_sync(full, tot, 0), sy = __shfl_sync(full, tot2, 0);
         const double sxx = __shfl_sync(full, tot, 8), syy = __shfl_sync(full, tot, 16), sxy = __shfl_sync(full, tot, 24);
         const double rr = fznz_r_from_moments(sxx, syy, sxy, sx, sy, (double)n_obs);      // NaN passes through (tests.jl:143, :381)
+        p_stat = (double)(float)rr;                                      // eltype of the data (Float32)
+    }
+    r.stat = p_stat;
+    r.pval = fz_pval_dev(p_stat, nz_consts(n_obs, n_obs_min));
+    r.suff = n_obs >= n_obs_min;
+    return r;
+}
+
+// Four pairs per warp: each group of 8 lanes (g = lane >> 3) tests its own pair, lane c = lane & 7 accumulates ALL five moments of
+// class c (one load / conversion / subtraction per row instead of one per moment lane).  The per-(class, moment) sums and their
+// combination are the ones of fznz_uni_warp, bit for bit.  Control flow outside the set-bit walk is warp-uniform (an invalid or
+// skipped group walks an empty mask).  wm: this GROUP's W words of scratch, or nullptr.
+__device__ NzUni fznz_uni_g8(const NzTable& t, i64 X, i64 Y, i64 n_obs_min, unsigned int* wm, bool valid) {
+    const int lane = threadIdx.x & 31, c = lane & 7, g0 = lane & 24;
+    const unsigned full = 0xffffffffu;
+    NzUni r; r.stat = 0.0; r.pval = 1.0; r.suff = false;
+    if (!valid) { X = 0; Y = 0; }
+    const bool short_x = valid && t.nnz[X] < n_obs_min;                                  // tests.jl:111-115,159
+    const float* x = t.data + X * t.ld; const float* y = t.data + Y * t.ld;
+    const unsigned int* mx = t.nzmask + X * t.W; const unsigned int* my = t.nzmask + Y * t.W;
+    int cnt = 0, first = 0x7fffffff;
+    __syncwarp();                                                        // the previous pairs are done with wm
+    for (int w = c; w < t.W; w += 8) {
+        const unsigned int m = (valid && !short_x) ? (mx[w] & my[w]) : 0u;
+        if (wm) wm[w] = m;
+        cnt += __popc(m);
+        if (m && first == 0x7fffffff) first = w * 32 + __ffs(m) - 1;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) { cnt += __shfl_xor_sync(full, cnt, o); first = min(first, __shfl_xor_sync(full, first, o)); }
+    const i64 n_obs = cnt;
+    const bool act = valid && !short_x && n_obs > 0 && n_obs >= n_obs_min;
+    double sx = 0.0, sy = 0.0, sxx = 0.0, syy = 0.0, sxy = 0.0;
+    const int frow = act ? first : 0;
+    const double cx = (double)x[frow], cy = (double)y[frow];
+    constexpr int U = 4;
+    for (int k = 0; k * 8 < t.W; ++k) {
+        unsigned int cw = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int w = 8 * k + i;
+            const unsigned int m = (act && w < t.W) ? (wm ? wm[w] : (mx[w] & my[w])) : 0u;
+            cw |= ((((m >> c) & 0x01010101u) * 0x10204080u) >> 28) << (4 * i);           // class word: see fznz_uni_warp
+        }
+        while (cw) {
+            int rows[U]; int nr = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (cw) { rows[u] = k * 256 + 8 * (__ffs(cw) - 1) + c; cw &= cw - 1u; nr = u + 1; } else rows[u] = frow;
+            }
+            float xa[U], ya[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { xa[u] = x[rows[u]]; ya[u] = y[rows[u]]; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u < nr) {
+                    const double da = __dsub_rn((double)xa[u], cx), db = __dsub_rn((double)ya[u], cy);
+                    sx = fma(da, 1.0, sx); sy = fma(db, 1.0, sy);
+                    sxx = fma(da, da, sxx); syy = fma(db, db, syy); sxy = fma(da, db, sxy);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    double tsx = 0.0, tsy = 0.0, tsxx = 0.0, tsyy = 0.0, tsxy = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        tsx += __shfl_sync(full, sx, g0 + k); tsy += __shfl_sync(full, sy, g0 + k);
+        tsxx += __shfl_sync(full, sxx, g0 + k); tsyy += __shfl_sync(full, syy, g0 + k); tsxy += __shfl_sync(full, sxy, g0 + k);
+    }
+    if (!valid) return r;
+    if (short_x) { r.stat = 0.0; r.pval = 1.0; r.suff = (0 >= n_obs_min); return r; }
+    double p_stat = 0.0;
+    if (act) {
+        const double rr = fznz_r_from_moments(tsxx, tsyy, tsxy, tsx, tsy, (double)n_obs);  // NaN passes through (tests.jl:143, :381)
         p_stat = (double)(float)rr;                                      // eltype of the data (Float32)
     }
     r.stat = p_stat;
@@ -357,28 +439,33 @@ __device__ int fznz_subcor_block(const NzTable& t, const i64* var, int nv, int x
 }
 
 // per-warp mask scratch of the pairwise kernels: WARPS x W words of dynamic shared memory when that fits (0 = re-read the masks)
-static inline size_t fznz_warp_scratch_bytes(int warps, int W) { const size_t b = (size_t)warps * W * sizeof(unsigned int); return b <= 96 * 1024 ? b : 0; }
+static inline size_t fznz_warp_scratch_bytes(int warps, int W) { const size_t b = (size_t)warps * 4 * W * sizeof(unsigned int); return b <= 96 * 1024 ? b : 0; }   // four pairs per warp
 
 // ---- pairwise stage: one warp per pair, unordered emission (tests.jl:410-433, :391-407) -----------------------
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) pw_fznz_rows_kernel(NzTable t, i64 n_obs_min, double alpha, int reliable_only,
                                                                   u64* counters, i64 cap, int* c_x, int* c_y, double* c_p, double* c_stat, int sh_rank, int sh_world, int use_wm) {
-    extern __shared__ unsigned int pw_wm[];                             // WARPS x W words (or nothing: see fznz_warp_scratch_bytes)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ unsigned int pw_wm[];                             // WARPS x 4 x W words (or nothing: see fznz_warp_scratch_bytes)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3;
     const i64 X = blockIdx.x;
     if (!pw_owns_group(X / PW_X_GROUP, sh_rank, sh_world)) return;
-    unsigned int* wm = use_wm ? pw_wm + (size_t)warp * t.W : nullptr;
+    unsigned int* wm = use_wm ? pw_wm + (size_t)(warp * 4 + g) * t.W : nullptr;
     i64 n_rel = 0;
-    for (i64 Y = X + 1 + warp; Y < t.p; Y += WARPS) {
-        NzUni r = fznz_uni_warp(t, X, Y, n_obs_min, wm);
-        const bool rel = (r.suff || !reliable_only) && !isnan(r.pval);
-        n_rel += rel;
-        if (rel && r.pval < alpha && lane == 0) {
-            u64 pos = atomicAdd(&counters[0], 1ull);
-            if ((i64)pos < cap) { c_x[pos] = (int)X; c_y[pos] = (int)Y; c_p[pos] = r.pval; c_stat[pos] = r.stat; }
+    for (i64 Y0 = X + 1 + warp * 4; Y0 < t.p; Y0 += WARPS * 4) {        // four pairs per warp: one per group of 8 lanes
+        const i64 Y = Y0 + g;
+        const bool valid = Y < t.p;
+        NzUni r = fznz_uni_g8(t, X, Y, n_obs_min, wm, valid);
+        const bool rel = valid && (r.suff || !reliable_only) && !isnan(r.pval);
+        if ((lane & 7) == 0) {
+            n_rel += rel;
+            if (rel && r.pval < alpha) {
+                u64 pos = atomicAdd(&counters[0], 1ull);
+                if ((i64)pos < cap) { c_x[pos] = (int)X; c_y[pos] = (int)Y; c_p[pos] = r.pval; c_stat[pos] = r.stat; }
+            }
         }
         __syncwarp();
     }
+    n_rel = __reduce_add_sync(0xffffffffu, (unsigned int)n_rel);
     if (lane == 0 && n_rel) atomicAdd(&counters[1], (u64)n_rel);
 }
 

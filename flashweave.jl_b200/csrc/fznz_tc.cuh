@@ -278,22 +278,27 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) fznz_candidates_kernel(NzTable t, i64 n_cand, const u64* __restrict__ keys,
                                                                      i64 n_obs_min, double alpha, int reliable_only,
                                                                      u64* counters, i64 cap, int* c_x, int* c_y, double* c_p, double* c_stat, int use_wm) {
-    extern __shared__ unsigned int cand_wm[];                           // WARPS x W words (fznz_warp_scratch_bytes)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned int* wm = use_wm ? cand_wm + (size_t)warp * t.W : nullptr;
+    extern __shared__ unsigned int cand_wm[];                           // WARPS x 4 x W words (fznz_warp_scratch_bytes)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3;
+    unsigned int* wm = use_wm ? cand_wm + (size_t)(warp * 4 + g) * t.W : nullptr;
     i64 n_rel = 0;
-    for (i64 i = (i64)blockIdx.x * WARPS + warp; i < n_cand; i += (i64)gridDim.x * WARPS) {
-        const u64 k = keys[i];
+    for (i64 i0 = ((i64)blockIdx.x * WARPS + warp) * 4; i0 < n_cand; i0 += (i64)gridDim.x * WARPS * 4) {   // four candidates per warp
+        const i64 i = i0 + g;
+        const bool valid = i < n_cand;
+        const u64 k = keys[valid ? i : i0];
         const i64 X = (i64)(((k >> 33) << 7) | ((k >> 6) & 127u)), Y = (i64)((((k >> 13) & 0xFFFFFu) << 6) | (k & 63u));
-        NzUni r = fznz_uni_warp(t, X, Y, n_obs_min, wm);
-        const bool rel = (r.suff || !reliable_only) && !isnan(r.pval);
-        n_rel += rel;
-        if (rel && r.pval < alpha && lane == 0) {
-            u64 pos = atomicAdd(&counters[2], 1ull);
-            if ((i64)pos < cap) { c_x[pos] = (int)X; c_y[pos] = (int)Y; c_p[pos] = r.pval; c_stat[pos] = r.stat; }
+        NzUni r = fznz_uni_g8(t, X, Y, n_obs_min, wm, valid);
+        const bool rel = valid && (r.suff || !reliable_only) && !isnan(r.pval);
+        if ((lane & 7) == 0) {
+            n_rel += rel;
+            if (rel && r.pval < alpha) {
+                u64 pos = atomicAdd(&counters[2], 1ull);
+                if ((i64)pos < cap) { c_x[pos] = (int)X; c_y[pos] = (int)Y; c_p[pos] = r.pval; c_stat[pos] = r.stat; }
+            }
         }
         __syncwarp();
     }
+    n_rel = __reduce_add_sync(0xffffffffu, (unsigned int)n_rel);
     if (lane == 0 && n_rel) atomicAdd(&counters[1], (u64)n_rel);
 }
 

@@ -601,7 +601,7 @@ static cudaError_t pairwise_fznz_collect(PairwiseScratch& S, fznztc::Planes& pla
             cub::DeviceRadixSort::SortKeys(nullptr, need, keys, keys2, (int)n_cand, 0, 33 + tb, st);
             PWCK(S.get(5, need, &tmp), "alloc");
             PWCK(cub::DeviceRadixSort::SortKeys(tmp, need, keys, keys2, (int)n_cand, 0, 33 + tb, st), "sort (candidates)"); (*n_launch) += 7;
-            const i64 blocks = std::min<i64>((n_cand + WARPS - 1) / WARPS, (i64)148 * 32);
+            const i64 blocks = std::min<i64>((n_cand + WARPS * 4 - 1) / (WARPS * 4), (i64)148 * 32);
             const size_t wmb = fznz_warp_scratch_bytes(WARPS, t.W);
             if (wmb > 48 * 1024) PWCK(cudaFuncSetAttribute(fznztc::fznz_candidates_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wmb), "cudaFuncSetAttribute(fznz_candidates_kernel)");
             fznztc::fznz_candidates_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, wmb, st>>>(t, n_cand, keys2, n_obs_min, alpha, reliable_only ? 1 : 0,
