@@ -270,32 +270,51 @@ __device__ void eval_subsets_fz_cached(const CorSlots r, const FzTab tab, int xs
         auto decode = [&](int q, int& a, int& b, int& c) {
             const unsigned int e = clx[q];
             a = e & 31; b = (e >> 5) & 31; c = e >> 10;
+        };
+        // reference (lexicographic) index: triples that start before a, pairs of the suffix that start before b, then c.  Needed only
+        // for a test that reaches the bookkeeping (or may belong to chunk 0): computed lazily
+        auto ref_index = [&](int a, int b, int c) {
             const int na = m - a - 1, pa = b - a - 1;
-            // reference (lexicographic) index: triples that start before a, pairs of the suffix that start before b, then c
             return c3 - ((na + 1) * na * (na - 1)) / 6 + pa * na - ((pa * (pa + 1)) >> 1) + (c - b - 1);
         };
         auto k3 = [&](int a, int b, int c, bool& special) {
             const int ab = a * FZ_TLD + b, ac = a * FZ_TLD + c, bc = b * FZ_TLD + c, ba = b * FZ_TLD + a, ca = c * FZ_TLD + a;
             return fz_k3_straight(S1[bc], S1[ac], S1[ab], S1[ca], S1[ba], S2[ac], S2[ab], S2[ca], S2[ba], S3[ab], S3[ba], A2[ab], special);
         };
+        // chunk 0 holds the reference indices [0, n0): a triple whose first position is >= a_lim0 starts at tri_off[a] >= n0
+        int a_lim0 = 0;
+        while (a_lim0 < m - 2 && (int)tri_off[a_lim0] < n0) ++a_lim0;
 #ifndef FW_HITON_INFLIGHT
 #define FW_HITON_INFLIGHT 2
 #endif
         constexpr int NF = FW_HITON_INFLIGHT;
         for (int q = tid; q < c3; q += NF * THREADS) {
-            int ia[NF], ib[NF], ic[NF], idx[NF]; bool has[NF], sp[NF]; double sv[NF];
+            int ia[NF], ib[NF], ic[NF]; bool has[NF], sp[NF]; double sv[NF];
+            // the smallest |stat| accepted so far in this scan (any thread): a larger significant |stat| needs no bookkeeping at all
+            const double skip_above = __longlong_as_double((i64)*reinterpret_cast<volatile u64*>(bound)) * (1.0 + 1e-8);
 #pragma unroll
             for (int u = 0; u < NF; ++u) {
                 has[u] = q + u * THREADS < c3;
-                idx[u] = decode(has[u] ? q + u * THREADS : q, ia[u], ib[u], ic[u]);
+                decode(has[u] ? q + u * THREADS : q, ia[u], ib[u], ic[u]);
                 sp[u] = false;
             }
 #pragma unroll
             for (int u = 0; u < NF; ++u) sv[u] = k3(ia[u], ib[u], ic[u], sp[u]);
+            bool slow = false;
 #pragma unroll
             for (int u = 0; u < NF; ++u) {
-                if (sp[u]) sv[u] = pcor_generic(r, xs, ys, acc[ia[u]], acc[ib[u]], acc[ic[u]], 3);
-                if (has[u] && idx[u] >= n0) consider(idx[u], sv[u]);
+                const double t = fabs(sv[u]);
+                slow |= has[u] && (sp[u] || ia[u] < a_lim0 || !(t >= fc.s_hi && t > skip_above));
+            }
+            if (slow) {
+#pragma unroll
+                for (int u = 0; u < NF; ++u) {
+                    if (!has[u]) continue;
+                    const int idx = ref_index(ia[u], ib[u], ic[u]);
+                    if (idx < n0) continue;                                     // already evaluated in chunk 0
+                    if (sp[u]) sv[u] = pcor_generic(r, xs, ys, acc[ia[u]], acc[ib[u]], acc[ic[u]], 3);
+                    consider(idx, sv[u]);
+                }
             }
         }
         for (int q = tid; q < c2; q += THREADS) {
