@@ -216,22 +216,22 @@ __device__ NzUni fznz_uni_g8(const NzTable& t, i64 X, i64 Y, i64 n_obs_min, unsi
     return r;
 }
 
-// ---- register-blocked Gram matrix of one job (nv <= 34 variables) ------------------------------------------------------------
+// ---- register-blocked Gram matrix of one job (nv <= 32 variables) ------------------------------------------------------------
 // All moments of cor_subset! in ONE pass over the table: with v = (x_0 .. x_{nv-1}, 1) the upper triangle of G = sum over the
-// view rows of v v^T holds every cross product, every sum of squares and every sum.  The rows are staged in tiles of
-// FZNZ_TROWS rows x nv variables (coalesced reads along each variable, converted to fp64 once and transposed into [row][33]
-// shared memory); a warp takes
-// every (THREADS/32)-th view row of the tile and each lane owns one B x B block of the upper triangle of G in fp64 registers
-// (B = 4; more than 32 blocks - 29 to 33 entries of v - take a second pass over the table), the next tile's global reads
-// are in flight while the current one is consumed, so a row costs 2B shared-memory reads and B*B DFMA per lane - the
-// pair-per-warp version re-read both columns from L2 for each of the nv(nv-1)/2 pairs.  Partial sums of the warps are added in
-// warp order (deterministic), then r_ab = (G_ab - S_a S_b / n) / sqrt((G_aa - S_a^2/n)(G_bb - S_b^2/n)) in fp64, rounded to
-// Float32 (cor_mat's eltype), NaN -> 0.  Same statistics as the two-pass form of Statistics.cor up to fp64 rounding.
-constexpr int FZNZ_TROWS = 128;
+// view rows of v v^T holds every cross product, every sum of squares and every sum.  Only the VIEW rows are staged (a FlashWeaveHE
+// view holds 20-45 % of the rows): a tile is the next FZNZ_CROWS view rows of each of the 8 row classes (class = row mod 8), found
+// by warp c walking the class words of the mask (fznz_uni_warp); the values are gathered, converted to fp64 once and stored as
+// [slot][33] in shared memory, the next tile's global reads are in flight while the current one is consumed.  Warp c consumes the
+// slots of class c in increasing row order and each lane owns one B x B block of the upper triangle of G in fp64 registers
+// (B = 4; more than 32 blocks - 29 to 33 entries of v - take a second pass), so a row costs 2B shared-memory reads and B*B DFMA
+// per lane.  Partial sums of the warps (= classes) are added in warp order: the canonical summation order of the header.  Then
+// r_ab = (G_ab - S_a S_b / n) / sqrt((G_aa - S_a^2/n)(G_bb - S_b^2/n)) in fp64, rounded to Float32 (cor_mat's eltype), NaN -> 0.
+constexpr int FZNZ_CROWS = 16;                          // view rows per class and tile
+constexpr int FZNZ_TROWS = 8 * FZNZ_CROWS;              // slots of a tile
 constexpr int FZNZ_TLD = 33;
 constexpr int FZNZ_GMAX = 36;                           // row stride of G (9 blocks of 4)
 constexpr int FZNZ_NVMAX = 32;                          // variables of a job on this path (+ the ones column = 33 = FZNZ_TLD)
-constexpr int FZNZ_GRAM_BYTES = (FZNZ_TROWS * FZNZ_TLD + 8) * 8 + FZNZ_GMAX * FZNZ_GMAX * 8 + 32;
+constexpr int FZNZ_GRAM_BYTES = (FZNZ_TROWS * FZNZ_TLD + 8) * 8 + FZNZ_GMAX * FZNZ_GMAX * 8 + 32 + 2 * (FZNZ_TROWS + 8) * 4;
 
 template <int THREADS>
 __device__ void fznz_gram_block(const float* __restrict__ data, i64 ldv, int n, int W, const i64* var, int nv, int rows,
@@ -246,20 +246,24 @@ __device__ void fznz_gram_block(const float* __restrict__ data, i64 ldv, int n, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* tile = reinterpret_cast<double*>(buf);                                       // [FZNZ_TROWS][FZNZ_TLD] (+ 8 of slack: blocks may over-read)
     double* G = tile + FZNZ_TROWS * FZNZ_TLD + 8;                                        // [ne][FZNZ_GMAX], upper triangle
+    int* trow = reinterpret_cast<int*>(G + FZNZ_GMAX * FZNZ_GMAX + 4);                   // [2][FZNZ_TROWS]: table row of each slot (double-buffered)
+    int* tcnt = trow + 2 * FZNZ_TROWS;                                                   // [2][8]: slots filled per class
     const int ne = nv + 1;                                                               // entries of v; v[nv] = 1
     const int g = (ne + B - 1) / B;                                                      // block grid of the upper triangle
     const int nblk = g * (g + 1) / 2;                                                    // <= 45: one or two passes of 32 blocks
     const int n_stage = nv * FZNZ_TROWS;
+    const int KW = (W + 7) >> 3;                                                         // class words
     auto block_of = [&](int q, int& bi, int& bj) { for (bi = 0; bi < g; ++bi) { const int len = g - bi; if (q < len) { bj = bi + q; return; } q -= len; } bi = bj = 0; };
-    auto next_tile = [&](int r0) {                                                       // first tile at or after r0 with a view row (uniform)
-        for (; r0 < n; r0 += FZNZ_TROWS) {
-            const int w0 = r0 >> 5;
-            unsigned int any = 0;
+    // class word kw of class `warp`: bit b <-> table row 256 kw + 8 b + warp (see fznz_uni_warp); warp-uniform
+    auto class_word = [&](int kw) {
+        unsigned int cw = 0u;
 #pragma unroll
-            for (int w = 0; w < FZNZ_TROWS / 32; ++w) any |= (w0 + w < W) ? mask[w0 + w] : 0u;
-            if (any) break;
+        for (int i = 0; i < 8; ++i) {
+            const int w = 8 * kw + i;
+            const unsigned int m = w < W ? mask[w] : 0u;
+            cw |= ((((m >> warp) & 0x01010101u) * 0x10204080u) >> 28) << (4 * i);
         }
-        return r0;
+        return cw;
     };
     for (int pass = 0; pass * 32 < nblk; ++pass) {
         const int q = lane + 32 * pass;
@@ -277,32 +281,54 @@ __device__ void fznz_gram_block(const float* __restrict__ data, i64 ldv, int n, 
 #pragma unroll 1
             for (int a = nv; a < FZNZ_TLD; ++a) tile[e * FZNZ_TLD + a] = (a == nv) ? 1.0 : 0.0;
         }
+        // cursor of this warp over the view rows of its class (warp-uniform registers)
+        int kw = 0; unsigned int cw = class_word(0);
+        auto fill = [&](int bsel) {                                                      // the next FZNZ_CROWS view rows of class `warp` -> trow[bsel]
+            int filled = 0;
+            while (filled < FZNZ_CROWS) {
+                if (!cw) { if (++kw >= KW) break; cw = class_word(kw); continue; }
+                const int cnt = __popc(cw);
+                const int take = cnt < FZNZ_CROWS - filled ? cnt : FZNZ_CROWS - filled;
+                if (lane < take) trow[bsel * FZNZ_TROWS + warp * FZNZ_CROWS + filled + lane] = kw * 256 + 8 * (int)__fns(cw, 0, lane + 1) + warp;
+                cw = take == cnt ? 0u : (cw & ~((1u << __fns(cw, 0, take + 1)) - 1u));   // drop the `take` lowest set bits
+                filled += take;
+            }
+            if (lane == 0) tcnt[bsel * 8 + warp] = filled;
+        };
         float pf[PF];
-        auto fetch = [&](int r0) {
+        auto fetch = [&](int bsel) {
 #pragma unroll
             for (int k = 0; k < PF; ++k) {
                 const int e = tid + k * THREADS;
-                const int a = e / FZNZ_TROWS, row = r0 + (e % FZNZ_TROWS);
-                pf[k] = (e < n_stage && row < n) ? __ldg(data + var[a] * ldv + row) : 0.0f;
+                const int a = e / FZNZ_TROWS, slot = e % FZNZ_TROWS;
+                const bool ok = e < n_stage && (slot % FZNZ_CROWS) < tcnt[bsel * 8 + slot / FZNZ_CROWS];
+                pf[k] = ok ? __ldg(data + var[a] * ldv + trow[bsel * FZNZ_TROWS + slot]) : 0.0f;
             }
         };
-        int r0 = next_tile(0);
-        if (r0 < n) fetch(r0);
-        while (r0 < n) {
+        auto any_rows = [&](int bsel) { int t_ = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) t_ |= tcnt[bsel * 8 + c];
+            return t_ != 0; };
+        int cur = 0;
+        fill(0);
+        __syncthreads();                                                                 // trow[0] / tcnt[0] visible
+        bool have = any_rows(0);
+        if (have) fetch(0);
+        while (have) {
             __syncthreads();                                                             // previous tile fully consumed
 #pragma unroll
             for (int k = 0; k < PF; ++k) {
                 const int e = tid + k * THREADS;
                 if (e < n_stage) tile[(e % FZNZ_TROWS) * FZNZ_TLD + e / FZNZ_TROWS] = __dsub_rn((double)pf[k], piv[e / FZNZ_TROWS]);
             }
+            fill(cur ^ 1);                                                               // rows of the next tile
             __syncthreads();
-            const int r1 = next_tile(r0 + FZNZ_TROWS);
-            if (r1 < n) fetch(r1);                                                       // in flight while this tile is consumed
-            for (int r = warp; r < FZNZ_TROWS; r += NW) {
-                const int row = r0 + r;
-                if (row >= n || !((mask[row >> 5] >> (row & 31)) & 1u)) continue;        // warp-uniform
-                if (live) {
-                    const double* v = tile + r * FZNZ_TLD;
+            const bool have_next = any_rows(cur ^ 1);
+            if (have_next) fetch(cur ^ 1);                                               // in flight while this tile is consumed
+            const int mine = tcnt[cur * 8 + warp];
+            if (live) {
+                for (int r = 0; r < mine; ++r) {
+                    const double* v = tile + (warp * FZNZ_CROWS + r) * FZNZ_TLD;
                     double vi[B], vj[B];
 #pragma unroll
                     for (int i = 0; i < B; ++i) { vi[i] = v[i0 + i]; vj[i] = v[j0 + i]; }
@@ -313,9 +339,9 @@ __device__ void fznz_gram_block(const float* __restrict__ data, i64 ldv, int n, 
                     }
                 }
             }
-            r0 = r1;
+            cur ^= 1; have = have_next;
         }
-        // cross-warp reduction in a fixed order (deterministic): partials through the tile buffer
+    // cross-warp reduction in a fixed order (deterministic): partials through the tile buffer
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < B; ++i) {
