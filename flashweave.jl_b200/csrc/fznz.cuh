@@ -226,7 +226,10 @@ __device__ NzUni fznz_uni_g8(const NzTable& t, i64 X, i64 Y, i64 n_obs_min, unsi
 // (B = 4; more than 32 blocks - 29 to 33 entries of v - take a second pass), so a row costs 2B shared-memory reads and B*B DFMA
 // per lane.  Partial sums of the warps (= classes) are added in warp order: the canonical summation order of the header.  Then
 // r_ab = (G_ab - S_a S_b / n) / sqrt((G_aa - S_a^2/n)(G_bb - S_b^2/n)) in fp64, rounded to Float32 (cor_mat's eltype), NaN -> 0.
-constexpr int FZNZ_CROWS = 16;                          // view rows per class and tile
+#ifndef FW_FZNZ_CROWS
+#define FW_FZNZ_CROWS 16
+#endif
+constexpr int FZNZ_CROWS = FW_FZNZ_CROWS;                // view rows per class and tile
 constexpr int FZNZ_TROWS = 8 * FZNZ_CROWS;              // slots of a tile
 constexpr int FZNZ_TLD = 33;
 constexpr int FZNZ_GMAX = 36;                           // row stride of G (9 blocks of 4)
