@@ -17,7 +17,8 @@ interleaved.jl hands targets to workers): scaling = "strong".  No collective in 
           fz, N = 1: column chunks of the upload hidden behind the GEMM (fw_upload_cor_f32).  fz, N > 1: the library's group path (include/fwgpu.h "multi-GPU"): every rank uploads 1/N of
           the columns, the standardising kernel reads the peers' slices over NVLink, cor_mat stays row-sharded and is read
           through peer mappings; no NCCL call in the data path (torch.distributed only sets the group up and reduces the
-          timings).  Other kinds, N > 1: table replicated (every rank uploads it over its own PCIe link), pairwise stage split by X with one
+          timings).  Other kinds, N > 1: every rank needs the whole table - fz_nz: each rank uploads 1/N of the columns and the slices are
+          broadcast once with NCCL over NVLink (mi: the 80 MB table is uploaded by every rank) -, pairwise stage split by X with one
           NCCL all-gather of the raw-significant records for the global BH step, targets sharded.
   parity_sample : the oracle re-runs a sample of the targets on the engine's own inputs and must reproduce the engine's PC sets,
           statistics and test counts; a mismatch fails the run.
@@ -327,6 +328,13 @@ def main_ours(a, rank, world, local_rank):
         c0, c1 = par.table_slice(p, rank, world)
         slice_host = torch.empty((c1 - c0, n), dtype=t_dtype, pin_memory=True)
         slice_host.copy_(host_x[c0:c1])
+    gather_tab = dist is not None and kind == "fz_nz"        # float table needed whole on every rank: upload 1/N each, NCCL broadcasts over NVLink
+    dev_table = None
+    if gather_tab:
+        c0, c1 = par.table_slice(p, rank, world)
+        slice_host = torch.empty((c1 - c0, n), dtype=t_dtype, pin_memory=True)
+        slice_host.copy_(host_x[c0:c1])
+        dev_table = torch.empty((p, n), dtype=t_dtype, device=torch.device("cuda", local_rank))
     ext = torch.cuda.ExternalStream(eng.stream)
 
     phase_wall = {"table_and_cor_ms": [], "pairwise_ms": [], "hiton_ms": [], "upload_ms": []}
@@ -347,6 +355,9 @@ def main_ours(a, rank, world, local_rank):
         elif kind == "mi":
             eng._ck(eng.L.fw_set_data_i32(eng.h, fw.C.c_void_p(host_x.data_ptr()), n, p, n))
             eng.kind, eng.n, eng.p = kind, n, p
+        elif gather_tab:
+            par.upload_and_gather_table(dist, dev_table, slice_host, rank, world)
+            eng.adopt_data_device(dev_table.data_ptr(), n, p, kind)
         else:
             eng.set_data_ptr(host_x.data_ptr(), n, p, kind)
         t1 = time.perf_counter()
@@ -392,6 +403,8 @@ def main_ours(a, rank, world, local_rank):
     tests_rank = int(res.num_tests.sum())
     if kind == "fz":
         h2d = p * n * 4 // world if group else p * n * 4
+    elif gather_tab:
+        h2d = slice_host.numel() * 4
     else:
         h2d = p * n * 4
     h2d += len(shard) * 8
@@ -513,7 +526,7 @@ def main_ours(a, rank, world, local_rank):
                 "phases_wall_ms_rank0": {k: float(np.mean(v)) for k, v in phase_wall.items() if v},
                 "pairwise_tests_per_s": p * (p - 1) / 2 / (float(np.mean(phase_wall["pairwise_ms"])) * 1e-3),
                 "multi_gpu_path": ("library group (CUDA IPC peer mappings over NVLink, row-sharded cor_mat, no NCCL in the data path)" if group else
-                                   ("replicated table, pairwise stage split by X (one NCCL all-gather of the raw-significant records), sharded targets" if world > 1 else "single GPU"))},
+                                   (("table uploaded 1/N per rank + NCCL broadcasts over NVLink, " if gather_tab else "replicated table upload, ") + "pairwise stage split by X (one NCCL all-gather of the raw-significant records), sharded targets" if world > 1 else "single GPU"))},
         "gpu_launches": int(sm[4].item()),
         "roofline": roofline,
         "clocks": clocks,

@@ -77,6 +77,21 @@ def table_slice(p, rank, world):
     return p * rank // world, p * (rank + 1) // world
 
 
+def upload_and_gather_table(dist, dev_table, host_slice, rank, world):
+    """The table once over NVLink instead of N times over PCIe (table-based kinds: every rank needs all of it): rank r copies its
+    columns [p*r/N, p*(r+1)/N) from (pinned) host memory into its place in `dev_table` ([p, n] CUDA tensor), then every slice is
+    broadcast from its owner (NCCL; slices may differ in length, which all_gather_into_tensor does not allow).  Returns after the
+    table is complete on this rank."""
+    import torch
+    p = dev_table.shape[0]
+    c0, c1 = table_slice(p, rank, world)
+    dev_table[c0:c1].copy_(host_slice, non_blocking=True)
+    for r in range(world):
+        a, b = table_slice(p, r, world)
+        dist.broadcast(dev_table[a:b], src=r)
+    torch.cuda.synchronize(dev_table.device)
+
+
 # ---- pairwise stage of the table-based kinds (mi, mi_nz, fz_nz) split over the ranks ---------------------------------------------
 def pack_records(rec):
     """the raw-significant records of one rank as ONE float64 array [4, n] (x, y, p, stat; indices are exact in float64)"""
