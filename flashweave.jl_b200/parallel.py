@@ -89,7 +89,8 @@ def upload_and_gather_table(dist, dev_table, host_slice, rank, world):
     for r in range(world):
         a, b = table_slice(p, r, world)
         dist.broadcast(dev_table[a:b], src=r)
-    torch.cuda.synchronize(dev_table.device)
+    if dev_table.is_cuda:
+        torch.cuda.synchronize(dev_table.device)
 
 
 # ---- pairwise stage of the table-based kinds (mi, mi_nz, fz_nz) split over the ranks ---------------------------------------------

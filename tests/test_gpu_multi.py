@@ -158,7 +158,15 @@ def _worker_nz(rank, world, port, q):
         x = synth.hetero(2600, 500, B=12, seed=21)[0] if kind == "fz_nz" else synth.binarize(synth.clique(2600, 400, B=10, seed=22))
         nom = 20 if kind == "fz_nz" else fw.auto_n_obs_min("mi", 3, 5, max_level=2)
         eng = fw.Engine(rank)
-        eng.set_data_colmajor(x, kind)
+        if kind == "fz_nz":
+            # the table once over NVLink: this rank uploads its column slice, the slices are broadcast from their owners
+            c0, c1 = par.table_slice(x.shape[0], rank, world)
+            dev = torch.empty(x.shape, dtype=torch.float32, device=torch.device("cuda", rank))
+            par.upload_and_gather_table(dist, dev, torch.from_numpy(np.ascontiguousarray(x[c0:c1])), rank, world)
+            ok &= bool((dev.cpu().numpy() == x).all())
+            eng.adopt_data_device(dev.data_ptr(), x.shape[1], x.shape[0], kind)
+        else:
+            eng.set_data_colmajor(x, kind)
         uni = par.sharded_pairwise(dist, eng, kind, alpha=0.01, n_obs_min=nom, device=torch.device("cuda", rank), want_host=True)
         order = fw.target_order(uni)
         res = eng.si_HITON_PC(par.shard_targets(order, rank, world), max_k=3, alpha=0.01, n_obs_min=nom, want_tpc=False, kind=kind)

@@ -129,3 +129,34 @@ def test_allgather_records_ragged():
             for k in ("x", "y", "p", "stat"):
                 assert got[r][k].dtype == sent[r][k].dtype and (got[r][k] == sent[r][k]).all()
             assert got[r]["n_reliable"] == sent[r]["n_reliable"]
+
+
+def _table_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    par = fwload.load_sub("parallel")
+    p, n = 37, 11                                           # 37 columns over 3 ranks: ragged slices
+    full = torch.arange(p * n, dtype=torch.float32).reshape(p, n)
+    c0, c1 = par.table_slice(p, rank, world)
+    dev = torch.full((p, n), -1.0)
+    par.upload_and_gather_table(dist, dev, full[c0:c1].clone(), rank, world)
+    q.put((rank, bool((dev == full).all())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_upload_and_gather_table_ragged():
+    """every rank contributes its column slice, every rank ends up with the whole table (parallel.upload_and_gather_table)"""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_table_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert sorted(r for r, _ in out) == [0, 1, 2] and all(ok for _, ok in out)
