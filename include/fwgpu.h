@@ -223,7 +223,8 @@ int32_t fw_pairwise_copy(fw_ctx* ctx, int64_t* offsets /* p+1 */, int64_t* nbr, 
  * fw_pairwise_merge with the concatenation and m_tests = sum of n_reliable (or p (p - 1) / 2): condensed-index order,
  * Benjamini-Hochberg and the neighbour lists exactly as fw_pairwise would produce them on one GPU.  The record arrays of
  * fw_pairwise_partial_copy / fw_pairwise_merge may be host or device memory (unified addressing): with NCCL the records never
- * leave the GPUs. */
+ * leave the GPUs.  Host records are validated (0 <= x < y < p, FW_ERR_INVALID otherwise); device records are taken as the ranks'
+ * fw_pairwise_partial produced them. */
 int32_t fw_pairwise_partial(fw_ctx* ctx, int32_t kind, double alpha, int64_t hps, int64_t n_obs_min, int32_t correct_reliable_only,
                             int32_t rank, int32_t world, int64_t* n_raw, int64_t* n_reliable);
 int32_t fw_pairwise_partial_copy(fw_ctx* ctx, int32_t* x, int32_t* y, double* pval, double* stat);
