@@ -12,8 +12,9 @@
 //
 // Roles per CTA (320 threads): warp 0 = TMA producer (own A rows, own half of B; the transaction bytes of BOTH CTAs are counted on the
 // leader's `full` barrier, cp.async.bulk.tensor ... .cta_group::2), warp 1 = TMEM allocation + (leader CTA only) the MMA-issuing
-// thread, warps 2-9 = epilogue (lane quarter = warp % 4, column half = (warp - 2) / 4): drain, clamp, unit diagonal, direct tile
-// staged through the idle pipeline buffers for 128-byte row stores, mirrored tile straight from registers.
+// thread, warps 2-9 = epilogue (lane quarter = warp % 4, column half = (warp - 2) / 4): chunk drains, clamp, unit diagonal, then the
+// tile is staged in the idle pipeline buffers and both the direct and the mirrored tile leave in 512-byte runs from compact loops
+// (mirror_block; the raw candidates of the univariate Fisher-z stage are collected there when armed).
 #pragma once
 #include "cor_tc.cuh"
 
